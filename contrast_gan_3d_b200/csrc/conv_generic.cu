@@ -1,0 +1,406 @@
+// Generic CUDA-core convolution kernels (any channel count, k in {1..7}, stride 1/2).
+// fp32 accumulation; storage type T = float or bf16; channels-last [B][X][Y][Z][C].
+// These are the always-available correct path and the on-device checker for the tcgen05
+// kernels in conv_tc.cu.  Replaces aten::convolution / convolution_backward
+// (reference model/blocks.py:29-38,52).
+#include "common.cuh"
+#include "conv_internal.cuh"
+
+namespace cg {
+
+// ------------------------------------------------------------------ weight packing
+template <typename T>
+__global__ void pack_weights_kernel(const float *__restrict__ w, T *__restrict__ p, int Cs, int Cb, int taps) {
+  int64_t total = (int64_t)taps * Cb * Cs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cs = (int)(i % Cs);
+    int cb = (int)((i / Cs) % Cb);
+    int t = (int)(i / ((int64_t)Cs * Cb));
+    p[i] = from_f<T>(w[((int64_t)cs * Cb + cb) * taps + t]);
+  }
+}
+
+// ------------------------------------------------------------------ gather (fprop)
+// one thread: VB consecutive z outputs x COB output channels
+template <typename T, int K, int S, int COB, int VB>
+__global__ void __launch_bounds__(128)
+gather_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict__ wp,
+              const float *__restrict__ bias, T *__restrict__ small) {
+  const int ncob = g.Cs / COB;
+  const int nzg = (g.Zs + VB - 1) / VB;
+  const int64_t total = (int64_t)g.B * g.Xs * g.Ys * nzg * ncob;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cob = (int)(idx % ncob); idx /= ncob;
+  const int zg = (int)(idx % nzg); idx /= nzg;
+  const int oy = (int)(idx % g.Ys); idx /= g.Ys;
+  const int ox = (int)(idx % g.Xs);
+  const int b = (int)(idx / g.Xs);
+  const int oz0 = zg * VB, co0 = cob * COB;
+  constexpr int NZ = (VB - 1) * S + K;
+  float acc[VB][COB];
+#pragma unroll
+  for (int v = 0; v < VB; ++v)
+#pragma unroll
+    for (int c = 0; c < COB; ++c) acc[v][c] = bias ? bias[co0 + c] : 0.f;
+  const int iz0 = oz0 * S - g.pad;
+  for (int kx = 0; kx < K; ++kx) {
+    const int ix = ox * S - g.pad + kx;
+    if ((unsigned)ix >= (unsigned)g.Xb) continue;
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * S - g.pad + ky;
+      if ((unsigned)iy >= (unsigned)g.Yb) continue;
+      const T *xrow = big + (((int64_t)b * g.Xb + ix) * g.Yb + iy) * (int64_t)g.Zb * g.Cb;
+      const T *wrow = wp + (int64_t)((kx * K + ky) * K) * g.Cb * g.Cs + co0;
+      for (int ci = 0; ci < g.Cb; ++ci) {
+        float xs[NZ];
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) {
+          const int iz = iz0 + j;
+          xs[j] = ((unsigned)iz < (unsigned)g.Zb) ? to_f(xrow[(int64_t)iz * g.Cb + ci]) : 0.f;
+        }
+#pragma unroll
+        for (int kz = 0; kz < K; ++kz) {
+          float w[COB];
+          const T *wq = wrow + (int64_t)(kz * g.Cb + ci) * g.Cs;
+#pragma unroll
+          for (int c = 0; c < COB; ++c) w[c] = to_f(wq[c]);
+#pragma unroll
+          for (int v = 0; v < VB; ++v)
+#pragma unroll
+            for (int c = 0; c < COB; ++c) acc[v][c] = fmaf(xs[v * S + kz], w[c], acc[v][c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VB; ++v) {
+    const int oz = oz0 + v;
+    if (oz < g.Zs) {
+      T *o = small + ((((int64_t)b * g.Xs + ox) * g.Ys + oy) * g.Zs + oz) * g.Cs + co0;
+#pragma unroll
+      for (int c = 0; c < COB; ++c) o[c] = from_f<T>(acc[v][c]);
+    }
+  }
+}
+
+template <typename T, int K, int S>
+static int launch_gather(const cgan3d_conv_geom &g, const T *big, const T *wp, const float *bias, T *small,
+                         cudaStream_t st) {
+  constexpr int VB = 4;
+  const int nzg = (g.Zs + VB - 1) / VB;
+  auto go = [&](auto cob_tag) {
+    constexpr int COB = decltype(cob_tag)::value;
+    int64_t total = (int64_t)g.B * g.Xs * g.Ys * nzg * (g.Cs / COB);
+    int blocks = (int)((total + 127) / 128);
+    gather_kernel<T, K, S, COB, VB><<<blocks, 128, 0, st>>>(g, big, wp, bias, small);
+  };
+  if (g.Cs % 8 == 0) go(std::integral_constant<int, 8>{});
+  else if (g.Cs % 4 == 0) go(std::integral_constant<int, 4>{});
+  else if (g.Cs % 2 == 0) go(std::integral_constant<int, 2>{});
+  else go(std::integral_constant<int, 1>{});
+  CG_LAUNCH_CHECK("conv_gather(generic)");
+  return 0;
+}
+
+// ------------------------------------------------------------------ scatter (dgrad / convT fprop)
+// one thread: one big-side voxel x CIB channels
+template <typename T, int K, int S, int CIB>
+__global__ void __launch_bounds__(128)
+scatter_kernel(cgan3d_conv_geom g, const T *__restrict__ small, const T *__restrict__ wp,
+               const float *__restrict__ bias, T *__restrict__ big) {
+  const int ncib = g.Cb / CIB;
+  const int64_t total = (int64_t)g.B * g.Xb * g.Yb * g.Zb * ncib;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cib = (int)(idx % ncib); idx /= ncib;
+  const int iz = (int)(idx % g.Zb); idx /= g.Zb;
+  const int iy = (int)(idx % g.Yb); idx /= g.Yb;
+  const int ix = (int)(idx % g.Xb);
+  const int b = (int)(idx / g.Xb);
+  const int ci0 = cib * CIB;
+  float acc[CIB];
+#pragma unroll
+  for (int c = 0; c < CIB; ++c) acc[c] = bias ? bias[ci0 + c] : 0.f;
+  for (int kx = 0; kx < K; ++kx) {
+    const int tx = ix + g.pad - kx;
+    if (tx < 0 || (tx % S) != 0) continue;
+    const int ox = tx / S;
+    if (ox >= g.Xs) continue;
+    for (int ky = 0; ky < K; ++ky) {
+      const int ty = iy + g.pad - ky;
+      if (ty < 0 || (ty % S) != 0) continue;
+      const int oy = ty / S;
+      if (oy >= g.Ys) continue;
+      for (int kz = 0; kz < K; ++kz) {
+        const int tz = iz + g.pad - kz;
+        if (tz < 0 || (tz % S) != 0) continue;
+        const int oz = tz / S;
+        if (oz >= g.Zs) continue;
+        const T *yrow = small + ((((int64_t)b * g.Xs + ox) * g.Ys + oy) * g.Zs + oz) * (int64_t)g.Cs;
+        const T *wrow = wp + ((int64_t)((kx * K + ky) * K + kz) * g.Cb + ci0) * g.Cs;
+        for (int co = 0; co < g.Cs; ++co) {
+          const float yv = to_f(yrow[co]);
+#pragma unroll
+          for (int c = 0; c < CIB; ++c) acc[c] = fmaf(yv, to_f(wrow[(int64_t)c * g.Cs + co]), acc[c]);
+        }
+      }
+    }
+  }
+  T *o = big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * (int64_t)g.Cb + ci0;
+#pragma unroll
+  for (int c = 0; c < CIB; ++c) o[c] = from_f<T>(acc[c]);
+}
+
+template <typename T, int K, int S>
+static int launch_scatter(const cgan3d_conv_geom &g, const T *small, const T *wp, const float *bias, T *big,
+                          cudaStream_t st) {
+  auto go = [&](auto tag) {
+    constexpr int CIB = decltype(tag)::value;
+    int64_t total = (int64_t)g.B * g.Xb * g.Yb * g.Zb * (g.Cb / CIB);
+    int blocks = (int)((total + 127) / 128);
+    scatter_kernel<T, K, S, CIB><<<blocks, 128, 0, st>>>(g, small, wp, bias, big);
+  };
+  if (g.Cb % 4 == 0) go(std::integral_constant<int, 4>{});
+  else if (g.Cb % 2 == 0) go(std::integral_constant<int, 2>{});
+  else go(std::integral_constant<int, 1>{});
+  CG_LAUNCH_CHECK("conv_scatter(generic)");
+  return 0;
+}
+
+// ------------------------------------------------------------------ wgrad
+// grid (taps, chunks); block 256 threads = lanes x (ncb x ncs) output sub-tiles of 4x4 (or 1-wide)
+template <typename T, int K, int S, int CBV, int CSV>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict__ small, float *__restrict__ dw,
+             int64_t vox_per_chunk, int cb_base, int cs_base, int ncb, int ncs) {
+  extern __shared__ float red[];  // [ncb*CBV][ncs*CSV]
+  const int tap = blockIdx.x;
+  const int kz = tap % K, ky = (tap / K) % K, kx = tap / (K * K);
+  const int per_lane = ncb * ncs;
+  const int lanes = blockDim.x / per_lane;
+  const int lane = threadIdx.x / per_lane;
+  const int r = threadIdx.x % per_lane;
+  const int tcb = r / ncs, tcs = r % ncs;
+  const int cb0 = cb_base + tcb * CBV, cs0 = cs_base + tcs * CSV;
+  const int tile_elems = ncb * CBV * ncs * CSV;
+  for (int i = threadIdx.x; i < tile_elems; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float acc[CBV][CSV];
+#pragma unroll
+  for (int a = 0; a < CBV; ++a)
+#pragma unroll
+    for (int c = 0; c < CSV; ++c) acc[a][c] = 0.f;
+  const int64_t n_vox = (int64_t)g.B * g.Xs * g.Ys * g.Zs;
+  const int64_t v0 = blockIdx.y * vox_per_chunk;
+  const int64_t v1 = min(n_vox, v0 + vox_per_chunk);
+  if (lane < lanes) {
+    for (int64_t v = v0 + lane; v < v1; v += lanes) {
+      int64_t t = v;
+      const int oz = (int)(t % g.Zs); t /= g.Zs;
+      const int oy = (int)(t % g.Ys); t /= g.Ys;
+      const int ox = (int)(t % g.Xs);
+      const int b = (int)(t / g.Xs);
+      const int ix = ox * S - g.pad + kx, iy = oy * S - g.pad + ky, iz = oz * S - g.pad + kz;
+      if ((unsigned)ix >= (unsigned)g.Xb || (unsigned)iy >= (unsigned)g.Yb || (unsigned)iz >= (unsigned)g.Zb) continue;
+      const T *xr = big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * (int64_t)g.Cb + cb0;
+      const T *yr = small + v * (int64_t)g.Cs + cs0;
+      float xv[CBV], yv[CSV];
+#pragma unroll
+      for (int a = 0; a < CBV; ++a) xv[a] = to_f(xr[a]);
+#pragma unroll
+      for (int c = 0; c < CSV; ++c) yv[c] = to_f(yr[c]);
+#pragma unroll
+      for (int a = 0; a < CBV; ++a)
+#pragma unroll
+        for (int c = 0; c < CSV; ++c) acc[a][c] = fmaf(xv[a], yv[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < CBV; ++a)
+#pragma unroll
+      for (int c = 0; c < CSV; ++c)
+        atomicAdd(&red[(tcb * CBV + a) * (ncs * CSV) + tcs * CSV + c], acc[a][c]);
+  }
+  __syncthreads();
+  const int taps = K * K * K;
+  for (int i = threadIdx.x; i < tile_elems; i += blockDim.x) {
+    const int a = i / (ncs * CSV), c = i % (ncs * CSV);
+    atomicAdd(&dw[((int64_t)(cs_base + c) * g.Cb + (cb_base + a)) * taps + tap], red[i]);
+  }
+}
+
+template <typename T, int K, int S>
+static int launch_wgrad(const cgan3d_conv_geom &g, const T *big, const T *small, float *dw, float beta,
+                        cudaStream_t st) {
+  const int taps = K * K * K;
+  const int64_t n_w = (int64_t)g.Cs * g.Cb * taps;
+  if (beta == 0.f) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, n_w * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad memset");
+  }
+  const int64_t n_vox = (int64_t)g.B * g.Xs * g.Ys * g.Zs;
+  int chunks = (int)mn<int64_t>(mx<int64_t>(1, (int64_t)num_sms() * 8 / taps), mx<int64_t>(1, n_vox / 64));
+  chunks = min(chunks, 65535);
+  const int64_t vpc = (n_vox + chunks - 1) / chunks;
+  auto go = [&](auto tcb_tag, auto tcs_tag) {
+    constexpr int CBV = decltype(tcb_tag)::value;
+    constexpr int CSV = decltype(tcs_tag)::value;
+    // tile the (Cb, Cs) plane so that one voxel lane needs at most 16 x 16 threads
+    constexpr int TB = 16 * CBV, TS = 16 * CSV;
+    for (int cb_base = 0; cb_base < g.Cb; cb_base += TB)
+      for (int cs_base = 0; cs_base < g.Cs; cs_base += TS) {
+        const int ncb = min(TB, g.Cb - cb_base) / CBV, ncs = min(TS, g.Cs - cs_base) / CSV;
+        const size_t smem = (size_t)ncb * CBV * ncs * CSV * sizeof(float);
+        wgrad_kernel<T, K, S, CBV, CSV><<<dim3(taps, chunks), 256, smem, st>>>(g, big, small, dw, vpc, cb_base,
+                                                                               cs_base, ncb, ncs);
+      }
+  };
+  const bool b4 = g.Cb % 4 == 0, s4 = g.Cs % 4 == 0;
+  if (b4 && s4) go(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
+  else if (b4) go(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+  else if (s4) go(std::integral_constant<int, 1>{}, std::integral_constant<int, 4>{});
+  else go(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+  CG_LAUNCH_CHECK("conv_wgrad(generic)");
+  return 0;
+}
+
+// ------------------------------------------------------------------ dispatch on (k, stride, dtype)
+#define CG_KS_DISPATCH(FN, ...)                                                       \
+  do {                                                                                \
+    const int ks = g.k * 10 + g.stride;                                               \
+    switch (ks) {                                                                     \
+      case 11: return FN<T, 1, 1>(__VA_ARGS__);                                       \
+      case 31: return FN<T, 3, 1>(__VA_ARGS__);                                       \
+      case 32: return FN<T, 3, 2>(__VA_ARGS__);                                       \
+      case 41: return FN<T, 4, 1>(__VA_ARGS__);                                       \
+      case 42: return FN<T, 4, 2>(__VA_ARGS__);                                       \
+      case 51: return FN<T, 5, 1>(__VA_ARGS__);                                       \
+      case 71: return FN<T, 7, 1>(__VA_ARGS__);                                       \
+      default: return fail(CGAN3D_E_UNSUPPORTED, "generic conv: k=%d stride=%d not built", g.k, g.stride); \
+    }                                                                                 \
+  } while (0)
+
+template <typename T>
+static int gather_t(const cgan3d_conv_geom &g, const void *big, const void *wp, const float *bias, void *small,
+                    cudaStream_t st) {
+  CG_KS_DISPATCH(launch_gather, g, (const T *)big, (const T *)wp, bias, (T *)small, st);
+}
+template <typename T>
+static int scatter_t(const cgan3d_conv_geom &g, const void *small, const void *wp, const float *bias, void *big,
+                     cudaStream_t st) {
+  CG_KS_DISPATCH(launch_scatter, g, (const T *)small, (const T *)wp, bias, (T *)big, st);
+}
+template <typename T>
+static int wgrad_t(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta,
+                   cudaStream_t st) {
+  CG_KS_DISPATCH(launch_wgrad, g, (const T *)big, (const T *)small, dw, beta, st);
+}
+
+int generic_gather(const cgan3d_conv_geom &g, int dtype, const void *big, const void *wp, const float *bias,
+                   void *small, cudaStream_t st) {
+  return dtype == CGAN3D_F32 ? gather_t<float>(g, big, wp, bias, small, st)
+                             : gather_t<__nv_bfloat16>(g, big, wp, bias, small, st);
+}
+int generic_scatter(const cgan3d_conv_geom &g, int dtype, const void *small, const void *wp, const float *bias,
+                    void *big, cudaStream_t st) {
+  return dtype == CGAN3D_F32 ? scatter_t<float>(g, small, wp, bias, big, st)
+                             : scatter_t<__nv_bfloat16>(g, small, wp, bias, big, st);
+}
+int generic_wgrad(const cgan3d_conv_geom &g, int dtype, const void *big, const void *small, float *dw, float beta,
+                  cudaStream_t st) {
+  return dtype == CGAN3D_F32 ? wgrad_t<float>(g, big, small, dw, beta, st)
+                             : wgrad_t<__nv_bfloat16>(g, big, small, dw, beta, st);
+}
+
+int pack_weights(const float *w, void *packed, int dtype, int Cs, int Cb, int k, cudaStream_t st) {
+  const int taps = k * k * k;
+  const int64_t total = (int64_t)taps * Cb * Cs;
+  const int blocks = (int)mn<int64_t>((total + 255) / 256, 4096);
+  if (dtype == CGAN3D_F32) pack_weights_kernel<float><<<blocks, 256, 0, st>>>(w, (float *)packed, Cs, Cb, taps);
+  else pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16 *)packed, Cs, Cb, taps);
+  CG_LAUNCH_CHECK("pack_weights");
+  return 0;
+}
+
+// ------------------------------------------------------------------ reflect padding
+__device__ __forceinline__ int reflect_idx(int j, int n) {  // j in [-p, n+p), p < n
+  if (j < 0) j = -j;
+  if (j >= n) j = 2 * (n - 1) - j;
+  return j;
+}
+
+template <typename T>
+__global__ void reflect_pad_kernel(const T *__restrict__ in, T *__restrict__ out, int B, int X, int Y, int Z, int C,
+                                   int p) {
+  const int Xp = X + 2 * p, Yp = Y + 2 * p, Zp = Z + 2 * p;
+  const int64_t total = (int64_t)B * Xp * Yp * Zp * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int c = (int)(t % C); t /= C;
+    const int z = (int)(t % Zp); t /= Zp;
+    const int y = (int)(t % Yp); t /= Yp;
+    const int x = (int)(t % Xp);
+    const int b = (int)(t / Xp);
+    const int sx = reflect_idx(x - p, X), sy = reflect_idx(y - p, Y), sz = reflect_idx(z - p, Z);
+    out[i] = in[((((int64_t)b * X + sx) * Y + sy) * Z + sz) * C + c];
+  }
+}
+
+// sources in padded coordinates that mirror onto interior index i (at most 3 per axis)
+__device__ __forceinline__ int reflect_sources(int i, int n, int p, int src[3]) {
+  int cnt = 0;
+  src[cnt++] = i + p;
+  if (i >= 1 && i <= p) src[cnt++] = p - i;
+  if (i <= n - 2 && i >= n - 1 - p) src[cnt++] = p + 2 * (n - 1) - i;
+  return cnt;
+}
+
+template <typename T>
+__global__ void reflect_pad_bwd_kernel(const T *__restrict__ gp, T *__restrict__ gi, int B, int X, int Y, int Z,
+                                       int C, int p) {
+  const int Yp = Y + 2 * p, Zp = Z + 2 * p, Xp = X + 2 * p;
+  const int64_t total = (int64_t)B * X * Y * Z * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int c = (int)(t % C); t /= C;
+    const int z = (int)(t % Z); t /= Z;
+    const int y = (int)(t % Y); t /= Y;
+    const int x = (int)(t % X);
+    const int b = (int)(t / X);
+    int sx[3], sy[3], sz[3];
+    const int nx = reflect_sources(x, X, p, sx), ny = reflect_sources(y, Y, p, sy), nz = reflect_sources(z, Z, p, sz);
+    float acc = 0.f;
+    for (int a = 0; a < nx; ++a)
+      for (int bb = 0; bb < ny; ++bb)
+        for (int cc = 0; cc < nz; ++cc)
+          acc += to_f(gp[((((int64_t)b * Xp + sx[a]) * Yp + sy[bb]) * Zp + sz[cc]) * C + c]);
+    gi[i] = from_f<T>(acc);
+  }
+}
+
+int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z, int C, int pad, cudaStream_t st) {
+  const int64_t total = (int64_t)B * (X + 2 * pad) * (Y + 2 * pad) * (Z + 2 * pad) * C;
+  const int blocks = (int)mn<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  if (dtype == CGAN3D_F32)
+    reflect_pad_kernel<float><<<blocks, 256, 0, st>>>((const float *)in, (float *)out, B, X, Y, Z, C, pad);
+  else
+    reflect_pad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, B, X,
+                                                              Y, Z, C, pad);
+  CG_LAUNCH_CHECK("reflect_pad");
+  return 0;
+}
+
+int reflect_pad_backward(const void *gp, void *gi, int dtype, int B, int X, int Y, int Z, int C, int pad,
+                         cudaStream_t st) {
+  const int64_t total = (int64_t)B * X * Y * Z * C;
+  const int blocks = (int)mn<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  if (dtype == CGAN3D_F32)
+    reflect_pad_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float *)gp, (float *)gi, B, X, Y, Z, C, pad);
+  else
+    reflect_pad_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16 *)gp, (__nv_bfloat16 *)gi, B,
+                                                                  X, Y, Z, C, pad);
+  CG_LAUNCH_CHECK("reflect_pad_backward");
+  return 0;
+}
+
+}  // namespace cg

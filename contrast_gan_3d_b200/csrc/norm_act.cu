@@ -1,0 +1,491 @@
+// BatchNorm (train/eval) + activation + residual, bias+activation, generator tail, dtype helpers.
+// HBM-bound row-major [n_rows][C] kernels (channels-last activations).
+// Replaces aten::native_batch_norm(+backward), relu_/leaky_relu_/tanh, add
+// (reference model/blocks.py:45,50,52-53,87-88; generator.py:85; trainer/Trainer.py:171).
+#include "common.cuh"
+
+namespace cg {
+
+// ---------------------------------------------------------------- column reductions
+// Block of 256 threads covers `lanes = 256 / Cw` rows at a time; thread (lane, c) walks rows
+// lane, lane+lanes, ... of its block's strip.  Per-thread fp32 partials over a short run are
+// promoted to fp64 before the cross-thread / cross-block combine, so the result is independent
+// of the block schedule to fp32 accuracy.
+template <int NS, typename F>
+__device__ __forceinline__ void col_reduce_body(int64_t n_rows, int C, int rows_per_block, double *sums, F f) {
+  extern __shared__ double sh[];  // [NS][lanes][Cw]
+  const int Cw = C <= 256 ? C : 256;
+  const int lanes = blockDim.x / Cw;
+  const int lane = threadIdx.x / Cw;
+  const int c0 = threadIdx.x % Cw;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(n_rows, r0 + rows_per_block);
+  for (int c = c0; c < C; c += Cw) {
+    double tot[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) tot[s] = 0.0;
+    if (lane < lanes) {
+      float part[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) part[s] = 0.f;
+      int run = 0;
+      for (int64_t r = r0 + lane; r < r1; r += lanes) {
+        float v[NS];
+        f(r, c, v);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) part[s] += v[s];
+        if (++run == 64) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) { tot[s] += (double)part[s]; part[s] = 0.f; }
+          run = 0;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) tot[s] += (double)part[s];
+    }
+    __syncthreads();
+    if (lane < lanes) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) sh[(s * lanes + lane) * Cw + c0] = tot[s];
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        double a = 0.0;
+        for (int l = 0; l < lanes; ++l) a += sh[(s * lanes + l) * Cw + c0];
+        atomicAdd(&sums[s * C + c], a);
+      }
+    }
+  }
+}
+
+struct ColGrid {
+  int blocks, rows_per_block;
+  size_t smem;
+};
+static ColGrid col_grid(int64_t n_rows, int C, int ns) {
+  const int Cw = C <= 256 ? C : 256;
+  const int lanes = 256 / Cw;
+  int64_t target_blocks = (int64_t)num_sms() * 8;
+  int64_t rpb = (n_rows + target_blocks - 1) / target_blocks;
+  rpb = mx<int64_t>(rpb, (int64_t)lanes * 8);
+  rpb = ((rpb + lanes - 1) / lanes) * lanes;
+  ColGrid g;
+  g.rows_per_block = (int)mn<int64_t>(rpb, 1 << 30);
+  g.blocks = (int)((n_rows + g.rows_per_block - 1) / g.rows_per_block);
+  g.smem = (size_t)ns * lanes * Cw * sizeof(double);
+  return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T *__restrict__ y, int64_t n_rows, int C, int rpb,
+                                                       double *sums) {
+  col_reduce_body<2>(n_rows, C, rpb, sums, [&](int64_t r, int c, float v[2]) {
+    const float x = to_f(y[r * C + c]);
+    v[0] = x;
+    v[1] = x * x;
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) col_sums_kernel(const T *__restrict__ x, int64_t n_rows, int C, int rpb,
+                                                       double *sums) {
+  col_reduce_body<1>(n_rows, C, rpb, sums, [&](int64_t r, int c, float v[1]) { v[0] = to_f(x[r * C + c]); });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t n_rows, int C, int rpb,
+                     const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta,
+                     int act, float slope, double *sums) {
+  col_reduce_body<2>(n_rows, C, rpb, sums, [&](int64_t r, int c, float v[2]) {
+    const float xh = (to_f(y[r * C + c]) - mi[c]) * mi[C + c];
+    const float pre = gamma[c] * xh + beta[c];
+    const float g = to_f(dz[r * C + c]) * act_bwd(pre, act, slope);
+    v[0] = g;
+    v[1] = g * xh;
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_bwd_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t n_rows, int C,
+                    int rpb, const float *__restrict__ bias, int act, float slope, double *sums) {
+  col_reduce_body<1>(n_rows, C, rpb, sums, [&](int64_t r, int c, float v[1]) {
+    const float pre = to_f(y[r * C + c]) + (bias ? bias[c] : 0.f);
+    const float g = to_f(dz[r * C + c]) * act_bwd(pre, act, slope);
+    dy[r * C + c] = from_f<T>(g);
+    v[0] = g;
+  });
+}
+
+// ---------------------------------------------------------------- finalize
+__global__ void bn_finalize_kernel(const double *__restrict__ sums, int64_t n, int C, float eps, float momentum,
+                                   float *__restrict__ mi, float *running_mean, float *running_var,
+                                   int64_t *num_batches_tracked) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (c >= C) return;
+  const double mean = sums[c] / (double)n;
+  double var = sums[C + c] / (double)n - mean * mean;  // biased variance used for normalisation
+  if (var < 0.0) var = 0.0;
+  mi[c] = (float)mean;
+  mi[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_params_kernel(const float *__restrict__ rm, const float *__restrict__ rv, int C, float eps,
+                                      float *__restrict__ mi) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mi[c] = rm[c];
+  mi[C + c] = 1.f / sqrtf(rv[c] + eps);
+}
+
+__global__ void sums_to_f32_kernel(const double *__restrict__ sums, float *__restrict__ out, int n, float scale,
+                                   float beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = (float)(sums[i] * (double)scale);
+  out[i] = beta != 0.f ? out[i] * beta + v : v;
+}
+
+// ---------------------------------------------------------------- elementwise
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const T *__restrict__ y, T *__restrict__ z, int64_t total, int C, const float *__restrict__ mi,
+                const float *__restrict__ gamma, const float *__restrict__ beta, int act, float slope,
+                const T *__restrict__ residual) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float v = gamma[c] * ((to_f(y[i]) - mi[c]) * mi[C + c]) + beta[c];
+    v = act_fwd(v, act, slope);
+    if (residual) v += to_f(residual[i]);
+    z[i] = from_f<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t total, int C,
+                    double inv_n, const float *__restrict__ mi, const float *__restrict__ gamma,
+                    const float *__restrict__ beta, int act, float slope, const double *__restrict__ sums) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float invstd = mi[C + c];
+    const float xh = (to_f(y[i]) - mi[c]) * invstd;
+    const float pre = gamma[c] * xh + beta[c];
+    const float g = to_f(dz[i]) * act_bwd(pre, act, slope);
+    const float mg = (float)(sums[c] * inv_n), mgx = (float)(sums[C + c] * inv_n);
+    dy[i] = from_f<T>(gamma[c] * invstd * (g - mg - xh * mgx));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_kernel(const T *__restrict__ y, T *__restrict__ z, int64_t total, int C, const float *__restrict__ bias,
+                int act, float slope) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    z[i] = from_f<T>(act_fwd(to_f(y[i]) + (bias ? bias[c] : 0.f), act, slope));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tanh_residual_kernel(const T *__restrict__ y, const float *__restrict__ bias, const float *__restrict__ x,
+                     float *__restrict__ att, float *__restrict__ opt_hat, int64_t n) {
+  const float b = bias ? bias[0] : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = tanhf(to_f(y[i]) + b);
+    att[i] = a;
+    if (opt_hat) opt_hat[i] = x[i] - a;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tanh_residual_bwd_kernel(const float *__restrict__ d_opt_hat, const float *__restrict__ d_att,
+                         const float *__restrict__ att, T *__restrict__ dy, int64_t n, double *dbias_sum) {
+  float part = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = att[i];
+    float up = 0.f;
+    if (d_opt_hat) up -= d_opt_hat[i];
+    if (d_att) up += d_att[i];
+    const float g = up * (1.f - a * a);
+    dy[i] = from_f<T>(g);
+    part += g;
+  }
+  if (dbias_sum) {
+    __shared__ double sh[8];
+    double p = warp_sum((double)part);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
+      atomicAdd(dbias_sum, a);
+    }
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI *__restrict__ in, TO *__restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = from_f<TO>(to_f(in[i]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) axpy_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f<T>(to_f(y[i]) + to_f(x[i]));
+}
+
+static inline int ew_blocks(int64_t n) { return (int)mx<int64_t>(1, mn<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16)); }
+
+}  // namespace cg
+
+using namespace cg;
+
+#define CG_DTYPE_OK(d, name) \
+  if ((d) != CGAN3D_F32 && (d) != CGAN3D_BF16) return fail(CGAN3D_E_DTYPE, name ": unknown dtype %d", (d))
+
+extern "C" {
+
+int cgan3d_bn_stats(const void *y, int dtype, int64_t n_rows, int C, double *sums, void *stream) {
+  CG_CHECK_ARG(y && sums, "bn_stats: NULL pointer");
+  CG_DTYPE_OK(dtype, "bn_stats");
+  CG_CHECK_SHAPE(n_rows >= 0 && C > 0 && (C <= 256 || C % 256 == 0), "bn_stats: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "bn_stats memset");
+  if (n_rows == 0) return 0;
+  ColGrid g = col_grid(n_rows, C, 2);
+  if (dtype == CGAN3D_F32)
+    bn_stats_kernel<float><<<g.blocks, 256, g.smem, st>>>((const float *)y, n_rows, C, g.rows_per_block, sums);
+  else
+    bn_stats_kernel<__nv_bfloat16><<<g.blocks, 256, g.smem, st>>>((const __nv_bfloat16 *)y, n_rows, C, g.rows_per_block, sums);
+  CG_LAUNCH_CHECK("bn_stats");
+  return 0;
+}
+
+int cgan3d_col_sums(const void *x, int dtype, int64_t n_rows, int C, double *sums, void *stream) {
+  CG_CHECK_ARG(x && sums, "col_sums: NULL pointer");
+  CG_DTYPE_OK(dtype, "col_sums");
+  CG_CHECK_SHAPE(n_rows >= 0 && C > 0 && (C <= 256 || C % 256 == 0), "col_sums: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)C * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "col_sums memset");
+  if (n_rows == 0) return 0;
+  ColGrid g = col_grid(n_rows, C, 1);
+  if (dtype == CGAN3D_F32)
+    col_sums_kernel<float><<<g.blocks, 256, g.smem, st>>>((const float *)x, n_rows, C, g.rows_per_block, sums);
+  else
+    col_sums_kernel<__nv_bfloat16><<<g.blocks, 256, g.smem, st>>>((const __nv_bfloat16 *)x, n_rows, C, g.rows_per_block, sums);
+  CG_LAUNCH_CHECK("col_sums");
+  return 0;
+}
+
+int cgan3d_bn_finalize(const double *sums, int64_t n_rows, int C, float eps, float momentum, float *mean_invstd,
+                       float *running_mean, float *running_var, int64_t *num_batches_tracked, void *stream) {
+  CG_CHECK_ARG(sums && mean_invstd, "bn_finalize: NULL pointer");
+  CG_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must come in pairs");
+  CG_CHECK_SHAPE(n_rows > 0 && C > 0, "bn_finalize: bad sizes");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(sums, n_rows, C, eps, momentum, mean_invstd,
+                                                                     running_mean, running_var, num_batches_tracked);
+  CG_LAUNCH_CHECK("bn_finalize");
+  return 0;
+}
+
+int cgan3d_bn_eval_params(const float *running_mean, const float *running_var, int C, float eps, float *mean_invstd,
+                          void *stream) {
+  CG_CHECK_ARG(running_mean && running_var && mean_invstd, "bn_eval_params: NULL pointer");
+  CG_CHECK_SHAPE(C > 0, "bn_eval_params: bad C");
+  bn_eval_params_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(running_mean, running_var, C, eps, mean_invstd);
+  CG_LAUNCH_CHECK("bn_eval_params");
+  return 0;
+}
+
+int cgan3d_sums_to_f32(const double *sums, float *out, int n, float scale, float beta, void *stream) {
+  CG_CHECK_ARG(sums && out && n > 0, "sums_to_f32: bad args");
+  sums_to_f32_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(sums, out, n, scale, beta);
+  CG_LAUNCH_CHECK("sums_to_f32");
+  return 0;
+}
+
+int cgan3d_bn_apply(const void *y, void *z, int dtype, int64_t n_rows, int C, const float *mean_invstd,
+                    const float *gamma, const float *beta, int act, float slope, const void *residual, void *stream) {
+  CG_CHECK_ARG(y && z && mean_invstd && gamma && beta, "bn_apply: NULL pointer");
+  CG_DTYPE_OK(dtype, "bn_apply");
+  CG_CHECK_SHAPE(n_rows >= 0 && C > 0, "bn_apply: bad sizes");
+  const int64_t total = n_rows * C;
+  if (total == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == CGAN3D_F32)
+    bn_apply_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)y, (float *)z, total, C, mean_invstd, gamma,
+                                                             beta, act, slope, (const float *)residual);
+  else
+    bn_apply_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16 *)y, (__nv_bfloat16 *)z, total,
+                                                                     C, mean_invstd, gamma, beta, act, slope,
+                                                                     (const __nv_bfloat16 *)residual);
+  CG_LAUNCH_CHECK("bn_apply");
+  return 0;
+}
+
+int cgan3d_bn_backward_reduce(const void *dz, const void *y, int dtype, int64_t n_rows, int C, const float *mean_invstd,
+                              const float *gamma, const float *beta, int act, float slope, double *sums, void *stream) {
+  CG_CHECK_ARG(dz && y && mean_invstd && gamma && beta && sums, "bn_backward_reduce: NULL pointer");
+  CG_DTYPE_OK(dtype, "bn_backward_reduce");
+  CG_CHECK_SHAPE(n_rows > 0 && C > 0 && (C <= 256 || C % 256 == 0), "bn_backward_reduce: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "bn_backward_reduce memset");
+  ColGrid g = col_grid(n_rows, C, 2);
+  if (dtype == CGAN3D_F32)
+    bn_bwd_reduce_kernel<float><<<g.blocks, 256, g.smem, st>>>((const float *)dz, (const float *)y, n_rows, C,
+                                                               g.rows_per_block, mean_invstd, gamma, beta, act, slope, sums);
+  else
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<g.blocks, 256, g.smem, st>>>((const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y,
+                                                                       n_rows, C, g.rows_per_block, mean_invstd, gamma,
+                                                                       beta, act, slope, sums);
+  CG_LAUNCH_CHECK("bn_backward_reduce");
+  return 0;
+}
+
+int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype, int64_t n_rows, int C,
+                             const float *mean_invstd, const float *gamma, const float *beta, int act, float slope,
+                             const double *sums, float *dgamma, float *dbeta, void *stream) {
+  CG_CHECK_ARG(dz && y && dy && mean_invstd && gamma && beta && sums, "bn_backward_apply: NULL pointer");
+  CG_DTYPE_OK(dtype, "bn_backward_apply");
+  CG_CHECK_SHAPE(n_rows > 0 && C > 0, "bn_backward_apply: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  const int64_t total = n_rows * C;
+  const double inv_n = 1.0 / (double)n_rows;
+  if (dtype == CGAN3D_F32)
+    bn_bwd_apply_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, total, C,
+                                                                 inv_n, mean_invstd, gamma, beta, act, slope, sums);
+  else
+    bn_bwd_apply_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(
+        (const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)dy, total, C, inv_n, mean_invstd, gamma, beta,
+        act, slope, sums);
+  CG_LAUNCH_CHECK("bn_backward_apply");
+  if (dbeta) {
+    sums_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dbeta, C, 1.f, 0.f);
+    CG_LAUNCH_CHECK("bn_backward dbeta");
+  }
+  if (dgamma) {
+    sums_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums + C, dgamma, C, 1.f, 0.f);
+    CG_LAUNCH_CHECK("bn_backward dgamma");
+  }
+  return 0;
+}
+
+int cgan3d_bias_act(const void *y, void *z, int dtype, int64_t n_rows, int C, const float *bias, int act, float slope,
+                    void *stream) {
+  CG_CHECK_ARG(y && z, "bias_act: NULL pointer");
+  CG_DTYPE_OK(dtype, "bias_act");
+  CG_CHECK_SHAPE(n_rows >= 0 && C > 0, "bias_act: bad sizes");
+  const int64_t total = n_rows * C;
+  if (total == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == CGAN3D_F32)
+    bias_act_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)y, (float *)z, total, C, bias, act, slope);
+  else
+    bias_act_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>((const __nv_bfloat16 *)y, (__nv_bfloat16 *)z, total, C,
+                                                                     bias, act, slope);
+  CG_LAUNCH_CHECK("bias_act");
+  return 0;
+}
+
+int cgan3d_bias_act_backward(const void *dz, const void *y, void *dy, int dtype, int64_t n_rows, int C, const float *bias,
+                             int act, float slope, double *dbias_sums, void *stream) {
+  CG_CHECK_ARG(dz && y && dy && dbias_sums, "bias_act_backward: NULL pointer");
+  CG_DTYPE_OK(dtype, "bias_act_backward");
+  CG_CHECK_SHAPE(n_rows > 0 && C > 0 && (C <= 256 || C % 256 == 0), "bias_act_backward: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(dbias_sums, 0, (size_t)C * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "bias_act_backward memset");
+  ColGrid g = col_grid(n_rows, C, 1);
+  if (dtype == CGAN3D_F32)
+    bias_act_bwd_kernel<float><<<g.blocks, 256, g.smem, st>>>((const float *)dz, (const float *)y, (float *)dy, n_rows, C,
+                                                              g.rows_per_block, bias, act, slope, dbias_sums);
+  else
+    bias_act_bwd_kernel<__nv_bfloat16><<<g.blocks, 256, g.smem, st>>>((const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y,
+                                                                      (__nv_bfloat16 *)dy, n_rows, C, g.rows_per_block,
+                                                                      bias, act, slope, dbias_sums);
+  CG_LAUNCH_CHECK("bias_act_backward");
+  return 0;
+}
+
+int cgan3d_tanh_residual(const void *y, const float *bias, const float *x, float *attenuation, float *opt_hat, int dtype,
+                         int64_t n, void *stream) {
+  CG_CHECK_ARG(y && attenuation, "tanh_residual: NULL pointer");
+  CG_CHECK_ARG(opt_hat == nullptr || x != nullptr, "tanh_residual: opt_hat requires x");
+  CG_DTYPE_OK(dtype, "tanh_residual");
+  if (n <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == CGAN3D_F32)
+    tanh_residual_kernel<float><<<ew_blocks(n), 256, 0, st>>>((const float *)y, bias, x, attenuation, opt_hat, n);
+  else
+    tanh_residual_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>((const __nv_bfloat16 *)y, bias, x, attenuation,
+                                                                      opt_hat, n);
+  CG_LAUNCH_CHECK("tanh_residual");
+  return 0;
+}
+
+int cgan3d_tanh_residual_backward(const float *d_opt_hat, const float *d_att, const float *attenuation, void *dy,
+                                  int dtype, int64_t n, double *dbias_sum, void *stream) {
+  CG_CHECK_ARG(attenuation && dy && (d_opt_hat || d_att), "tanh_residual_backward: NULL pointer");
+  CG_DTYPE_OK(dtype, "tanh_residual_backward");
+  if (n <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dbias_sum) {
+    cudaError_t e = cudaMemsetAsync(dbias_sum, 0, sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "tanh_residual_backward memset");
+  }
+  if (dtype == CGAN3D_F32)
+    tanh_residual_bwd_kernel<float><<<ew_blocks(n), 256, 0, st>>>(d_opt_hat, d_att, attenuation, (float *)dy, n, dbias_sum);
+  else
+    tanh_residual_bwd_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(d_opt_hat, d_att, attenuation,
+                                                                          (__nv_bfloat16 *)dy, n, dbias_sum);
+  CG_LAUNCH_CHECK("tanh_residual_backward");
+  return 0;
+}
+
+int cgan3d_cast(const void *in, int in_dtype, void *out, int out_dtype, int64_t n, void *stream) {
+  CG_CHECK_ARG(in && out, "cast: NULL pointer");
+  CG_DTYPE_OK(in_dtype, "cast");
+  CG_DTYPE_OK(out_dtype, "cast");
+  if (n <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int nb = ew_blocks(n);
+  if (in_dtype == CGAN3D_F32 && out_dtype == CGAN3D_BF16)
+    cast_kernel<float, __nv_bfloat16><<<nb, 256, 0, st>>>((const float *)in, (__nv_bfloat16 *)out, n);
+  else if (in_dtype == CGAN3D_BF16 && out_dtype == CGAN3D_F32)
+    cast_kernel<__nv_bfloat16, float><<<nb, 256, 0, st>>>((const __nv_bfloat16 *)in, (float *)out, n);
+  else if (in_dtype == CGAN3D_F32)
+    cast_kernel<float, float><<<nb, 256, 0, st>>>((const float *)in, (float *)out, n);
+  else
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, n);
+  CG_LAUNCH_CHECK("cast");
+  return 0;
+}
+
+int cgan3d_axpy(const void *x, void *y, int dtype, int64_t n, void *stream) {
+  CG_CHECK_ARG(x && y, "axpy: NULL pointer");
+  CG_DTYPE_OK(dtype, "axpy");
+  if (n <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == CGAN3D_F32) axpy_kernel<float><<<ew_blocks(n), 256, 0, st>>>((const float *)x, (float *)y, n);
+  else axpy_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, n);
+  CG_LAUNCH_CHECK("axpy");
+  return 0;
+}
+
+}  // extern "C"

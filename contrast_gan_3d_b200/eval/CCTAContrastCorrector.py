@@ -1,0 +1,105 @@
+"""Whole-volume inference with the reference's class name and call signature
+(reference eval/CCTAContrastCorrector.py:24-135): tile -> patch - G(patch) -> stitch -> unscale to HU.
+
+The int16 volume is uploaded once; tiling, int16->f32 scaling, stitching (average where tiles overlap) and the
+HU unscale are device kernels.  Like the reference, the generator is NOT switched to eval mode: BatchNorm uses the
+statistics of the tiles sharing a batch and tiles go through in row-major (x, y, z) order."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from .._lib import call
+from ..data.Scaler import FactorZeroCenterScaler
+from ..model.utils import compute_convolution_filters_shape
+
+
+def grid_tiles(volume_shape: Sequence[int], patch: Sequence[int]) -> List[Tuple[int, int, int]]:
+    """Regular grid with step = patch, z fastest; a trailing partial tile is squeezed back inside the volume."""
+    starts = []
+    for s, p in zip(volume_shape, patch):
+        if s < p:
+            raise ValueError(f"volume extent {s} smaller than inference patch {p}")
+        a = list(range(0, s - p + 1, p))
+        if a[-1] + p < s:
+            a.append(s - p)
+        starts.append(a)
+    return [(x, y, z) for x in starts[0] for y in starts[1] for z in starts[2]]
+
+
+@dataclass
+class CCTAContrastCorrector:
+    model: Callable[[], nn.Module]
+    scaler: FactorZeroCenterScaler
+    device: torch.device
+    inference_patch_size: Optional[Sequence[int]] = None
+    checkpoint_path: Optional[Path] = None
+    upsampler: Callable = field(init=False, default=None)
+
+    def __post_init__(self):
+        self.model = self.model()
+        if self.checkpoint_path is not None:
+            self.load_model(self.checkpoint_path)
+        self.model = self.model.to(self.device)
+        if self.inference_patch_size is None or len(self.inference_patch_size) < 3:
+            raise NotImplementedError("2D slice-wise correction is outside the B200 hot path (SURVEY §8f rank 4)")
+        out_shape = compute_convolution_filters_shape(self.model, (1, *self.inference_patch_size), show=False)
+        if out_shape[1:] != list(self.inference_patch_size):
+            raise NotImplementedError(f"inference patch {tuple(self.inference_patch_size)} does not round-trip through the "
+                                      f"generator (output {out_shape[1:]}); the reference's nn.Upsample path is not built")
+
+    def load_model(self, checkpoint_path: Union[str, Path]):
+        ckpt = torch.load(checkpoint_path, map_location="cpu")
+        self.model.load_state_dict(ckpt["generator"])
+        self.checkpoint_path = Path(checkpoint_path)
+
+    def correct_scan_3D(self, ccta, batch_size: int, desc: Optional[str] = None) -> Tensor:
+        """Returns the corrected scan in network units, [1, W, H, D] on the device."""
+        if isinstance(ccta, np.ndarray):
+            if ccta.dtype != np.int16:
+                ccta = np.rint(ccta).astype(np.int16) if np.issubdtype(ccta.dtype, np.floating) else ccta.astype(np.int16)
+            vol = torch.from_numpy(np.ascontiguousarray(ccta)).to(self.device, non_blocking=True)
+        else:
+            vol = ccta.to(self.device).to(torch.int16).contiguous()
+        X, Y, Z = vol.shape
+        P = tuple(int(p) for p in self.inference_patch_size)
+        tiles = grid_tiles((X, Y, Z), P)
+        acc = torch.zeros((X, Y, Z), dtype=torch.float32, device=self.device)
+        cnt = torch.zeros((X, Y, Z), dtype=torch.float32, device=self.device)
+        st = ops._st
+        for i in range(0, len(tiles), batch_size):
+            chunk = tiles[i:i + batch_size]
+            xb = torch.empty((len(chunk), 1, *P), dtype=torch.float32, device=self.device)
+            for j, (x0, y0, z0) in enumerate(chunk):
+                call("cgan3d_tile_extract", vol.data_ptr(), X, Y, Z, x0, y0, z0, *P, float(self.scaler.shift),
+                     float(self.scaler.factor), xb[j].data_ptr(), st())
+            if hasattr(self.model, "forward_corrected"):
+                _, corrected = self.model.forward_corrected(xb)
+            else:
+                corrected = xb - self.model(xb)
+            for j, (x0, y0, z0) in enumerate(chunk):
+                call("cgan3d_tile_accumulate", corrected[j].data_ptr(), acc.data_ptr(), cnt.data_ptr(), X, Y, Z, x0, y0, z0,
+                     *P, st())
+        self._acc, self._cnt = acc, cnt
+        return acc, cnt
+
+    @torch.no_grad()
+    def __call__(self, ccta, batch_size: int = 16, **kwargs) -> Tensor:
+        acc, cnt = self.correct_scan_3D(ccta, batch_size, **kwargs)
+        out = torch.empty_like(acc)
+        call("cgan3d_tile_finalize", acc.data_ptr(), cnt.data_ptr(), out.data_ptr(), acc.numel(), float(self.scaler.shift),
+             float(self.scaler.factor), ops._st())
+        return out.cpu()
+
+    @classmethod
+    def from_checkpoint(cls, inference_patch_size, device, checkpoint_path, generator_class=None, scaler=None):
+        if generator_class is None:
+            from ..experiments.b200_conf import generator_class
+        return cls(generator_class, scaler or FactorZeroCenterScaler(-1024, 1500, 600), device,
+                   inference_patch_size=inference_patch_size, checkpoint_path=checkpoint_path)

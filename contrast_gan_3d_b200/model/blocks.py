@@ -1,0 +1,118 @@
+"""ConvBlock / ResNetBlock with the reference's constructor signatures, attribute names and
+state_dict keys (reference model/blocks.py:4-88); forward runs on libcgan3d kernels.
+
+`self.conv` / `self.normalization` are stock torch modules used ONLY as parameter containers
+(identical default init, `.to()`, `state_dict()`); their own forward is never called.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from .. import _lib, ops
+
+
+def _act_code(activation_fn) -> int:
+    if activation_fn in (nn.ReLU,):
+        return _lib.ACT_RELU
+    if activation_fn in (nn.LeakyReLU,):
+        return _lib.ACT_LRELU
+    if activation_fn in (nn.Identity,):
+        return _lib.ACT_NONE
+    raise NotImplementedError(f"activation {activation_fn} is not part of the hot path")
+
+
+def to_channels_last(x: Tensor) -> Tensor:
+    """[B, C, X, Y, Z] -> [B, X, Y, Z, C] (a free view when C == 1)."""
+    if x.shape[1] == 1:
+        return x.contiguous().reshape(x.shape[0], *x.shape[2:], 1)
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def from_channels_last(x: Tensor) -> Tensor:
+    if x.shape[-1] == 1:
+        return x.reshape(x.shape[0], 1, *x.shape[1:-1])
+    return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+class ConvBlock(nn.Module):
+    def __init__(
+        self,
+        is_2D: bool,
+        channels_in: int,
+        channels_out: int,
+        kernel_size: int,
+        upsample: bool = False,
+        output_padding: int = 0,
+        padding_mode: str = "zeros",
+        padding: int = 0,
+        stride: int = 1,
+        activation_fn: nn.Module = nn.ReLU,
+        norm_layer: Optional[nn.Module] = None,
+        **kwargs,
+    ):
+        super().__init__()
+        if is_2D:
+            raise NotImplementedError("2D variant (conf_2D.py) is outside the B200 hot path (SURVEY §8f rank 4)")
+        if norm_layer is None:
+            norm_layer = nn.BatchNorm3d
+        if norm_layer not in (nn.BatchNorm3d, nn.Identity):
+            raise NotImplementedError("only BatchNorm3d / Identity norms are on the hot path (LayerNorm: §8f rank 4)")
+        if padding_mode not in ("zeros", "reflect"):
+            raise NotImplementedError(f"padding_mode {padding_mode!r}")
+        args = {}
+        conv_class = nn.Conv3d
+        if upsample:
+            args = {"output_padding": output_padding}
+            conv_class = nn.ConvTranspose3d
+        self.conv = conv_class(channels_in, channels_out, kernel_size, stride=stride, bias=norm_layer == nn.Identity,
+                               padding_mode=padding_mode, padding=padding, **args)
+        self.normalization = norm_layer(channels_out)
+        activation_kwargs = {}
+        self.negative_slope = 0.0
+        if (ns := kwargs.get("negative_slope")) is not None:
+            activation_kwargs["negative_slope"] = ns
+        self.activation_fn = activation_fn(inplace=True, **activation_kwargs)
+        if isinstance(self.activation_fn, nn.LeakyReLU):
+            self.negative_slope = float(self.activation_fn.negative_slope)
+        self.act_code = _act_code(activation_fn)
+        self.spec = ops.ConvSpec(transposed=upsample, cin=channels_in, cout=channels_out, k=kernel_size, stride=stride,
+                                 pad=padding, reflect=padding_mode == "reflect", out_pad=output_padding)
+        self.compute_dtype = kwargs.get("compute_dtype", torch.float32)
+
+    def forward_cl(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+        bn = self.normalization if isinstance(self.normalization, nn.BatchNorm3d) else None
+        cfg = ops.BlockCfg(spec=self.spec, act=self.act_code, slope=self.negative_slope, dtype=self.compute_dtype,
+                           training=self.training or (bn is not None and not bn.track_running_stats),
+                           momentum=0.1 if bn is None or bn.momentum is None else bn.momentum,
+                           eps=1e-5 if bn is None else bn.eps)
+        if bn is not None:
+            return ops.ConvBlockFn.apply(x, self.conv.weight, None, bn.weight, bn.bias, residual, bn.running_mean,
+                                         bn.running_var, bn.num_batches_tracked, cfg)
+        return ops.ConvBlockFn.apply(x, self.conv.weight, self.conv.bias, None, None, residual, None, None, None, cfg)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return from_channels_last(self.forward_cl(to_channels_last(x)).float())
+
+
+class ResNetBlock(nn.Module):
+    def __init__(self, is_2D: bool, channels_in: int, channels_out: int, kernel_size: int = 3,
+                 dropout_prob: float = 0.0, padding_mode: str = "zeros", **kwargs):
+        super().__init__()
+        padding_amount = 1
+        self.block0 = ConvBlock(is_2D, channels_in, channels_out, kernel_size, padding_mode=padding_mode,
+                                padding=padding_amount, activation_fn=nn.Identity, **kwargs)
+        if dropout_prob > 0:
+            raise NotImplementedError("resnet_dropout_prob > 0 is not on the hot path (reference default is 0)")
+        self.dropout = nn.Identity()
+        self.block1 = ConvBlock(is_2D, channels_out, channels_out, kernel_size, padding_mode=padding_mode,
+                                padding=padding_amount, **kwargs)
+
+    def forward_cl(self, x: Tensor) -> Tensor:
+        # x + block1(dropout(block0(x))): the skip add is fused into block1's normalise/activate pass
+        return self.block1.forward_cl(self.block0.forward_cl(x), residual=x)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return from_channels_last(self.forward_cl(to_channels_last(x)).float())

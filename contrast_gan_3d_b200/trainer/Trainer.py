@@ -1,0 +1,293 @@
+"""Trainer with the reference's constructor, method names, loss-dict keys and checkpoint layout
+(reference trainer/Trainer.py:34-363); the step internals run on libcgan3d kernels.
+
+Differences, all deliberate and listed in DESIGN.md:
+  * `opt_hat = subopt - G(subopt)` is fused into the generator's tanh epilogue when the generator offers
+    `forward_corrected` (Trainer.py:170-171);
+  * ZNCC + HU are one fused pass when the HU loss is ours (Trainer.py:152-153);
+  * the critic weight clip is fused into FusedAdam when the critic optimizer is ours (Trainer.py:136-138);
+  * checkpoints additionally carry `critic_state_dict` (the reference's "discriminator" entry is always None
+    because of an attribute-name mismatch, Trainer.py:311-319 vs :89); the reference can still load ours;
+  * optional `grad_reducer` (data-parallel gradient averaging, no reference counterpart).
+"""
+from __future__ import annotations
+
+import logging
+from functools import partial
+from pathlib import Path
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from ..model.loss import HULoss, WassersteinLoss, ZNCCLoss, fused_similarity_and_hu
+from ..optim import FusedAdam
+
+logger = logging.getLogger(__name__)
+
+SCAN_TYPE_ORDER = (0, -1, 1)  # ScanType iteration order OPT, LOW, HIGH (reference alias.py:24-27)
+
+
+def find_latest_checkpoint(ckpt_dir: Union[Path, str]) -> Optional[Path]:
+    """Highest-numbered `<int>.pt` in the directory (reference trainer/utils.py:26-34)."""
+    nums = []
+    for f in Path(ckpt_dir).glob("*.pt"):
+        try:
+            nums.append(int(f.stem))
+        except ValueError:
+            pass
+    return None if not nums else Path(ckpt_dir) / f"{max(nums)}.pt"
+
+
+class NullLogger:
+    """Logger interface stand-in (reference trainer/logger/LoggerInterface.py:14-32)."""
+
+    class _Inner:
+        def __init__(self):
+            self.records = []
+
+        def log_loss(self, losses, iteration, stage):
+            self.records.append((stage, iteration, {k: float(v) for k, v in losses.items()}))
+
+    def __init__(self):
+        self.logger = NullLogger._Inner()
+
+    def __call__(self, *a, **k):
+        pass
+
+    def end_hook(self):
+        pass
+
+
+class Trainer:
+    def __init__(
+        self,
+        train_iterations: int,
+        val_iterations: int,
+        validate_every: int,
+        train_generator_every: int,
+        train_critic_every: int,
+        log_every: int,
+        log_images_every: int,
+        generator_class: partial,
+        critic_class: partial,
+        generator_optim_class: partial,
+        critic_optim_class: partial,
+        hu_loss_instance: nn.Module,
+        logger_interface,
+        device: torch.device,
+        debug: bool = False,
+        checkpoint_dir: Optional[Union[str, Path]] = None,
+        weight_clip: Optional[float] = None,
+        generator_lr_scheduler_class: Optional[partial] = None,
+        critic_lr_scheduler_class: Optional[partial] = None,
+        hu_loss_weight: float = 1.0,
+        sim_loss_weight: float = 1.0,
+        gan_loss_weight: float = 1.0,
+        gp_weight: float = 10,
+        checkpoint_every: Optional[int] = 1000,
+        rng: Optional[np.random.Generator] = None,
+        grad_reducer=None,
+    ):
+        self.rng = rng
+        self.device = torch.device(device)
+        self.debug = debug
+        self.train_log_sample_size, self.val_log_sample_size = None, None
+        self.train_iterations = train_iterations
+        self.val_iterations = val_iterations
+        self.val_every = validate_every
+        self.train_generator_every = train_generator_every
+        self.train_critic_every = train_critic_every
+        self.log_every = log_every
+        self.log_images_every = log_images_every
+        self.hu_loss_w = hu_loss_weight
+        self.sim_loss_w = sim_loss_weight
+        self.gan_loss_w = gan_loss_weight
+        self.gp_w = gp_weight
+        self.weight_clip = weight_clip
+        if weight_clip is None:
+            raise NotImplementedError("WGAN-GP (weight_clip=None) needs double-backward convs: SURVEY §8f rank 1")
+
+        # construction order G then D matters for seeded-init parity (reference Trainer.py:83,89)
+        self.generator: nn.Module = generator_class().to(self.device)
+        self.optimizer_G = generator_optim_class(self.generator.parameters())
+        self.lr_scheduler_G = generator_lr_scheduler_class
+        if self.lr_scheduler_G is not None:
+            self.lr_scheduler_G = self.lr_scheduler_G(self.optimizer_G)
+        self.critic: nn.Module = critic_class().to(self.device)
+        self.optimizer_D = critic_optim_class(self.critic.parameters())
+        self.lr_scheduler_D = critic_lr_scheduler_class
+        if self.lr_scheduler_D is not None:
+            self.lr_scheduler_D = self.lr_scheduler_D(self.optimizer_D)
+
+        self.loss_GAN = WassersteinLoss()
+        self.loss_similarity = ZNCCLoss()
+        self.loss_HU = hu_loss_instance
+        self.logger_interface = logger_interface
+        self.grad_reducer = grad_reducer
+
+        self.iteration = 0
+        self.checkpoint_every = checkpoint_every
+        self.checkpoint_dir = checkpoint_dir
+        if self.checkpoint_dir is not None:
+            self.checkpoint_dir = Path(self.checkpoint_dir)
+            self.checkpoint_dir.mkdir(exist_ok=True, parents=True)
+            self.load_checkpoint(find_latest_checkpoint(self.checkpoint_dir))
+
+    # ---------------------------------------------------------------- critic / generator updates
+    def train_critic(self, real: Tensor, reconstructions: Tensor, retain_graph: bool) -> Dict[str, Tensor]:
+        self.optimizer_D.zero_grad(set_to_none=True)
+        real_logits = self.critic(real)
+        fake_logits = self.critic(reconstructions.detach())
+        loss_critic = self.gan_loss_w * self.loss_GAN(fake_logits, real_logits)
+        loss_critic.backward()
+        if self.grad_reducer is not None:
+            self.grad_reducer.reduce(self.critic.parameters())
+        if isinstance(self.optimizer_D, FusedAdam):
+            self.optimizer_D.step(clip=self.weight_clip)  # Adam + clamp(+-clip) in one kernel
+        else:
+            self.optimizer_D.step()
+            for p in self.critic.parameters():
+                p.data.clamp_(-self.weight_clip, self.weight_clip)
+        if self.lr_scheduler_D is not None:
+            self.lr_scheduler_D.step()
+        return {"D": loss_critic}
+
+    def train_generator(self, inputs: Tensor, reconstructions: Tensor, centerlines_masks: Tensor) -> Dict[str, Tensor]:
+        self.optimizer_G.zero_grad(set_to_none=True)
+        loss_G = self.gan_loss_w * -self.loss_GAN(self.critic(reconstructions))
+        if isinstance(self.loss_HU, HULoss):
+            loss_sim, loss_hu = fused_similarity_and_hu(reconstructions, inputs, centerlines_masks, self.loss_HU,
+                                                        self.sim_loss_w, self.hu_loss_w)
+        else:
+            loss_sim = self.sim_loss_w * self.loss_similarity(reconstructions, inputs)
+            loss_hu = self.hu_loss_w * self.loss_HU(reconstructions, centerlines_masks)
+        full_loss_G = loss_G + loss_sim + loss_hu
+        full_loss_G.backward()
+        if self.grad_reducer is not None:
+            self.grad_reducer.reduce(self.generator.parameters())
+        self.optimizer_G.step()
+        if self.lr_scheduler_G is not None:
+            self.lr_scheduler_G.step()
+        return {"G": loss_G, "G-full": full_loss_G, "sim": loss_sim, "HU": loss_hu}
+
+    def _generate(self, subopt: Tensor):
+        if hasattr(self.generator, "forward_corrected"):
+            return self.generator.forward_corrected(subopt)
+        attenuation = self.generator(subopt)
+        return attenuation, subopt - attenuation
+
+    def train_step(self, patches: List[dict], iteration: int) -> Dict[str, Tensor]:
+        opt, low, high = patches
+        opt_t: Tensor = opt["data"].to(self.device, non_blocking=True)
+        subopt = torch.cat([low["data"], high["data"]]).to(self.device, non_blocking=True)
+        attenuation, opt_hat = self._generate(subopt)
+
+        do_train_generator = iteration % self.train_generator_every == 0
+        log_dict: Dict[str, Tensor] = {}
+        if iteration % self.train_critic_every == 0:
+            log_dict = self.train_critic(opt_t, opt_hat, do_train_generator)
+        if do_train_generator:
+            subopt_mask = torch.cat([low["seg"], high["seg"]]).to(self.device, non_blocking=True)
+            log_dict |= self.train_generator(subopt, opt_hat, subopt_mask)
+
+        if self.log_every and iteration % self.log_every == 0:
+            self.logger_interface.logger.log_loss({k: v.detach().mean() for k, v in log_dict.items()}, iteration, "train")
+        if self.log_images_every and iteration % self.log_images_every == 0:
+            self.maybe_set_log_images_sample_size("train", patches[0]["data"].shape)
+            cut = len(low["data"])
+            self.logger_interface(patches, [None, opt_hat[:cut], opt_hat[cut:]], [None, attenuation[:cut], attenuation[cut:]],
+                                  list(SCAN_TYPE_ORDER), iteration, "train", self.train_log_sample_size)
+        return log_dict
+
+    # ---------------------------------------------------------------- loop
+    def fit(self, train_loaders: Dict[int, object], val_loaders: Dict[int, object], profiler=None):
+        self.generator.train()
+        self.critic.train()
+        augmenters = {"train": train_loaders, "val": val_loaders}
+        self._manage_augmenters(augmenters, "start")
+        for iteration in range(self.iteration, self.train_iterations):
+            patches = [next(train_loaders[st]) for st in SCAN_TYPE_ORDER]
+            self.train_step(patches, iteration)
+            if self.val_every is not None and iteration != 0 and iteration % self.val_every == 0:
+                self.validate(val_loaders, iteration)
+            if self.checkpoint_every is not None and iteration != 0 and iteration % self.checkpoint_every == 0:
+                self.save_checkpoint(iteration)
+            if profiler:
+                profiler.step()
+        if profiler:
+            profiler.stop()
+        if self.checkpoint_every is not None and self.checkpoint_dir is not None:
+            self.save_checkpoint(self.train_iterations)
+        self._manage_augmenters(augmenters, "end")
+        self.logger_interface.end_hook()
+
+    def validate(self, val_loaders: Dict[int, object], train_iteration: int):
+        self.critic.eval()
+        self.generator.eval()
+        z = torch.zeros(4, dtype=torch.float32, device=self.device)
+        loss_sim, loss_G, loss_real_C, loss_fake_C = z.chunk(4)
+        with torch.no_grad():
+            for _ in range(self.val_iterations):
+                for st in SCAN_TYPE_ORDER:
+                    batch = next(val_loaders[st])
+                    sample = batch["data"].to(self.device, non_blocking=True)
+                    if st == 0:
+                        loss_real_C -= self.loss_GAN(self.critic(sample))
+                    else:
+                        _, sample_hat = self._generate(sample)
+                        loss_fake = self.loss_GAN(self.critic(sample_hat))
+                        loss_fake_C += loss_fake
+                        loss_G -= loss_fake
+                        loss_sim += self.loss_similarity(sample_hat, sample)
+        self.critic.train()
+        self.generator.train()
+        val_loss = {"D": (loss_real_C + loss_fake_C) / self.val_iterations,
+                    "G": loss_G / (self.val_iterations * 2),
+                    "sim": loss_sim / (self.val_iterations * 2)}
+        self.logger_interface.logger.log_loss(val_loss, train_iteration, "validation")
+        return val_loss
+
+    # ---------------------------------------------------------------- checkpoints
+    @property
+    def model_torch_attrs(self) -> List[str]:
+        return ["generator", "optimizer_G", "lr_scheduler_G", "discriminator", "optimizer_D", "lr_scheduler_D"]
+
+    def save_checkpoint(self, iteration: int):
+        state = {"iteration": iteration}
+        for attr in self.model_torch_attrs:
+            el = getattr(self, attr, None)  # "discriminator" stays None exactly as in the reference
+            state[attr] = el if el is None else el.state_dict()
+        state["critic_state_dict"] = self.critic.state_dict()
+        torch.save(state, self.checkpoint_dir / f"{iteration}.pt")
+
+    def load_checkpoint(self, ckpt_path: Optional[Path]):
+        if ckpt_path is not None and Path(ckpt_path).is_file():
+            checkpoint: dict = torch.load(ckpt_path, map_location="cpu")
+            for k, v in checkpoint.items():
+                if k == "critic_state_dict":
+                    self.critic.load_state_dict(v)
+                elif k in self.model_torch_attrs:
+                    if v is not None and hasattr(self, k):
+                        getattr(self, k).load_state_dict(v)
+                else:
+                    setattr(self, k, v)
+        logger.info("Starting from iteration %d", self.iteration)
+
+    def _manage_augmenters(self, augmenters, event: str):
+        assert event in ["start", "end"]
+        for mode, d in augmenters.items():
+            if d is None or (mode == "val" and self.val_every is None):
+                continue
+            for aug in d.values():
+                if event == "start" and hasattr(aug, "restart"):
+                    aug.restart()
+                elif event == "end" and hasattr(aug, "_finish"):
+                    aug._finish()
+
+    def maybe_set_log_images_sample_size(self, mode: str, batch_shape):
+        name = f"{mode}_log_sample_size"
+        if getattr(self, name) is None:
+            bs = batch_shape[-1 if len(batch_shape) == 5 else 0]
+            setattr(self, name, min(bs, 64))
