@@ -1,17 +1,361 @@
-// tcgen05 implicit-GEMM convolution path (placeholder until the kernels land).
+// tcgen05 implicit-GEMM convolutions for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Kernel 1: conv_s1_tc_kernel — 3x3x3, stride 1, pad 1, Cin % 16 == 0, Cout % 16 == 0 (the 8 ResNet convs of the
+// generator: 46 % of its FLOPs), used for fprop (gather) and for dgrad (scatter == gather with flipped, transposed
+// filter).  Replaces aten::convolution / convolution_backward(input) at reference model/blocks.py:68-85.
+//
+// Design ("flattened-shift" implicit GEMM, no im2col materialisation, every input byte fetched from L2 once):
+//   * One CTA owns an output slab (b, x0..x0+xlen, y0..y0+Yt, z0..z0+Zt) and marches along x.  For each input plane x
+//     it TMA-loads the halo slab (Yt+2) x (Zt+2) x Cin ONCE, as Cin/8 boxes of 8 channels, into the UMMA
+//     SWIZZLE_NONE K-major layout [Cin/8][row][8 ch] where row = yy*(Zt+2) + zz is the flattened halo position.
+//     TMA's out-of-bounds zero fill implements the zero padding on all three axes.
+//   * In that layout a filter tap (dx,dy,dz) is a pure ROW SHIFT of the A operand: the A descriptor for tap (dy,dz)
+//     starts (dy*(Zt+2)+dz)*16 B further, plane dx selects one of three resident x-planes.  Output rows are the
+//     flattened halo positions too; rows that fall on the halo columns are computed and discarded
+//     (efficiency Yt*Zt / (mtiles*128)).
+//   * Weights for one tap ([Cin/8][Cout][8] bf16, a K-major B operand) stream through a 4-stage ring with 1-D bulk
+//     copies; each stage feeds mtiles*Cin/16 MMAs (M=128, N=Cout, K=16).
+//   * Accumulators (mtiles x [128 x Cout] fp32) live in TMEM, double-buffered across output planes, so the
+//     epilogue (tcgen05.ld -> bf16 -> 16 B global stores) of plane x overlaps the MMAs of plane x+1.
+//   * Warp roles: 0-3 epilogue, 4 activation-plane TMA producer, 5 MMA issuer (+TMEM alloc), 6 weight producer.
 #include "common.cuh"
 #include "conv_internal.cuh"
+#include "tc_common.cuh"
 
 namespace cg {
-bool tc_supported(const cgan3d_conv_geom &, int, int) { return false; }
-size_t tc_workspace_bytes(const cgan3d_conv_geom &, int, int) { return 0; }
-int tc_gather(const cgan3d_conv_geom &, const void *, const void *, const float *, void *, void *, size_t, cudaStream_t) {
-  return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 gather not built");
+
+using bf16 = __nv_bfloat16;
+
+struct TcPlan {
+  int B, X, Y, Z, Cin, N;
+  int Zt, nzt, Zh;
+  int Yt, nslabs, Yh;
+  int xseg, nxseg;
+  int mtiles, rows_alloc, nitems, b_stages;
+  uint32_t plane_bytes, btile_bytes, box_bytes, tmem_cols, smem_bytes;
+};
+
+constexpr int kPlaneSlots = 3;
+constexpr int kThreads = 224;
+constexpr uint32_t kSmemLimit = 232448 - 1024;
+
+__device__ __forceinline__ void decode_item(const TcPlan &p, int item, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x0,
+                                            int &xlen) {
+  const int xs = item % p.nxseg; item /= p.nxseg;
+  const int sl = item % p.nslabs; item /= p.nslabs;
+  const int zt = item % p.nzt;
+  b = item / p.nzt;
+  x0 = xs * p.xseg; xlen = min(p.xseg, p.X - x0);
+  y0 = sl * p.Yt; ylen = min(p.Yt, p.Y - y0);
+  z0 = zt * p.Zt; zlen = min(p.Zt, p.Z - z0);
 }
-int tc_scatter(const cgan3d_conv_geom &, const void *, const void *, const float *, void *, void *, size_t, cudaStream_t) {
-  return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 scatter not built");
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out, const TcPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *planes = smem;
+  uint8_t *bt = planes + (size_t)kPlaneSlots * p.plane_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bt + (size_t)p.b_stages * p.btile_bytes);
+  uint64_t *plane_full = bars, *plane_empty = bars + kPlaneSlots;
+  uint64_t *b_full = bars + 2 * kPlaneSlots, *b_empty = b_full + p.b_stages;
+  uint64_t *tm_full = b_empty + p.b_stages, *tm_empty = tm_full + 2;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tm_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPlaneSlots; ++i) { tc::mbar_init(&plane_full[i], 1); tc::mbar_init(&plane_empty[i], 1); }
+    for (int i = 0; i < p.b_stages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) {
+    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmA);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int kchunks8 = p.Cin >> 3, ksteps = p.Cin >> 4;
+  const int taps = 27;
+
+  if (warp == 4) {
+    // ------------------------------------------------ activation-plane producer
+    if (lane == 0) {
+      uint32_t e = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        int b, z0, zlen, y0, ylen, x0, xlen;
+        decode_item(p, item, b, z0, zlen, y0, ylen, x0, xlen);
+        for (int px = x0 - 1; px <= x0 + xlen; ++px, ++e) {
+          const uint32_t slot = e % kPlaneSlots, use = e / kPlaneSlots;
+          if (use > 0) tc::mbar_wait(&plane_empty[slot], (use - 1) & 1);
+          tc::mbar_expect_tx(&plane_full[slot], p.box_bytes * kchunks8);
+          uint8_t *dst = planes + (size_t)slot * p.plane_bytes;
+          for (int cc = 0; cc < kchunks8; ++cc)
+            tc::tma_load_5d(dst + (size_t)cc * p.rows_alloc * 16, &tmA, &plane_full[slot], cc * 8, z0 - 1, y0 - 1, px, b);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------ weight-tap producer
+    if (lane == 0) {
+      uint32_t t = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        int b, z0, zlen, y0, ylen, x0, xlen;
+        decode_item(p, item, b, z0, zlen, y0, ylen, x0, xlen);
+        for (int i = 0; i < xlen; ++i)
+          for (int tap = 0; tap < taps; ++tap, ++t) {
+            const uint32_t s = t % p.b_stages, use = t / p.b_stages;
+            if (use > 0) tc::mbar_wait(&b_empty[s], (use - 1) & 1);
+            tc::mbar_expect_tx(&b_full[s], p.btile_bytes);
+            tc::bulk_g2s(bt + (size_t)s * p.btile_bytes, reinterpret_cast<const uint8_t *>(wB) + (size_t)tap * p.btile_bytes,
+                         p.btile_bytes, &b_full[s]);
+          }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.N, 0, 0);
+      const uint32_t planes_u32 = tc::smem_u32(planes), bt_u32 = tc::smem_u32(bt);
+      const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16, b_lbo = (uint32_t)p.N * 16;
+      uint32_t e_base = 0, t = 0, acc = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        int b, z0, zlen, y0, ylen, x0, xlen;
+        decode_item(p, item, b, z0, zlen, y0, ylen, x0, xlen);
+        for (int i = 0; i < xlen; ++i, ++acc) {
+          const uint32_t q = acc & 1, uq = acc >> 1;
+          if (uq > 0) tc::mbar_wait(&tm_empty[q], (uq - 1) & 1);
+          tc::tc_fence_after();
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t e = e_base + i + dx, slot = e % kPlaneSlots;
+            tc::mbar_wait(&plane_full[slot], (e / kPlaneSlots) & 1);
+            tc::tc_fence_after();
+            const uint32_t a_plane = planes_u32 + slot * p.plane_bytes;
+            for (int dy = 0; dy < 3; ++dy)
+              for (int dz = 0; dz < 3; ++dz, ++t) {
+                const int tap = (dx * 3 + dy) * 3 + dz;
+                const uint32_t s = t % p.b_stages;
+                tc::mbar_wait(&b_full[s], (t / p.b_stages) & 1);
+                tc::tc_fence_after();
+                const uint32_t b_tile = bt_u32 + s * p.btile_bytes;
+                const uint32_t row_shift = (uint32_t)(dy * p.Zh + dz) * 16;
+                for (int mt = 0; mt < p.mtiles; ++mt) {
+                  const uint32_t d_tmem = tmem_base + (q * p.mtiles + mt) * p.N;
+                  const uint32_t a_row = a_plane + row_shift + (uint32_t)mt * 128 * 16;
+                  for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint64_t a_desc = tc::make_desc(a_row + 2 * kk * a_lbo, a_lbo, 128);
+                    const uint64_t b_desc = tc::make_desc(b_tile + 2 * kk * b_lbo, b_lbo, 128);
+                    tc::umma_bf16(d_tmem, a_desc, b_desc, idesc, (tap | kk) != 0);
+                  }
+                }
+                tc::umma_commit(&b_empty[s]);
+              }
+            if (dx == 0) tc::umma_commit(&plane_empty[slot]);  // last use of input plane x-1
+          }
+          tc::umma_commit(&tm_full[q]);
+        }
+        tc::umma_commit(&plane_empty[(e_base + xlen) % kPlaneSlots]);
+        tc::umma_commit(&plane_empty[(e_base + xlen + 1) % kPlaneSlots]);
+        e_base += xlen + 2;
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 0..3 <-> TMEM lanes 32*warp..)
+    uint32_t acc = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      int b, z0, zlen, y0, ylen, x0, xlen;
+      decode_item(p, item, b, z0, zlen, y0, ylen, x0, xlen);
+      for (int i = 0; i < xlen; ++i, ++acc) {
+        const uint32_t q = acc & 1;
+        tc::mbar_wait(&tm_full[q], (acc >> 1) & 1);
+        tc::tc_fence_after();
+        for (int mt = 0; mt < p.mtiles; ++mt) {
+          const int r = mt * 128 + warp * 32 + lane;
+          const int oy = r / p.Zh, oz = r - oy * p.Zh;
+          const bool valid = oy < ylen && oz < zlen;
+          bf16 *dst = out + ((((size_t)b * p.X + (x0 + i)) * p.Y + (y0 + oy)) * p.Z + (z0 + oz)) * p.N;
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (q * p.mtiles + mt) * p.N;
+          for (int c0 = 0; c0 < p.N; c0 += 16) {
+            uint32_t v[16];
+            tc::tmem_ld16(taddr + c0, v);
+            tc::tmem_ld_wait();
+            if (valid) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                pk[j] = *reinterpret_cast<uint32_t *>(&h);
+              }
+              uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
+              d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
+
+// [tap][Cb][Cs] (generic packed) -> [tap'][Cin/8][N][8]; flip = dgrad (reverse taps, swap channel roles)
+__global__ void repack_b_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int taps, int flip) {
+  const int Cin = flip ? Cs : Cb, N = flip ? Cb : Cs;
+  const int64_t total = (int64_t)taps * Cin * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i & 7);
+    int64_t t = i >> 3;
+    const int n = (int)(t % N); t /= N;
+    const int cc = (int)(t % (Cin >> 3));
+    const int tap = (int)(t / (Cin >> 3));
+    const int ci = cc * 8 + c8;
+    const int src_tap = flip ? (taps - 1 - tap) : tap;
+    const int cb = flip ? n : ci, cs = flip ? ci : n;
+    wb[i] = wp[((int64_t)src_tap * Cb + cb) * Cs + cs];
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
+  if (Cin % 16 || N % 16 || Cin > 256 || N > 256 || Cin < 16 || N < 16) return false;
+  TcPlan p{};
+  p.B = B; p.X = X; p.Y = Y; p.Z = Z; p.Cin = Cin; p.N = N;
+  p.nzt = (Z + 61) / 62;
+  p.Zt = (Z + p.nzt - 1) / p.nzt;
+  p.Zh = p.Zt + 2;
+  p.btile_bytes = (uint32_t)Cin * N * 2;
+  p.b_stages = 4;
+  double best_eff = 0;
+  bool found = false;
+  for (int Yt = 1; Yt <= Y && Yt + 2 <= 256; ++Yt) {
+    const int mt = (Yt * p.Zh + 127) / 128;
+    if (2 * mt * N > 512) break;
+    const int rows_alloc = ((mt * 128 + 2 * p.Zh + 2) + 7) / 8 * 8;
+    const uint32_t plane_bytes = (uint32_t)(Cin / 8) * rows_alloc * 16;
+    const uint32_t smem = kPlaneSlots * plane_bytes + p.b_stages * p.btile_bytes + 512;
+    if (smem > kSmemLimit) break;
+    const int nslabs = (Y + Yt - 1) / Yt;
+    const double eff = (double)Y * p.Zt / ((double)nslabs * mt * 128);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      found = true;
+      best = p;
+      best.Yt = Yt; best.Yh = Yt + 2; best.nslabs = nslabs; best.mtiles = mt; best.rows_alloc = rows_alloc;
+      best.plane_bytes = plane_bytes; best.smem_bytes = smem;
+    }
+  }
+  if (!found) return false;
+  TcPlan &q = best;
+  q.box_bytes = 16u * q.Zh * q.Yh;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * q.mtiles * N)) cols <<= 1;
+  q.tmem_cols = cols;
+  // x segments: enough items for ~3 waves of persistent CTAs, but at least 4 planes per item (2 halo planes each)
+  const int sms = num_sms();
+  int xseg = X;
+  auto items = [&](int xs) { return (int64_t)B * q.nzt * q.nslabs * ((X + xs - 1) / xs); };
+  while (xseg > 4 && items(xseg) < 3 * (int64_t)sms) xseg = (xseg + 1) / 2;
+  q.xseg = xseg;
+  q.nxseg = (X + xseg - 1) / xseg;
+  q.nitems = (int)items(xseg);
+  return true;
+}
+
+static bool s1_shape_ok(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (dtype != CGAN3D_BF16 || (op != 0 && op != 1)) return false;
+  if (g.k != 3 || g.stride != 1 || g.pad != 1) return false;
+  if (g.Xb != g.Xs || g.Yb != g.Ys || g.Zb != g.Zs) return false;
+  return true;
+}
+
+bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (!s1_shape_ok(g, dtype, op)) return false;
+  if (!cgan3d_device_supports_tc() || encode_fn() == nullptr) return false;
+  TcPlan p;
+  const int Cin = op == 0 ? g.Cb : g.Cs, N = op == 0 ? g.Cs : g.Cb;
+  return plan_s1(g.B, g.Xb, g.Yb, g.Zb, Cin, N, p);
+}
+
+size_t tc_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (!s1_shape_ok(g, dtype, op)) return 0;
+  return (size_t)27 * g.Cb * g.Cs * 2 + 256;
+}
+
+static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  const int Cin = flip ? g.Cs : g.Cb, N = flip ? g.Cb : g.Cs;
+  TcPlan p;
+  if (!plan_s1(g.B, g.Xb, g.Yb, g.Zb, Cin, N, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: no tiling for this shape");
+  const size_t need = (size_t)27 * Cin * N * 2;
+  if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 conv: workspace %zu < %zu", ws_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
+    return fail(CGAN3D_E_ARG, "tcgen05 conv: pointers must be 16-byte aligned");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  bf16 *wb = reinterpret_cast<bf16 *>(ws);
+  repack_b_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, 27, flip);
+  CG_LAUNCH_CHECK("repack_b");
+  CUtensorMap tm;
+  const cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)p.B};
+  const cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)p.Z * Cin * 2, (cuuint64_t)p.Y * p.Z * Cin * 2,
+                              (cuuint64_t)p.X * p.Y * p.Z * Cin * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_s1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit + 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_s1_tc_kernel)");
+    attr_set = true;
+  }
+  const int grid = min(p.nitems, num_sms());
+  conv_s1_tc_kernel<<<grid, kThreads, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
+  CG_LAUNCH_CHECK("conv_s1_tc_kernel");
+  return 0;
+}
+
+int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const float *bias, void *small, void *ws,
+              size_t ws_bytes, cudaStream_t st) {
+  if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  return run_s1(g, 0, big, wp, small, ws, ws_bytes, st);
+}
+
+int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, const float *bias, void *big, void *ws,
+               size_t ws_bytes, cudaStream_t st) {
+  if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  return run_s1(g, 1, small, wp, big, ws, ws_bytes, st);
+}
+
 int tc_wgrad(const cgan3d_conv_geom &, const void *, const void *, float *, float, void *, size_t, cudaStream_t) {
   return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 wgrad not built");
 }
+
 }  // namespace cg
