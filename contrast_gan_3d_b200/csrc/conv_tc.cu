@@ -50,6 +50,7 @@ __device__ __forceinline__ void decode_item(const TcPlan &p, int item, int &b, i
   z0 = zt * p.Zt; zlen = min(p.Zt, p.Z - z0);
 }
 
+template <int KSTEPS, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out, const TcPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -77,7 +78,7 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int kchunks8 = p.Cin >> 3, ksteps = p.Cin >> 4;
+  const int kchunks8 = p.Cin >> 3;
   const int taps = 27;
 
   if (warp == 4) {
@@ -116,10 +117,16 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
     }
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow so that ptxas keeps descriptors, TMEM addresses and loop
+    // state in UNIFORM registers; only the tcgen05.mma / tcgen05.commit themselves are issued by one elected lane.
+    // (A lane-0-only loop forces per-MMA R2UR transfers and made the issue thread, not the tensor pipe, the limit.)
+    {
+      const bool leader = tc::elect_one();
       const uint32_t idesc = tc::make_idesc_bf16(128, p.N, 0, 0);
       const uint32_t planes_u32 = tc::smem_u32(planes), bt_u32 = tc::smem_u32(bt);
       const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16, b_lbo = (uint32_t)p.N * 16;
+      const uint64_t a_desc_hi = tc::make_desc(0, a_lbo, 128), b_desc_hi = tc::make_desc(0, b_lbo, 128);
+      const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;  // descriptor address units (16 B)
       uint32_t e_base = 0, t = 0, acc = 0;
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
         int b, z0, zlen, y0, ylen, x0, xlen;
@@ -132,33 +139,39 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
             const uint32_t e = e_base + i + dx, slot = e % kPlaneSlots;
             tc::mbar_wait(&plane_full[slot], (e / kPlaneSlots) & 1);
             tc::tc_fence_after();
-            const uint32_t a_plane = planes_u32 + slot * p.plane_bytes;
+            const uint32_t a_plane = (planes_u32 + slot * p.plane_bytes) >> 4;
             for (int dy = 0; dy < 3; ++dy)
               for (int dz = 0; dz < 3; ++dz, ++t) {
                 const int tap = (dx * 3 + dy) * 3 + dz;
                 const uint32_t s = t % p.b_stages;
                 tc::mbar_wait(&b_full[s], (t / p.b_stages) & 1);
                 tc::tc_fence_after();
-                const uint32_t b_tile = bt_u32 + s * p.btile_bytes;
-                const uint32_t row_shift = (uint32_t)(dy * p.Zh + dz) * 16;
-                for (int mt = 0; mt < p.mtiles; ++mt) {
-                  const uint32_t d_tmem = tmem_base + (q * p.mtiles + mt) * p.N;
-                  const uint32_t a_row = a_plane + row_shift + (uint32_t)mt * 128 * 16;
-                  for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint64_t a_desc = tc::make_desc(a_row + 2 * kk * a_lbo, a_lbo, 128);
-                    const uint64_t b_desc = tc::make_desc(b_tile + 2 * kk * b_lbo, b_lbo, 128);
-                    tc::umma_bf16(d_tmem, a_desc, b_desc, idesc, (tap | kk) != 0);
+                const uint64_t b_desc0 = b_desc_hi | (uint64_t)(((bt_u32 + s * p.btile_bytes) >> 4) & 0x3FFF);
+                const uint32_t a_tap = a_plane + (uint32_t)(dy * p.Zh + dz);
+                const uint64_t a_desc0 = a_desc_hi | (uint64_t)(a_tap & 0x3FFF);
+                const uint32_t d_tmem0 = tmem_base + q * (MT * p.N);
+                if (leader) {
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk)
+                      tc::umma_bf16(d_tmem0 + mt * p.N, a_desc0 + (uint64_t)(mt * 128 + kk * a_kstep),
+                                    b_desc0 + (uint64_t)(kk * b_kstep), idesc, (uint32_t)((tap | kk) != 0));
                   }
+                  tc::umma_commit(&b_empty[s]);
                 }
-                tc::umma_commit(&b_empty[s]);
+                __syncwarp();
               }
-            if (dx == 0) tc::umma_commit(&plane_empty[slot]);  // last use of input plane x-1
+            if (dx == 0 && leader) tc::umma_commit(&plane_empty[slot]);  // last use of input plane x-1
           }
-          tc::umma_commit(&tm_full[q]);
+          if (leader) tc::umma_commit(&tm_full[q]);
         }
-        tc::umma_commit(&plane_empty[(e_base + xlen) % kPlaneSlots]);
-        tc::umma_commit(&plane_empty[(e_base + xlen + 1) % kPlaneSlots]);
+        if (leader) {
+          tc::umma_commit(&plane_empty[(e_base + xlen) % kPlaneSlots]);
+          tc::umma_commit(&plane_empty[(e_base + xlen + 1) % kPlaneSlots]);
+        }
         e_base += xlen + 2;
+        __syncwarp();
       }
     }
   } else {
@@ -242,22 +255,24 @@ static EncodeTiledFn encode_fn() {
 }
 
 static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
-  if (Cin % 16 || N % 16 || Cin > 256 || N > 256 || Cin < 16 || N < 16) return false;
+  if (N % 16 || N > 256 || N < 16) return false;
+  if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
   TcPlan p{};
   p.B = B; p.X = X; p.Y = Y; p.Z = Z; p.Cin = Cin; p.N = N;
   p.nzt = (Z + 61) / 62;
   p.Zt = (Z + p.nzt - 1) / p.nzt;
   p.Zh = p.Zt + 2;
   p.btile_bytes = (uint32_t)Cin * N * 2;
-  p.b_stages = 4;
+  p.b_stages = p.btile_bytes <= 8192 ? 4 : (p.btile_bytes <= 16384 ? 3 : 2);
   double best_eff = 0;
   bool found = false;
   for (int Yt = 1; Yt <= Y && Yt + 2 <= 256; ++Yt) {
     const int mt = (Yt * p.Zh + 127) / 128;
-    if (2 * mt * N > 512) break;
+    if (2 * mt * N > 512 || mt > 4) break;
     const int rows_alloc = ((mt * 128 + 2 * p.Zh + 2) + 7) / 8 * 8;
     const uint32_t plane_bytes = (uint32_t)(Cin / 8) * rows_alloc * 16;
     const uint32_t smem = kPlaneSlots * plane_bytes + p.b_stages * p.btile_bytes + 512;
+    if (rows_alloc * 16 > 16383 * 16) break;
     if (smem > kSmemLimit) break;
     const int nslabs = (Y + Yt - 1) / Yt;
     const double eff = (double)Y * p.Zt / ((double)nslabs * mt * 128);
@@ -330,16 +345,37 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_s1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit + 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_s1_tc_kernel)");
-    attr_set = true;
-  }
   const int grid = min(p.nitems, num_sms());
-  conv_s1_tc_kernel<<<grid, kThreads, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
-  CG_LAUNCH_CHECK("conv_s1_tc_kernel");
-  return 0;
+  auto launch = [&](auto ks_tag, auto mt_tag) -> int {
+    constexpr int KS = decltype(ks_tag)::value;
+    constexpr int MT = decltype(mt_tag)::value;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv_s1_tc_kernel<KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kSmemLimit + 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_s1_tc_kernel)");
+      attr_set = true;
+    }
+    conv_s1_tc_kernel<KS, MT><<<grid, kThreads, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
+    CG_LAUNCH_CHECK("conv_s1_tc_kernel");
+    return 0;
+  };
+  auto by_mt = [&](auto ks_tag) -> int {
+    switch (p.mtiles) {
+      case 1: return launch(ks_tag, std::integral_constant<int, 1>{});
+      case 2: return launch(ks_tag, std::integral_constant<int, 2>{});
+      case 3: return launch(ks_tag, std::integral_constant<int, 3>{});
+      case 4: return launch(ks_tag, std::integral_constant<int, 4>{});
+      default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: mtiles %d not built", p.mtiles);
+    }
+  };
+  switch (Cin >> 4) {
+    case 1: return by_mt(std::integral_constant<int, 1>{});
+    case 2: return by_mt(std::integral_constant<int, 2>{});
+    case 4: return by_mt(std::integral_constant<int, 4>{});
+    case 8: return by_mt(std::integral_constant<int, 8>{});
+    default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: Cin must be 16, 32, 64 or 128");
+  }
 }
 
 int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const float *bias, void *small, void *ws,

@@ -1,0 +1,84 @@
+"""Micro-benchmark of the convolution kernels (BASELINE config C5 style): per-op device time with CUDA events.
+
+    python tools/bench_conv.py [--cases res,down,...] [--impls tc,generic] [--iters 20]
+Prints one JSON line per (case, op, impl): TFLOP/s of algorithmic 2*MAC work and the fraction of the measured bf16 peak.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from contrast_gan_3d_b200 import _lib, ops  # noqa: E402
+
+CASES = {
+    # name: (transposed, cin, cout, k, stride, pad, out_pad, B, spatial_in)
+    "res": (False, 64, 64, 3, 1, 1, 0, 16, (32, 32, 32)),
+    "res_b2": (False, 64, 64, 3, 1, 1, 0, 2, (32, 32, 32)),
+    "c32_64": (False, 32, 32, 3, 1, 1, 0, 4, (64, 64, 64)),
+    "c16_128": (False, 16, 16, 3, 1, 1, 0, 2, (128, 128, 128)),
+    "c128_32": (False, 128, 128, 3, 1, 1, 0, 8, (32, 32, 32)),
+    "down0": (False, 16, 32, 3, 2, 1, 0, 4, (128, 128, 128)),
+    "down1": (False, 32, 64, 3, 2, 1, 0, 8, (64, 64, 64)),
+    "up0": (True, 64, 32, 3, 2, 1, 1, 8, (32, 32, 32)),
+    "up1": (True, 32, 16, 3, 2, 1, 1, 4, (64, 64, 64)),
+    "first": (False, 1, 16, 7, 1, 0, 0, 2, (134, 134, 134)),
+    "last": (False, 16, 1, 7, 1, 0, 0, 2, (134, 134, 134)),
+    "d_first": (False, 1, 8, 4, 2, 1, 0, 16, (128, 128, 128)),
+    "d_mid0": (False, 8, 16, 4, 2, 1, 0, 16, (64, 64, 64)),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="res")
+    ap.add_argument("--impls", default="tc,generic")
+    ap.add_argument("--ops", default="gather,scatter,wgrad")
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    peak = 1396.9
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peak = json.loads(pk.read_text())["bf16_tflops"]
+    dev = torch.device("cuda:0")
+    for name in args.cases.split(","):
+        tr, cin, cout, k, s, p, op_, B, sp = CASES[name]
+        spec = ops.ConvSpec(transposed=tr, cin=cin, cout=cout, k=k, stride=s, pad=p, out_pad=op_)
+        g, out_sp = spec.geometry(B, sp)
+        big = torch.randn((g.B, g.Xb, g.Yb, g.Zb, g.Cb), device=dev).bfloat16()
+        small = torch.randn((g.B, g.Xs, g.Ys, g.Zs, g.Cs), device=dev).bfloat16()
+        w = torch.randn((g.Cs, g.Cb, k, k, k), device=dev) / (g.Cb * k ** 3) ** 0.5
+        wp = ops.pack_weights(w, torch.bfloat16)
+        flops = 2.0 * g.B * g.Xs * g.Ys * g.Zs * g.Cs * g.Cb * k ** 3
+        for opn in args.ops.split(","):
+            opi = {"gather": 0, "scatter": 1, "wgrad": 2}[opn]
+            for impl in args.impls.split(","):
+                ii = {"tc": _lib.IMPL_TC, "generic": _lib.IMPL_GENERIC}[impl]
+                if impl == "tc" and _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, opi) != 2:
+                    continue
+                fn = {"gather": lambda: ops.conv_gather(g, big, wp, impl=ii), "scatter": lambda: ops.conv_scatter(g, small, wp, impl=ii),
+                      "wgrad": lambda: ops.conv_wgrad(g, big, small, impl=ii)}[opn]
+                iters = args.iters if impl == "tc" else max(2, args.iters // 5)
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+                tf = flops / (ms * 1e-3) / 1e12
+                print(json.dumps({"case": name, "op": opn, "impl": impl, "ms": round(ms, 4), "tflops": round(tf, 2),
+                                  "frac_of_bf16_burst_peak": round(tf / peak, 4), "gflop": round(flops / 1e9, 2)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
