@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--conv-impl", default="auto", choices=["auto", "generic", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-conv-kernel device-time table of the timed region here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -248,6 +249,15 @@ def main():
                 "step_tflops": pairs_per_step / world * PAIR_GFLOP_128 * (args.patch / 128) ** 3 / (ms * 1e-3) / 1e3,
                 }
         roof["step_frac_of_peak"] = roof["step_tflops"] / pk["bf16_sustained"]
+
+    if args.breakdown and conv_t:
+        rows = sorted(([k[0], "tc" if v[3] == 2 else "generic", list(k[2:]), v[0] / args.steps, v[1] / args.steps,
+                        v[2] * v[0] / v[1] / 1e9 if v[1] > 0 else 0.0] for k, v in conv_t.items()), key=lambda r: -r[4])
+        with open(args.breakdown, "w") as f:
+            f.write("op impl [B,Xb,Yb,Zb,Cb,Xs,Ys,Zs,Cs,k,stride,pad] launches/step ms/step TFLOP/s\n")
+            for r in rows:
+                f.write(f"{r[0]:8s} {r[1]:8s} {str(r[2]):58s} {r[3]:5.1f} {r[4]:10.3f} {r[5]:9.2f}\n")
+            f.write(f"conv total ms/step {sum(r[4] for r in rows):.3f} of step {ms:.3f}\n")
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -44,7 +44,8 @@ int cgan3d_pack_weights(const float *w, void *packed, int dtype, int Cs, int Cb,
 
 size_t cgan3d_conv_workspace_bytes(const cgan3d_conv_geom *g, int dtype, int op) {
   if (!g || check_geom(g, dtype) != 0) return 0;
-  return tc_supported(*g, dtype, op) ? tc_workspace_bytes(*g, dtype, op) : 0;
+  const size_t a = tc_supported(*g, dtype, op) ? tc_workspace_bytes(*g, dtype, op) : 0, b = generic_workspace_bytes(*g, dtype, op);
+  return a > b ? a : b;
 }
 
 int cgan3d_conv_select(const cgan3d_conv_geom *g, int dtype, int op) {
@@ -75,7 +76,7 @@ int cgan3d_conv_scatter(const cgan3d_conv_geom *g, int dtype, const void *small,
   bool tc = false;
   if ((r = pick(*g, dtype, 1, impl, &tc))) return r;
   if (tc) return tc_scatter(*g, small, wpacked, bias, big, workspace, workspace_bytes, as_stream(stream));
-  return generic_scatter(*g, dtype, small, wpacked, bias, big, as_stream(stream));
+  return generic_scatter(*g, dtype, small, wpacked, bias, big, workspace, workspace_bytes, as_stream(stream));
 }
 
 int cgan3d_conv_wgrad(const cgan3d_conv_geom *g, int dtype, const void *big, const void *small, float *dw, float beta,

@@ -84,11 +84,102 @@ gather_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict
   }
 }
 
+
+// ------------------------------------------------------------------ gather, Cs == 1 (last_conv / critic logits)
+// one thread: VB consecutive z outputs of the single output channel; input channels are consumed 8 at a time
+// (one 16 B / 32 B vector load per voxel), weights [tap][Cb][1] are contiguous over ci.
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float *p) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16 *p) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+template <typename T, int K, int S, int VB>
+__global__ void __launch_bounds__(128)
+gather_co1_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict__ wp, const float *__restrict__ bias,
+                  T *__restrict__ small) {
+  const int nzg = (g.Zs + VB - 1) / VB;
+  const int64_t total = (int64_t)g.B * g.Xs * g.Ys * nzg;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int zg = (int)(idx % nzg); idx /= nzg;
+  const int oy = (int)(idx % g.Ys); idx /= g.Ys;
+  const int ox = (int)(idx % g.Xs);
+  const int b = (int)(idx / g.Xs);
+  const int oz0 = zg * VB;
+  constexpr int NZ = (VB - 1) * S + K;
+  float acc[VB];
+#pragma unroll
+  for (int v = 0; v < VB; ++v) acc[v] = bias ? bias[0] : 0.f;
+  const int iz0 = oz0 * S - g.pad;
+  for (int kx = 0; kx < K; ++kx) {
+    const int ix = ox * S - g.pad + kx;
+    if ((unsigned)ix >= (unsigned)g.Xb) continue;
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * S - g.pad + ky;
+      if ((unsigned)iy >= (unsigned)g.Yb) continue;
+      const T *xrow = big + (((int64_t)b * g.Xb + ix) * g.Yb + iy) * (int64_t)g.Zb * g.Cb;
+      const T *wrow = wp + (int64_t)((kx * K + ky) * K) * g.Cb;
+      for (int c0 = 0; c0 < g.Cb; c0 += 8) {
+        Vec8<T> wv[K];
+#pragma unroll
+        for (int kz = 0; kz < K; ++kz) wv[kz].load(wrow + (int64_t)kz * g.Cb + c0);
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) {
+          const int iz = iz0 + j;
+          if ((unsigned)iz >= (unsigned)g.Zb) continue;
+          Vec8<T> xv;
+          xv.load(xrow + (int64_t)iz * g.Cb + c0);
+#pragma unroll
+          for (int kz = 0; kz < K; ++kz) {
+            const int jv = j - kz;  // output v = (j - kz) / S when divisible
+            if (jv >= 0 && jv % S == 0 && jv / S < VB) {
+              float sum = 0.f;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) sum = fmaf(xv.v[c], wv[kz].v[c], sum);
+              acc[jv / S] += sum;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VB; ++v) {
+    const int oz = oz0 + v;
+    if (oz < g.Zs) small[(((int64_t)b * g.Xs + ox) * g.Ys + oy) * g.Zs + oz] = from_f<T>(acc[v]);
+  }
+}
+
 template <typename T, int K, int S>
 static int launch_gather(const cgan3d_conv_geom &g, const T *big, const T *wp, const float *bias, T *small,
                          cudaStream_t st) {
   constexpr int VB = 4;
   const int nzg = (g.Zs + VB - 1) / VB;
+  if (g.Cs == 1 && g.Cb % 8 == 0 && (reinterpret_cast<uintptr_t>(big) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0) {
+    const int64_t total = (int64_t)g.B * g.Xs * g.Ys * nzg;
+    gather_co1_kernel<T, K, S, VB><<<(int)((total + 127) / 128), 128, 0, st>>>(g, big, wp, bias, small);
+    CG_LAUNCH_CHECK("conv_gather(generic, Cout=1)");
+    return 0;
+  }
   auto go = [&](auto cob_tag) {
     constexpr int COB = decltype(cob_tag)::value;
     int64_t total = (int64_t)g.B * g.Xs * g.Ys * nzg * (g.Cs / COB);
@@ -150,6 +241,85 @@ scatter_kernel(cgan3d_conv_geom g, const T *__restrict__ small, const T *__restr
   T *o = big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * (int64_t)g.Cb + ci0;
 #pragma unroll
   for (int c = 0; c < CIB; ++c) o[c] = from_f<T>(acc[c]);
+}
+
+
+// ------------------------------------------------------------------ scatter, strided (transposed conv / dgrad of a strided conv)
+// one thread: one big-side voxel x CIB channels; filter pre-transposed to [tap][Cs][Cb] so that the CIB weights of
+// one (tap, cs) are one contiguous vector load and the small-side value is a warp-broadcast scalar.
+template <typename T, int K, int S, int CIB>
+__global__ void __launch_bounds__(128)
+scatter_tw_kernel(cgan3d_conv_geom g, const T *__restrict__ small, const T *__restrict__ wt, const float *__restrict__ bias,
+                  T *__restrict__ big) {
+  const int ncib = g.Cb / CIB;
+  const int64_t total = (int64_t)g.B * g.Xb * g.Yb * g.Zb * ncib;
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cib = (int)(idx % ncib); idx /= ncib;
+  const int iz = (int)(idx % g.Zb); idx /= g.Zb;
+  const int iy = (int)(idx % g.Yb); idx /= g.Yb;
+  const int ix = (int)(idx % g.Xb);
+  const int b = (int)(idx / g.Xb);
+  const int ci0 = cib * CIB;
+  float acc[CIB];
+#pragma unroll
+  for (int c = 0; c < CIB; ++c) acc[c] = bias ? bias[ci0 + c] : 0.f;
+  for (int kx = 0; kx < K; ++kx) {
+    const int tx = ix + g.pad - kx;
+    if (tx < 0 || (tx % S) != 0) continue;
+    const int ox = tx / S;
+    if (ox >= g.Xs) continue;
+    for (int ky = 0; ky < K; ++ky) {
+      const int ty = iy + g.pad - ky;
+      if (ty < 0 || (ty % S) != 0) continue;
+      const int oy = ty / S;
+      if (oy >= g.Ys) continue;
+      for (int kz = 0; kz < K; ++kz) {
+        const int tz = iz + g.pad - kz;
+        if (tz < 0 || (tz % S) != 0) continue;
+        const int oz = tz / S;
+        if (oz >= g.Zs) continue;
+        const T *yrow = small + ((((int64_t)b * g.Xs + ox) * g.Ys + oy) * g.Zs + oz) * (int64_t)g.Cs;
+        const T *wrow = wt + (int64_t)((kx * K + ky) * K + kz) * g.Cs * g.Cb + ci0;
+#pragma unroll 4
+        for (int co = 0; co < g.Cs; ++co) {
+          const float yv = to_f(yrow[co]);
+          Vec8<T> w;
+          w.load(wrow + (int64_t)co * g.Cb);
+#pragma unroll
+          for (int c = 0; c < CIB; ++c) acc[c] = fmaf(yv, w.v[c], acc[c]);
+        }
+      }
+    }
+  }
+  T *o = big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * (int64_t)g.Cb + ci0;
+#pragma unroll
+  for (int c = 0; c < CIB; ++c) o[c] = from_f<T>(acc[c]);
+}
+
+// [tap][Cb][Cs] -> [tap][Cs][Cb]
+template <typename T>
+__global__ void transpose_w_kernel(const T *__restrict__ wp, T *__restrict__ wt, int Cb, int Cs, int taps) {
+  const int64_t total = (int64_t)taps * Cb * Cs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cb = (int)(i % Cb);
+    const int cs = (int)((i / Cb) % Cs);
+    const int t = (int)(i / ((int64_t)Cb * Cs));
+    wt[i] = wp[((int64_t)t * Cb + cb) * Cs + cs];
+  }
+}
+
+template <typename T, int K, int S>
+static int launch_scatter_tw(const cgan3d_conv_geom &g, const T *small, const T *wp, const float *bias, T *big, T *ws,
+                             cudaStream_t st) {
+  const int taps = K * K * K;
+  const int64_t nw = (int64_t)taps * g.Cb * g.Cs;
+  transpose_w_kernel<T><<<(int)mn<int64_t>((nw + 255) / 256, 1024), 256, 0, st>>>(wp, ws, g.Cb, g.Cs, taps);
+  CG_LAUNCH_CHECK("transpose_w");
+  const int64_t total = (int64_t)g.B * g.Xb * g.Yb * g.Zb * (g.Cb / 8);
+  scatter_tw_kernel<T, K, S, 8><<<(int)((total + 127) / 128), 128, 0, st>>>(g, small, ws, bias, big);
+  CG_LAUNCH_CHECK("conv_scatter(generic, transposed filter)");
+  return 0;
 }
 
 template <typename T, int K, int S>
@@ -229,6 +399,120 @@ wgrad_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict_
   }
 }
 
+
+// ------------------------------------------------------------------ wgrad, thin side (Cb == 1 or Cs == 1), stride 1
+// The 7^3 first / last convolutions of the generator (343 taps x C channels of output, K = all voxels).
+// One thread owns (dy, c) and all K*K (dx, dz) taps as register accumulators; a block walks output tiles
+// (YT lines x ZT voxels), stages the input halo lines of one dx plane and the dY tile in shared memory (fp32) and
+// slides a K-wide register window along z: per z step 2 LDS feed K FMAs.  Partial sums of all tiles a block
+// processes stay in registers; one atomicAdd per (block, output) at the end.
+template <typename T, int K, int C, bool BIG_MULTI>
+__global__ void __launch_bounds__(((K * C + 31) / 32) * 32)
+wgrad_thin_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict__ small, float *__restrict__ dw) {
+  constexpr int YT = 4, ZT = 64;
+  constexpr int CX = BIG_MULTI ? C : 1, CY = BIG_MULTI ? 1 : C;
+  constexpr int ZH = ZT + K - 1, YH = YT + K - 1;
+  extern __shared__ float sm[];
+  float *xs = sm;                      // [YH][ZH][CX]
+  float *dys = sm + YH * ZH * CX;      // [YT][ZT][CY]
+  const int tid = threadIdx.x;
+  const bool active = tid < K * C;
+  const int c = tid % C, dy = tid / C;
+  float acc[K][K];
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int d = 0; d < K; ++d) acc[a][d] = 0.f;
+  const int nyt = (g.Ys + YT - 1) / YT, nzt = (g.Zs + ZT - 1) / ZT;
+  const int64_t ntiles = (int64_t)g.B * g.Xs * nyt * nzt;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int64_t t = tile;
+    const int zt = (int)(t % nzt); t /= nzt;
+    const int yt = (int)(t % nyt); t /= nyt;
+    const int ox = (int)(t % g.Xs);
+    const int b = (int)(t / g.Xs);
+    const int oy0 = yt * YT, oz0 = zt * ZT;
+    __syncthreads();
+    for (int i = tid; i < YT * ZT * CY; i += blockDim.x) {
+      const int cc = i % CY, z = (i / CY) % ZT, y = i / (CY * ZT);
+      const int oy = oy0 + y, oz = oz0 + z;
+      float v = 0.f;
+      if (oy < g.Ys && oz < g.Zs) v = to_f(small[((((int64_t)b * g.Xs + ox) * g.Ys + oy) * g.Zs + oz) * CY + cc]);
+      dys[i] = v;
+    }
+#pragma unroll 1
+    for (int dx = 0; dx < K; ++dx) {
+      const int ix = ox - g.pad + dx;
+      __syncthreads();
+      for (int i = tid; i < YH * ZH * CX; i += blockDim.x) {
+        const int cc = i % CX, z = (i / CX) % ZH, y = i / (CX * ZH);
+        const int iy = oy0 - g.pad + y, iz = oz0 - g.pad + z;
+        float v = 0.f;
+        if ((unsigned)ix < (unsigned)g.Xb && (unsigned)iy < (unsigned)g.Yb && (unsigned)iz < (unsigned)g.Zb)
+          v = to_f(big[((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * CX + cc]);
+        xs[i] = v;
+      }
+      __syncthreads();
+      if (active) {
+        float a[K];
+#pragma unroll
+        for (int d = 0; d < K; ++d) a[d] = 0.f;
+#pragma unroll 1
+        for (int y = 0; y < YT; ++y) {
+          const float *xl = xs + ((y + dy) * ZH) * CX + (BIG_MULTI ? c : 0);
+          const float *dl = dys + (y * ZT) * CY + (BIG_MULTI ? 0 : c);
+          float w[K];
+#pragma unroll
+          for (int d = 0; d < K - 1; ++d) w[d] = xl[d * CX];
+#pragma unroll 7
+          for (int z = 0; z < ZT; ++z) {
+            w[K - 1] = xl[(z + K - 1) * CX];
+            const float dv = dl[z * CY];
+#pragma unroll
+            for (int d = 0; d < K; ++d) a[d] = fmaf(w[d], dv, a[d]);
+#pragma unroll
+            for (int d = 0; d < K - 1; ++d) w[d] = w[d + 1];
+          }
+        }
+        // fold this plane's sums into the dx-indexed accumulators without dynamic register indexing
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+          if (q == dx) {
+#pragma unroll
+            for (int d = 0; d < K; ++d) acc[q][d] += a[d];
+          }
+      }
+    }
+  }
+  if (active) {
+    constexpr int taps = K * K * K;
+#pragma unroll
+    for (int dx = 0; dx < K; ++dx)
+#pragma unroll
+      for (int dz = 0; dz < K; ++dz) atomicAdd(&dw[(int64_t)c * taps + (dx * K + dy) * K + dz], acc[dx][dz]);
+  }
+}
+
+template <typename T, int K, int C, bool BIG_MULTI>
+static int launch_wgrad_thin(const cgan3d_conv_geom &g, const T *big, const T *small, float *dw, cudaStream_t st) {
+  constexpr int YT = 4, ZT = 64, CX = BIG_MULTI ? C : 1, CY = BIG_MULTI ? 1 : C;
+  constexpr int threads = ((K * C + 31) / 32) * 32;
+  const size_t smem = ((size_t)(YT + K - 1) * (ZT + K - 1) * CX + (size_t)YT * ZT * CY) * sizeof(float);
+  auto kern = wgrad_thin_kernel<T, K, C, BIG_MULTI>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(wgrad_thin)");
+    attr = true;
+  }
+  const int per_sm = (int)mx<size_t>(1, mn<size_t>(6, (size_t)200000 / (smem + 1024)));
+  const int64_t ntiles = (int64_t)g.B * g.Xs * ((g.Ys + YT - 1) / YT) * ((g.Zs + ZT - 1) / ZT);
+  const int grid = (int)mn<int64_t>(ntiles, (int64_t)num_sms() * per_sm);
+  kern<<<grid, threads, smem, st>>>(g, big, small, dw);
+  CG_LAUNCH_CHECK("conv_wgrad(thin)");
+  return 0;
+}
+
 template <typename T, int K, int S>
 static int launch_wgrad(const cgan3d_conv_geom &g, const T *big, const T *small, float *dw, float beta,
                         cudaStream_t st) {
@@ -237,6 +521,12 @@ static int launch_wgrad(const cgan3d_conv_geom &g, const T *big, const T *small,
   if (beta == 0.f) {
     cudaError_t e = cudaMemsetAsync(dw, 0, n_w * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad memset");
+  }
+  if constexpr (S == 1 && K >= 5) {
+    if (g.Cb == 1 && g.Cs == 16) return launch_wgrad_thin<T, K, 16, false>(g, big, small, dw, st);
+    if (g.Cb == 16 && g.Cs == 1) return launch_wgrad_thin<T, K, 16, true>(g, big, small, dw, st);
+    if (g.Cb == 1 && g.Cs == 8) return launch_wgrad_thin<T, K, 8, false>(g, big, small, dw, st);
+    if (g.Cb == 8 && g.Cs == 1) return launch_wgrad_thin<T, K, 8, true>(g, big, small, dw, st);
   }
   const int64_t n_vox = (int64_t)g.B * g.Xs * g.Ys * g.Zs;
   int chunks = (int)mn<int64_t>(mx<int64_t>(1, (int64_t)num_sms() * 8 / taps), mx<int64_t>(1, n_vox / 64));
@@ -301,8 +591,52 @@ int generic_gather(const cgan3d_conv_geom &g, int dtype, const void *big, const 
   return dtype == CGAN3D_F32 ? gather_t<float>(g, big, wp, bias, small, st)
                              : gather_t<__nv_bfloat16>(g, big, wp, bias, small, st);
 }
+// [tap][Cb][Cs] -> [taps-1-tap][Cs][Cb]
+template <typename T>
+__global__ void flip_transpose_kernel(const T *__restrict__ wp, T *__restrict__ wf, int Cb, int Cs, int taps) {
+  const int64_t total = (int64_t)taps * Cb * Cs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cb = (int)(i % Cb);
+    const int cs = (int)((i / Cb) % Cs);
+    const int t = (int)(i / ((int64_t)Cb * Cs));
+    wf[i] = wp[((int64_t)(taps - 1 - t) * Cb + cb) * Cs + cs];
+  }
+}
+
+size_t generic_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (op == 1) return (size_t)g.k * g.k * g.k * g.Cb * g.Cs * (dtype == CGAN3D_F32 ? 4 : 2) + 16;
+  return 0;
+}
+
+template <typename T>
+static int scatter_tw_t(const cgan3d_conv_geom &g, const void *small, const void *wp, const float *bias, void *big, void *ws,
+                        cudaStream_t st) {
+  CG_KS_DISPATCH(launch_scatter_tw, g, (const T *)small, (const T *)wp, bias, (T *)big, (T *)ws, st);
+}
+
 int generic_scatter(const cgan3d_conv_geom &g, int dtype, const void *small, const void *wp, const float *bias,
-                    void *big, cudaStream_t st) {
+                    void *big, void *ws, size_t ws_bytes, cudaStream_t st) {
+  if (g.stride == 1 && ws != nullptr && ws_bytes >= generic_workspace_bytes(g, dtype, 1) &&
+      (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+    // dgrad of a stride-1 conv == conv of the small side with the flipped filter, pad' = k-1-pad (register-tiled gather)
+    const int taps = g.k * g.k * g.k;
+    const int64_t total = (int64_t)taps * g.Cb * g.Cs;
+    const int blocks = (int)mn<int64_t>((total + 255) / 256, 1024);
+    if (dtype == CGAN3D_F32)
+      flip_transpose_kernel<float><<<blocks, 256, 0, st>>>((const float *)wp, (float *)ws, g.Cb, g.Cs, taps);
+    else
+      flip_transpose_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16 *)wp, (__nv_bfloat16 *)ws, g.Cb, g.Cs, taps);
+    CG_LAUNCH_CHECK("flip_transpose");
+    cgan3d_conv_geom f = g;
+    f.Xb = g.Xs; f.Yb = g.Ys; f.Zb = g.Zs; f.Cb = g.Cs;
+    f.Xs = g.Xb; f.Ys = g.Yb; f.Zs = g.Zb; f.Cs = g.Cb;
+    f.pad = g.k - 1 - g.pad;
+    return generic_gather(f, dtype, small, ws, bias, big, st);
+  }
+  if (g.stride > 1 && g.Cb % 8 == 0 && ws != nullptr && ws_bytes >= generic_workspace_bytes(g, dtype, 1) &&
+      (reinterpret_cast<uintptr_t>(ws) & 15) == 0)
+    return dtype == CGAN3D_F32 ? scatter_tw_t<float>(g, small, wp, bias, big, ws, st)
+                               : scatter_tw_t<__nv_bfloat16>(g, small, wp, bias, big, ws, st);
   return dtype == CGAN3D_F32 ? scatter_t<float>(g, small, wp, bias, big, st)
                              : scatter_t<__nv_bfloat16>(g, small, wp, bias, big, st);
 }

@@ -10,7 +10,8 @@ int pack_weights(const float *w, void *packed, int dtype, int Cs, int Cb, int k,
 int generic_gather(const cgan3d_conv_geom &g, int dtype, const void *big, const void *wp, const float *bias,
                    void *small, cudaStream_t st);
 int generic_scatter(const cgan3d_conv_geom &g, int dtype, const void *small, const void *wp, const float *bias,
-                    void *big, cudaStream_t st);
+                    void *big, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t generic_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
 int generic_wgrad(const cgan3d_conv_geom &g, int dtype, const void *big, const void *small, float *dw, float beta,
                   cudaStream_t st);
 int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z, int C, int pad, cudaStream_t st);

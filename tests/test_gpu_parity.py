@@ -410,6 +410,7 @@ TC_CASES = [
     ("ztiled_16_32", 16, 32, 1, (6, 12, 70)),
     ("c128", 128, 128, 1, (9, 16, 16)),
     ("ragged_32_16", 32, 16, 3, (5, 13, 11)),
+    ("c32_to_64", 32, 64, 2, (7, 9, 20)),
 ]
 
 
@@ -437,6 +438,13 @@ def test_tcgen05_conv3_s1_fprop_and_dgrad(case):
     xr = x.clone().requires_grad_(True)
     y_ref = F.conv3d(xr, w, padding=1)
     dx_ref, = torch.autograd.grad(y_ref, xr, gy)
+    if _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 2) == 2:  # tcgen05 wgrad (Cout == 64)
+        dw_tc = ops.conv_wgrad(g, xd, gyd, impl=_lib.IMPL_TC)
+        wr = w.clone().requires_grad_(True)
+        dw_ref, = torch.autograd.grad(F.conv3d(x, wr, padding=1), wr, gy)
+        assert_close32(dw_tc, dw_ref, rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()), msg="wgrad vs ATen")
+    else:
+        assert cout != 64
     for got, gen_, ref, nm in ((y_tc, y_gen, y_ref, "fprop"), (dx_tc, dx_gen, dx_ref, "dgrad")):
         assert torch.isfinite(got.float()).all(), nm
         assert_close32(ncl(got), ref, rtol=8e-3, atol=2e-3, msg=nm + " vs ATen")
