@@ -338,6 +338,22 @@ static int launch_scatter(const cgan3d_conv_geom &g, const T *small, const T *wp
   return 0;
 }
 
+// N consecutive channels as floats; N == 4 uses one 16 B (fp32) / 8 B (bf16) load (callers guarantee alignment: C % 4 == 0)
+template <typename T, int N>
+__device__ __forceinline__ void load_n(const T *p, float (&v)[N]) {
+  if constexpr (N == 4 && sizeof(T) == 4) {
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else if constexpr (N == 4 && sizeof(T) == 2) {
+    const uint2 a = *reinterpret_cast<const uint2 *>(p);
+    v[0] = __uint_as_float(a.x << 16); v[1] = __uint_as_float(a.x & 0xffff0000u);
+    v[2] = __uint_as_float(a.y << 16); v[3] = __uint_as_float(a.y & 0xffff0000u);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = to_f(p[i]);
+  }
+}
+
 // ------------------------------------------------------------------ wgrad
 // grid (taps, chunks); block 256 threads = lanes x (ncb x ncs) output sub-tiles of 4x4 (or 1-wide)
 template <typename T, int K, int S, int CBV, int CSV>
@@ -361,29 +377,32 @@ wgrad_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict_
   for (int a = 0; a < CBV; ++a)
 #pragma unroll
     for (int c = 0; c < CSV; ++c) acc[a][c] = 0.f;
-  const int64_t n_vox = (int64_t)g.B * g.Xs * g.Ys * g.Zs;
-  const int64_t v0 = blockIdx.y * vox_per_chunk;
-  const int64_t v1 = min(n_vox, v0 + vox_per_chunk);
+  // a chunk is a range of output lines (b, ox, oy); lanes stride over z inside a line, so the index decomposition
+  // (integer divisions) happens once per line instead of once per voxel
+  const int64_t n_lines = (int64_t)g.B * g.Xs * g.Ys;
+  const int64_t l0 = blockIdx.y * vox_per_chunk;
+  const int64_t l1 = min(n_lines, l0 + vox_per_chunk);
   if (lane < lanes) {
-    for (int64_t v = v0 + lane; v < v1; v += lanes) {
-      int64_t t = v;
-      const int oz = (int)(t % g.Zs); t /= g.Zs;
-      const int oy = (int)(t % g.Ys); t /= g.Ys;
+    for (int64_t l = l0; l < l1; ++l) {
+      const int oy = (int)(l % g.Ys);
+      const int64_t t = l / g.Ys;
       const int ox = (int)(t % g.Xs);
       const int b = (int)(t / g.Xs);
-      const int ix = ox * S - g.pad + kx, iy = oy * S - g.pad + ky, iz = oz * S - g.pad + kz;
-      if ((unsigned)ix >= (unsigned)g.Xb || (unsigned)iy >= (unsigned)g.Yb || (unsigned)iz >= (unsigned)g.Zb) continue;
-      const T *xr = big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * (int64_t)g.Cb + cb0;
-      const T *yr = small + v * (int64_t)g.Cs + cs0;
-      float xv[CBV], yv[CSV];
+      const int ix = ox * S - g.pad + kx, iy = oy * S - g.pad + ky;
+      if ((unsigned)ix >= (unsigned)g.Xb || (unsigned)iy >= (unsigned)g.Yb) continue;
+      const T *xline = big + (((int64_t)b * g.Xb + ix) * g.Yb + iy) * (int64_t)g.Zb * g.Cb + cb0;
+      const T *yline = small + l * (int64_t)g.Zs * g.Cs + cs0;
+      for (int oz = lane; oz < g.Zs; oz += lanes) {
+        const int iz = oz * S - g.pad + kz;
+        if ((unsigned)iz >= (unsigned)g.Zb) continue;
+        float xv[CBV], yv[CSV];
+        load_n<T, CBV>(xline + (int64_t)iz * g.Cb, xv);
+        load_n<T, CSV>(yline + (int64_t)oz * g.Cs, yv);
 #pragma unroll
-      for (int a = 0; a < CBV; ++a) xv[a] = to_f(xr[a]);
+        for (int a = 0; a < CBV; ++a)
 #pragma unroll
-      for (int c = 0; c < CSV; ++c) yv[c] = to_f(yr[c]);
-#pragma unroll
-      for (int a = 0; a < CBV; ++a)
-#pragma unroll
-        for (int c = 0; c < CSV; ++c) acc[a][c] = fmaf(xv[a], yv[c], acc[a][c]);
+          for (int c = 0; c < CSV; ++c) acc[a][c] = fmaf(xv[a], yv[c], acc[a][c]);
+      }
     }
 #pragma unroll
     for (int a = 0; a < CBV; ++a)
@@ -444,13 +463,28 @@ wgrad_thin_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__rest
     for (int dx = 0; dx < K; ++dx) {
       const int ix = ox - g.pad + dx;
       __syncthreads();
-      for (int i = tid; i < YH * ZH * CX; i += blockDim.x) {
-        const int cc = i % CX, z = (i / CX) % ZH, y = i / (CX * ZH);
-        const int iy = oy0 - g.pad + y, iz = oz0 - g.pad + z;
-        float v = 0.f;
-        if ((unsigned)ix < (unsigned)g.Xb && (unsigned)iy < (unsigned)g.Yb && (unsigned)iz < (unsigned)g.Zb)
-          v = to_f(big[((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * CX + cc]);
-        xs[i] = v;
+      if constexpr (CX % 8 == 0) {  // 8 channels (16 B of bf16 / 32 B of fp32) per load
+        for (int i = tid; i < YH * ZH * (CX / 8); i += blockDim.x) {
+          const int c8 = i % (CX / 8), z = (i / (CX / 8)) % ZH, y = i / ((CX / 8) * ZH);
+          const int iy = oy0 - g.pad + y, iz = oz0 - g.pad + z;
+          Vec8<T> v;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v.v[k] = 0.f;
+          if ((unsigned)ix < (unsigned)g.Xb && (unsigned)iy < (unsigned)g.Yb && (unsigned)iz < (unsigned)g.Zb)
+            v.load(big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * CX + c8 * 8);
+          float4 *d = reinterpret_cast<float4 *>(xs + (y * ZH + z) * CX + c8 * 8);
+          d[0] = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+          d[1] = make_float4(v.v[4], v.v[5], v.v[6], v.v[7]);
+        }
+      } else {
+        for (int i = tid; i < YH * ZH * CX; i += blockDim.x) {
+          const int cc = i % CX, z = (i / CX) % ZH, y = i / (CX * ZH);
+          const int iy = oy0 - g.pad + y, iz = oz0 - g.pad + z;
+          float v = 0.f;
+          if ((unsigned)ix < (unsigned)g.Xb && (unsigned)iy < (unsigned)g.Yb && (unsigned)iz < (unsigned)g.Zb)
+            v = to_f(big[((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * CX + cc]);
+          xs[i] = v;
+        }
       }
       __syncthreads();
       if (active) {
@@ -528,10 +562,10 @@ static int launch_wgrad(const cgan3d_conv_geom &g, const T *big, const T *small,
     if (g.Cb == 1 && g.Cs == 8) return launch_wgrad_thin<T, K, 8, false>(g, big, small, dw, st);
     if (g.Cb == 8 && g.Cs == 1) return launch_wgrad_thin<T, K, 8, true>(g, big, small, dw, st);
   }
-  const int64_t n_vox = (int64_t)g.B * g.Xs * g.Ys * g.Zs;
-  int chunks = (int)mn<int64_t>(mx<int64_t>(1, (int64_t)num_sms() * 8 / taps), mx<int64_t>(1, n_vox / 64));
+  const int64_t n_lines = (int64_t)g.B * g.Xs * g.Ys;
+  int chunks = (int)mn<int64_t>(mx<int64_t>(1, (int64_t)num_sms() * 8 / taps), n_lines);
   chunks = min(chunks, 65535);
-  const int64_t vpc = (n_vox + chunks - 1) / chunks;
+  const int64_t vpc = (n_lines + chunks - 1) / chunks;  // lines per chunk
   auto go = [&](auto tcb_tag, auto tcs_tag) {
     constexpr int CBV = decltype(tcb_tag)::value;
     constexpr int CSV = decltype(tcs_tag)::value;

@@ -120,6 +120,192 @@ bias_act_bwd_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__rest
   });
 }
 
+
+// ---------------------------------------------------------------- 8-wide vector access (C % 8 == 0 fast paths)
+template <typename T>
+struct V8;
+template <>
+struct V8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float *p) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float *p) const {
+    reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct V8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16 *p) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16 *p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// vectorised column reduction: thread (lane, c8) owns 8 adjacent channels; f(row, c0, out[NS][8])
+template <int NS, typename F>
+__device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, int rows_per_block, double *sums, F f) {
+  extern __shared__ double sh[];  // [lanes][NS][C]
+  const int C8 = C >> 3;
+  const int lanes = blockDim.x / C8;
+  const int lane = threadIdx.x / C8;
+  const int c0 = (threadIdx.x % C8) * 8;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(n_rows, r0 + rows_per_block);
+  double tot[NS][8];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot[s][k] = 0.0;
+  if (lane < lanes) {
+    float part[NS][8];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part[s][k] = 0.f;
+    int run = 0;
+    for (int64_t r = r0 + lane; r < r1; r += lanes) {
+      float v[NS][8];
+      f(r, c0, v);
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part[s][k] += v[s][k];
+      if (++run == 32) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { tot[s][k] += (double)part[s][k]; part[s][k] = 0.f; }
+        run = 0;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot[s][k] += (double)part[s][k];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sh[((size_t)lane * NS + s) * C + c0 + k] = tot[s][k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NS * C; i += blockDim.x) {
+    double a = 0.0;
+    for (int l = 0; l < lanes; ++l) a += sh[(size_t)l * NS * C + i];
+    atomicAdd(&sums[i], a);
+  }
+}
+
+static bool vec8_ok(int C, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr) {
+  auto al = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return C % 8 == 0 && C <= 2048 && al(a) && al(b) && al(c) && al(d);
+}
+static ColGrid col_grid8(int64_t n_rows, int C, int ns) {
+  const int lanes = 256 / (C >> 3);
+  int64_t target_blocks = (int64_t)num_sms() * 8;
+  int64_t rpb = (n_rows + target_blocks - 1) / target_blocks;
+  rpb = mx<int64_t>(rpb, (int64_t)lanes * 4);
+  rpb = ((rpb + lanes - 1) / lanes) * lanes;
+  ColGrid g;
+  g.rows_per_block = (int)mn<int64_t>(rpb, 1 << 30);
+  g.blocks = (int)((n_rows + g.rows_per_block - 1) / g.rows_per_block);
+  g.smem = (size_t)ns * lanes * C * sizeof(double);
+  return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats8_kernel(const T *__restrict__ y, int64_t n_rows, int C, int rpb, double *sums) {
+  col_reduce8_body<2>(n_rows, C, rpb, sums, [&](int64_t r, int c0, float (&v)[2][8]) {
+    V8<T> x;
+    x.load(y + r * C + c0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[0][k] = x.v[k]; v[1][k] = x.v[k] * x.v[k]; }
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t n_rows, int C, int rpb,
+                      const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
+                      float slope, double *sums) {
+  col_reduce8_body<2>(n_rows, C, rpb, sums, [&](int64_t r, int c0, float (&v)[2][8]) {
+    V8<T> yy, dd;
+    yy.load(y + r * C + c0);
+    dd.load(dz + r * C + c0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      const float xh = (yy.v[k] - mi[c]) * mi[C + c];
+      const float g = dd.v[k] * act_bwd(gamma[c] * xh + beta[c], act, slope);
+      v[0][k] = g;
+      v[1][k] = g * xh;
+    }
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply8_kernel(const T *__restrict__ y, T *__restrict__ z, int64_t total8, int C, const float *__restrict__ mi,
+                 const float *__restrict__ gamma, const float *__restrict__ beta, int act, float slope,
+                 const T *__restrict__ residual) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 8;
+    const int c0 = (int)(e % C);
+    V8<T> v, r;
+    v.load(y + e);
+    if (residual) r.load(residual + e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      float t = act_fwd(gamma[c] * ((v.v[k] - mi[c]) * mi[C + c]) + beta[c], act, slope);
+      if (residual) t += r.v[k];
+      v.v[k] = t;
+    }
+    v.store(z + e);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t total8, int C, double inv_n,
+                     const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
+                     float slope, const double *__restrict__ sums) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 8;
+    const int c0 = (int)(e % C);
+    V8<T> yy, dd;
+    yy.load(y + e);
+    dd.load(dz + e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      const float invstd = mi[C + c];
+      const float xh = (yy.v[k] - mi[c]) * invstd;
+      const float g = dd.v[k] * act_bwd(gamma[c] * xh + beta[c], act, slope);
+      const float mg = (float)(sums[c] * inv_n), mgx = (float)(sums[C + c] * inv_n);
+      dd.v[k] = gamma[c] * invstd * (g - mg - xh * mgx);
+    }
+    dd.store(dy + e);
+  }
+}
+
 // ---------------------------------------------------------------- finalize
 __global__ void bn_finalize_kernel(const double *__restrict__ sums, int64_t n, int C, float eps, float momentum,
                                    float *__restrict__ mi, float *running_mean, float *running_var,
@@ -266,6 +452,15 @@ int cgan3d_bn_stats(const void *y, int dtype, int64_t n_rows, int C, double *sum
   cudaError_t e = cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "bn_stats memset");
   if (n_rows == 0) return 0;
+  if (vec8_ok(C, y)) {
+    ColGrid g8 = col_grid8(n_rows, C, 2);
+    if (dtype == CGAN3D_F32)
+      bn_stats8_kernel<float><<<g8.blocks, 256, g8.smem, st>>>((const float *)y, n_rows, C, g8.rows_per_block, sums);
+    else
+      bn_stats8_kernel<__nv_bfloat16><<<g8.blocks, 256, g8.smem, st>>>((const __nv_bfloat16 *)y, n_rows, C, g8.rows_per_block, sums);
+    CG_LAUNCH_CHECK("bn_stats(vec8)");
+    return 0;
+  }
   ColGrid g = col_grid(n_rows, C, 2);
   if (dtype == CGAN3D_F32)
     bn_stats_kernel<float><<<g.blocks, 256, g.smem, st>>>((const float *)y, n_rows, C, g.rows_per_block, sums);
@@ -327,6 +522,17 @@ int cgan3d_bn_apply(const void *y, void *z, int dtype, int64_t n_rows, int C, co
   const int64_t total = n_rows * C;
   if (total == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (vec8_ok(C, y, z, residual)) {
+    const int64_t t8 = total / 8;
+    if (dtype == CGAN3D_F32)
+      bn_apply8_kernel<float><<<ew_blocks(t8), 256, 0, st>>>((const float *)y, (float *)z, t8, C, mean_invstd, gamma, beta, act,
+                                                             slope, (const float *)residual);
+    else
+      bn_apply8_kernel<__nv_bfloat16><<<ew_blocks(t8), 256, 0, st>>>((const __nv_bfloat16 *)y, (__nv_bfloat16 *)z, t8, C, mean_invstd,
+                                                                     gamma, beta, act, slope, (const __nv_bfloat16 *)residual);
+    CG_LAUNCH_CHECK("bn_apply(vec8)");
+    return 0;
+  }
   if (dtype == CGAN3D_F32)
     bn_apply_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)y, (float *)z, total, C, mean_invstd, gamma,
                                                              beta, act, slope, (const float *)residual);
@@ -346,6 +552,17 @@ int cgan3d_bn_backward_reduce(const void *dz, const void *y, int dtype, int64_t 
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "bn_backward_reduce memset");
+  if (vec8_ok(C, dz, y)) {
+    ColGrid g8 = col_grid8(n_rows, C, 2);
+    if (dtype == CGAN3D_F32)
+      bn_bwd_reduce8_kernel<float><<<g8.blocks, 256, g8.smem, st>>>((const float *)dz, (const float *)y, n_rows, C,
+                                                                   g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums);
+    else
+      bn_bwd_reduce8_kernel<__nv_bfloat16><<<g8.blocks, 256, g8.smem, st>>>(
+          (const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y, n_rows, C, g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums);
+    CG_LAUNCH_CHECK("bn_backward_reduce(vec8)");
+    return 0;
+  }
   ColGrid g = col_grid(n_rows, C, 2);
   if (dtype == CGAN3D_F32)
     bn_bwd_reduce_kernel<float><<<g.blocks, 256, g.smem, st>>>((const float *)dz, (const float *)y, n_rows, C,
@@ -367,7 +584,17 @@ int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype,
   cudaStream_t st = as_stream(stream);
   const int64_t total = n_rows * C;
   const double inv_n = 1.0 / (double)n_rows;
-  if (dtype == CGAN3D_F32)
+  if (vec8_ok(C, dz, y, dy)) {
+    const int64_t t8 = total / 8;
+    if (dtype == CGAN3D_F32)
+      bn_bwd_apply8_kernel<float><<<ew_blocks(t8), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, t8, C, inv_n,
+                                                                 mean_invstd, gamma, beta, act, slope, sums);
+    else
+      bn_bwd_apply8_kernel<__nv_bfloat16><<<ew_blocks(t8), 256, 0, st>>>((const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y,
+                                                                         (__nv_bfloat16 *)dy, t8, C, inv_n, mean_invstd, gamma,
+                                                                         beta, act, slope, sums);
+    CG_LAUNCH_CHECK("bn_backward_apply(vec8)");
+  } else if (dtype == CGAN3D_F32)
     bn_bwd_apply_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, total, C,
                                                                  inv_n, mean_invstd, gamma, beta, act, slope, sums);
   else
