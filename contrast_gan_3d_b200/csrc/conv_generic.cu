@@ -175,8 +175,9 @@ static int launch_gather(const cgan3d_conv_geom &g, const T *big, const T *wp, c
   constexpr int VB = 4;
   const int nzg = (g.Zs + VB - 1) / VB;
   if (g.Cs == 1 && g.Cb % 8 == 0 && (reinterpret_cast<uintptr_t>(big) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0) {
-    const int64_t total = (int64_t)g.B * g.Xs * g.Ys * nzg;
-    gather_co1_kernel<T, K, S, VB><<<(int)((total + 127) / 128), 128, 0, st>>>(g, big, wp, bias, small);
+    constexpr int VB1 = 8;
+    const int64_t total = (int64_t)g.B * g.Xs * g.Ys * ((g.Zs + VB1 - 1) / VB1);
+    gather_co1_kernel<T, K, S, VB1><<<(int)((total + 127) / 128), 128, 0, st>>>(g, big, wp, bias, small);
     CG_LAUNCH_CHECK("conv_gather(generic, Cout=1)");
     return 0;
   }
@@ -348,6 +349,11 @@ __device__ __forceinline__ void load_n(const T *p, float (&v)[N]) {
     const uint2 a = *reinterpret_cast<const uint2 *>(p);
     v[0] = __uint_as_float(a.x << 16); v[1] = __uint_as_float(a.x & 0xffff0000u);
     v[2] = __uint_as_float(a.y << 16); v[3] = __uint_as_float(a.y & 0xffff0000u);
+  } else if constexpr (N == 8) {
+    Vec8<T> t;
+    t.load(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t.v[i];
   } else {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = to_f(p[i]);
@@ -425,12 +431,12 @@ wgrad_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict_
 // (YT lines x ZT voxels), stages the input halo lines of one dx plane and the dY tile in shared memory (fp32) and
 // slides a K-wide register window along z: per z step 2 LDS feed K FMAs.  Partial sums of all tiles a block
 // processes stay in registers; one atomicAdd per (block, output) at the end.
-template <typename T, int K, int C, bool BIG_MULTI>
+template <typename T, int K, int S, int C, bool BIG_MULTI>
 __global__ void __launch_bounds__(((K * C + 31) / 32) * 32)
 wgrad_thin_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict__ small, float *__restrict__ dw) {
-  constexpr int YT = 4, ZT = 64;
+  constexpr int YT = 4, ZT = S == 1 ? 64 : 32;
   constexpr int CX = BIG_MULTI ? C : 1, CY = BIG_MULTI ? 1 : C;
-  constexpr int ZH = ZT + K - 1, YH = YT + K - 1;
+  constexpr int ZH = (ZT - 1) * S + K, YH = (YT - 1) * S + K;
   extern __shared__ float sm[];
   float *xs = sm;                      // [YH][ZH][CX]
   float *dys = sm + YH * ZH * CX;      // [YT][ZT][CY]
@@ -461,12 +467,12 @@ wgrad_thin_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__rest
     }
 #pragma unroll 1
     for (int dx = 0; dx < K; ++dx) {
-      const int ix = ox - g.pad + dx;
+      const int ix = ox * S - g.pad + dx;
       __syncthreads();
       if constexpr (CX % 8 == 0) {  // 8 channels (16 B of bf16 / 32 B of fp32) per load
         for (int i = tid; i < YH * ZH * (CX / 8); i += blockDim.x) {
           const int c8 = i % (CX / 8), z = (i / (CX / 8)) % ZH, y = i / ((CX / 8) * ZH);
-          const int iy = oy0 - g.pad + y, iz = oz0 - g.pad + z;
+          const int iy = oy0 * S - g.pad + y, iz = oz0 * S - g.pad + z;
           Vec8<T> v;
 #pragma unroll
           for (int k = 0; k < 8; ++k) v.v[k] = 0.f;
@@ -479,7 +485,7 @@ wgrad_thin_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__rest
       } else {
         for (int i = tid; i < YH * ZH * CX; i += blockDim.x) {
           const int cc = i % CX, z = (i / CX) % ZH, y = i / (CX * ZH);
-          const int iy = oy0 - g.pad + y, iz = oz0 - g.pad + z;
+          const int iy = oy0 * S - g.pad + y, iz = oz0 * S - g.pad + z;
           float v = 0.f;
           if ((unsigned)ix < (unsigned)g.Xb && (unsigned)iy < (unsigned)g.Yb && (unsigned)iz < (unsigned)g.Zb)
             v = to_f(big[((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * CX + cc]);
@@ -493,19 +499,20 @@ wgrad_thin_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__rest
         for (int d = 0; d < K; ++d) a[d] = 0.f;
 #pragma unroll 1
         for (int y = 0; y < YT; ++y) {
-          const float *xl = xs + ((y + dy) * ZH) * CX + (BIG_MULTI ? c : 0);
+          const float *xl = xs + ((y * S + dy) * ZH) * CX + (BIG_MULTI ? c : 0);
           const float *dl = dys + (y * ZT) * CY + (BIG_MULTI ? 0 : c);
           float w[K];
 #pragma unroll
-          for (int d = 0; d < K - 1; ++d) w[d] = xl[d * CX];
+          for (int d = 0; d < K - S; ++d) w[d] = xl[d * CX];
 #pragma unroll 7
           for (int z = 0; z < ZT; ++z) {
-            w[K - 1] = xl[(z + K - 1) * CX];
+#pragma unroll
+            for (int q = 0; q < S; ++q) w[K - S + q] = xl[(z * S + K - S + q) * CX];
             const float dv = dl[z * CY];
 #pragma unroll
             for (int d = 0; d < K; ++d) a[d] = fmaf(w[d], dv, a[d]);
 #pragma unroll
-            for (int d = 0; d < K - 1; ++d) w[d] = w[d + 1];
+            for (int d = 0; d < K - S; ++d) w[d] = w[d + S];
           }
         }
         // fold this plane's sums into the dx-indexed accumulators without dynamic register indexing
@@ -527,12 +534,12 @@ wgrad_thin_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__rest
   }
 }
 
-template <typename T, int K, int C, bool BIG_MULTI>
+template <typename T, int K, int S, int C, bool BIG_MULTI>
 static int launch_wgrad_thin(const cgan3d_conv_geom &g, const T *big, const T *small, float *dw, cudaStream_t st) {
-  constexpr int YT = 4, ZT = 64, CX = BIG_MULTI ? C : 1, CY = BIG_MULTI ? 1 : C;
+  constexpr int YT = 4, ZT = S == 1 ? 64 : 32, CX = BIG_MULTI ? C : 1, CY = BIG_MULTI ? 1 : C;
   constexpr int threads = ((K * C + 31) / 32) * 32;
-  const size_t smem = ((size_t)(YT + K - 1) * (ZT + K - 1) * CX + (size_t)YT * ZT * CY) * sizeof(float);
-  auto kern = wgrad_thin_kernel<T, K, C, BIG_MULTI>;
+  const size_t smem = ((size_t)((YT - 1) * S + K) * ((ZT - 1) * S + K) * CX + (size_t)YT * ZT * CY) * sizeof(float);
+  auto kern = wgrad_thin_kernel<T, K, S, C, BIG_MULTI>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -556,11 +563,11 @@ static int launch_wgrad(const cgan3d_conv_geom &g, const T *big, const T *small,
     cudaError_t e = cudaMemsetAsync(dw, 0, n_w * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad memset");
   }
-  if constexpr (S == 1 && K >= 5) {
-    if (g.Cb == 1 && g.Cs == 16) return launch_wgrad_thin<T, K, 16, false>(g, big, small, dw, st);
-    if (g.Cb == 16 && g.Cs == 1) return launch_wgrad_thin<T, K, 16, true>(g, big, small, dw, st);
-    if (g.Cb == 1 && g.Cs == 8) return launch_wgrad_thin<T, K, 8, false>(g, big, small, dw, st);
-    if (g.Cb == 8 && g.Cs == 1) return launch_wgrad_thin<T, K, 8, true>(g, big, small, dw, st);
+  if constexpr (K >= 4) {
+    if (g.Cb == 1 && g.Cs == 16) return launch_wgrad_thin<T, K, S, 16, false>(g, big, small, dw, st);
+    if (g.Cb == 16 && g.Cs == 1) return launch_wgrad_thin<T, K, S, 16, true>(g, big, small, dw, st);
+    if (g.Cb == 1 && g.Cs == 8) return launch_wgrad_thin<T, K, S, 8, false>(g, big, small, dw, st);
+    if (g.Cb == 8 && g.Cs == 1) return launch_wgrad_thin<T, K, S, 8, true>(g, big, small, dw, st);
   }
   const int64_t n_lines = (int64_t)g.B * g.Xs * g.Ys;
   int chunks = (int)mn<int64_t>(mx<int64_t>(1, (int64_t)num_sms() * 8 / taps), n_lines);
@@ -580,7 +587,9 @@ static int launch_wgrad(const cgan3d_conv_geom &g, const T *big, const T *small,
       }
   };
   const bool b4 = g.Cb % 4 == 0, s4 = g.Cs % 4 == 0;
-  if (b4 && s4) go(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
+  const bool al16 = (reinterpret_cast<uintptr_t>(big) & 15) == 0 && (reinterpret_cast<uintptr_t>(small) & 15) == 0;
+  if (g.Cb % 8 == 0 && g.Cs % 8 == 0 && al16) go(std::integral_constant<int, 8>{}, std::integral_constant<int, 8>{});
+  else if (b4 && s4) go(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
   else if (b4) go(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
   else if (s4) go(std::integral_constant<int, 1>{}, std::integral_constant<int, 4>{});
   else go(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});

@@ -172,6 +172,14 @@ class Trainer:
             self.lr_scheduler_G.step()
         return {"G": loss_G, "G-full": full_loss_G, "sim": loss_sim, "HU": loss_hu}
 
+    def _upload_cat(self, a: Tensor, b: Tensor) -> Tensor:
+        """torch.cat([a, b]).to(device) (reference Trainer.py:166,182) without the pageable host-side concatenation:
+        each part goes straight from its (pinned) host buffer into its slice of one device tensor."""
+        out = torch.empty((a.shape[0] + b.shape[0], *a.shape[1:]), dtype=a.dtype, device=self.device)
+        out[: a.shape[0]].copy_(a, non_blocking=True)
+        out[a.shape[0]:].copy_(b, non_blocking=True)
+        return out
+
     def _generate(self, subopt: Tensor):
         if hasattr(self.generator, "forward_corrected"):
             return self.generator.forward_corrected(subopt)
@@ -181,7 +189,7 @@ class Trainer:
     def train_step(self, patches: List[dict], iteration: int) -> Dict[str, Tensor]:
         opt, low, high = patches
         opt_t: Tensor = opt["data"].to(self.device, non_blocking=True)
-        subopt = torch.cat([low["data"], high["data"]]).to(self.device, non_blocking=True)
+        subopt = self._upload_cat(low["data"], high["data"])
         attenuation, opt_hat = self._generate(subopt)
 
         do_train_generator = iteration % self.train_generator_every == 0
@@ -189,7 +197,7 @@ class Trainer:
         if iteration % self.train_critic_every == 0:
             log_dict = self.train_critic(opt_t, opt_hat, do_train_generator)
         if do_train_generator:
-            subopt_mask = torch.cat([low["seg"], high["seg"]]).to(self.device, non_blocking=True)
+            subopt_mask = self._upload_cat(low["seg"], high["seg"])
             log_dict |= self.train_generator(subopt, opt_hat, subopt_mask)
 
         if self.log_every and iteration % self.log_every == 0:
