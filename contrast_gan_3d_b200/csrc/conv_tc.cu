@@ -264,6 +264,14 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+void *tc_encode_fn_ptr() { return reinterpret_cast<void *>(encode_fn()); }
+
+// conv_tc_prog.cu
+bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op);
+size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
+int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
+                cudaStream_t st);
+
 static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
   if (N % 16 || N > 256 || N < 16) return false;
   if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
@@ -500,8 +508,8 @@ static bool s1_shape_ok(const cgan3d_conv_geom &g, int dtype, int op) {
 }
 
 bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
-  if (!s1_shape_ok(g, dtype, op)) return false;
   if (!cgan3d_device_supports_tc() || encode_fn() == nullptr) return false;
+  if (!s1_shape_ok(g, dtype, op)) return tc_prog_supported(g, dtype, op);
   if (op == 2) {
     WgPlan w;
     return plan_wgrad(g, w);
@@ -512,7 +520,8 @@ bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
 }
 
 size_t tc_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
-  if (!s1_shape_ok(g, dtype, op) || op == 2) return 0;
+  if (!s1_shape_ok(g, dtype, op)) return tc_prog_workspace_bytes(g, dtype, op);
+  if (op == 2) return 0;
   return (size_t)27 * g.Cb * g.Cs * 2 + 256;
 }
 
@@ -576,12 +585,14 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
 int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const float *bias, void *small, void *ws,
               size_t ws_bytes, cudaStream_t st) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  if (!s1_shape_ok(g, CGAN3D_BF16, 0)) return tc_prog_run(g, 0, big, wp, small, ws, ws_bytes, st);
   return run_s1(g, 0, big, wp, small, ws, ws_bytes, st);
 }
 
 int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, const float *bias, void *big, void *ws,
                size_t ws_bytes, cudaStream_t st) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  if (!s1_shape_ok(g, CGAN3D_BF16, 1)) return tc_prog_run(g, 1, small, wp, big, ws, ws_bytes, st);
   return run_s1(g, 1, small, wp, big, ws, ws_bytes, st);
 }
 

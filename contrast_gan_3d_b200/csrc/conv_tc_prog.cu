@@ -1,0 +1,439 @@
+// tcgen05 implicit GEMM for the STRIDED convolutions (stride 2, k = 3 or 4, pad 1): down-sampling convs of the
+// generator and the critic (gather), ConvTranspose3d up-sampling and the dgrad of strided convs (scatter).
+// Replaces aten::convolution / convolution_backward(input) / conv_transpose3d at reference model/generator.py:40-46,
+// :60-76, model/discriminator.py:48-67 (via model/blocks.py:21-38,52).
+//
+// Both directions are decomposed into stride-1 "flattened-shift" sub-problems on the SMALL grid (see conv_tc.cu for the
+// row-shift idea) and driven by a small host-built TAP PROGRAM:
+//   * gather (small = conv_s2(big)): the big side is sampled by parity class.  For input x-plane 2*ox+dx-1 and class
+//     (q, r) = parity of (y, z), one TMA load with elementStrides (1,2,2,1,1) fetches the sub-slab
+//     y = 2*(y0+yy) - q, z = 2*(z0+zz) - r straight from the dense NDHWC tensor; inside a class every filter tap is a row
+//     shift (0 or +1 line / +1 voxel).  One accumulator.
+//   * scatter (big = conv_s2^T(small)): the 8 output parity phases (p,q,r) are 8 accumulators over the same small-grid
+//     rows; each (phase, tap) pair that exists is one row-shifted MMA group on the small-side slab of plane i+xo.
+//     The epilogue writes phase (p,q,r) of row (i,j,k) to big voxel (2i+p, 2j+q, 2k+r).
+//   * All filter tiles ([Cin/8][N][8] bf16 each) stay RESIDENT in shared memory for the whole kernel (<= 108 KB for
+//     the layers of this model), so the only streamed operand is the activation slab; each slab is released as soon
+//     as its taps are issued (ring of slots, no cross-plane reuse: these layers are L2/HBM-bound).
+#include "common.cuh"
+#include "conv_internal.cuh"
+#include "tc_common.cuh"
+
+namespace cg {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kMaxEntries = 16, kMaxTaps = 64;
+constexpr uint32_t kSmemLimitProg = 232448 - 1024;
+
+struct ProgTap {
+  uint16_t row_shift;  // rows (16 B units) added to the A descriptor start
+  uint8_t btile;       // resident filter tile
+  uint8_t acc;         // accumulator (output phase)
+  uint8_t first;       // 1 = first MMA group into this accumulator (overwrite)
+  uint8_t pad[3];
+};
+struct ProgEntry {
+  int8_t cx, cy, cz;  // TMA start coordinate = scale * tile origin + c*
+  uint8_t ntaps, tap0;
+  uint8_t pad[3];
+};
+struct ProgPlan {
+  int B, Xg, Yg, Zg;     // small ("grid") side extents: rows of every MMA live on this grid
+  int Xo, Yo, Zo;        // output tensor extents
+  int Cin, N, nacc;
+  int in_scale;          // 2: gather from the big side (strided TMA), 1: scatter from the small side
+  int out_scale;         // 1: gather, 2: scatter (output voxel = out_scale*grid + phase)
+  int Zt, nzt, Zh, Yt, nslabs, Yh;
+  int mtiles, rows_alloc, nslots, nbt;
+  int nentries, ntaps;
+  uint32_t slot_bytes, btile_bytes, box_bytes, tmem_cols, smem_bytes;
+  ProgEntry entries[kMaxEntries];
+  ProgTap taps[kMaxTaps];
+};
+
+template <int KSTEPS, int MT>
+__global__ void __launch_bounds__(192, 1)
+conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out,
+                    const __grid_constant__ ProgPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *bres = smem;                                         // resident filter tiles
+  uint8_t *ring = bres + (size_t)p.nbt * p.btile_bytes;         // activation slab slots
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)p.nslots * p.slot_bytes);
+  uint64_t *b_ready = bars, *s_full = bars + 1, *s_empty = s_full + p.nslots;
+  uint64_t *tm_full = s_empty + p.nslots, *tm_empty = tm_full + 2;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tm_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(b_ready, 1);
+    for (int i = 0; i < p.nslots; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) {
+    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // contiguous, balanced range of steps (column-major over (b, z-tile, y-slab) x output plane)
+  const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
+  const int s_begin = (int)(total * blockIdx.x / gridDim.x), s_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  const int kch = p.Cin >> 3;
+  auto decode = [&](int st, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x) {
+    x = st % p.Xg; st /= p.Xg;
+    const int sl = st % p.nslabs; st /= p.nslabs;
+    const int zt = st % p.nzt;
+    b = st / p.nzt;
+    y0 = sl * p.Yt; ylen = min(p.Yt, p.Yg - y0);
+    z0 = zt * p.Zt; zlen = min(p.Zt, p.Zg - z0);
+  };
+
+  if (warp == 4) {
+    // ------------------------------------------------ producer: resident filters once, then the slab stream
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmA);
+      tc::mbar_expect_tx(b_ready, (uint32_t)p.nbt * p.btile_bytes);
+      for (int t = 0; t < p.nbt; ++t)
+        tc::bulk_g2s(bres + (size_t)t * p.btile_bytes, reinterpret_cast<const uint8_t *>(wB) + (size_t)t * p.btile_bytes,
+                     p.btile_bytes, b_ready);
+      uint32_t e = 0;
+      for (int st = s_begin; st < s_end; ++st) {
+        int b, z0, zlen, y0, ylen, x;
+        decode(st, b, z0, zlen, y0, ylen, x);
+        for (int en = 0; en < p.nentries; ++en, ++e) {
+          const ProgEntry &E = p.entries[en];
+          const uint32_t slot = e % p.nslots, use = e / p.nslots;
+          if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
+          tc::mbar_expect_tx(&s_full[slot], p.box_bytes * kch);
+          uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
+          const int cz = p.in_scale * z0 + E.cz, cy = p.in_scale * y0 + E.cy, cx = p.in_scale * x + E.cx;
+          for (int cc = 0; cc < kch; ++cc)
+            tc::tma_load_5d(dst + (size_t)cc * p.rows_alloc * 16, &tmA, &s_full[slot], cc * 8, cz, cy, cx, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
+    const bool leader = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_bf16(128, p.N, 0, 0);
+    const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
+    const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16, b_lbo = (uint32_t)p.N * 16;
+    const uint64_t a_hi = tc::make_desc(0, a_lbo, 128), b_hi = tc::make_desc(0, b_lbo, 128);
+    const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
+    tc::mbar_wait(b_ready, 0);
+    tc::tc_fence_after();
+    uint32_t e = 0, acc = 0;
+    for (int st = s_begin; st < s_end; ++st, ++acc) {
+      const uint32_t q = acc & 1, uq = acc >> 1;
+      if (uq > 0) tc::mbar_wait(&tm_empty[q], (uq - 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t d_base = tmem_base + q * (uint32_t)(p.nacc * MT * p.N);
+      for (int en = 0; en < p.nentries; ++en, ++e) {
+        const ProgEntry &E = p.entries[en];
+        const uint32_t slot = e % p.nslots;
+        tc::mbar_wait(&s_full[slot], (e / p.nslots) & 1);
+        tc::tc_fence_after();
+        const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
+        for (int t = 0; t < E.ntaps; ++t) {
+          const ProgTap &T = p.taps[E.tap0 + t];
+          const uint64_t a0 = a_hi | (uint64_t)((a_slot + T.row_shift) & 0x3FFF);
+          const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)T.btile * p.btile_bytes) >> 4) & 0x3FFF);
+          const uint32_t d0 = d_base + (uint32_t)T.acc * (MT * p.N);
+          const uint32_t keep = T.first ? 0u : 1u;
+          if (leader) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk)
+                tc::umma_bf16(d0 + mt * p.N, a0 + (uint64_t)(mt * 128 + kk * a_kstep), b0 + (uint64_t)(kk * b_kstep), idesc,
+                              (kk != 0) ? 1u : keep);
+            }
+          }
+          __syncwarp();
+        }
+        if (leader) tc::umma_commit(&s_empty[slot]);
+        __syncwarp();
+      }
+      if (leader) tc::umma_commit(&tm_full[q]);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 0..3 <-> TMEM lanes 32*warp..)
+    uint32_t acc = 0;
+    for (int st = s_begin; st < s_end; ++st, ++acc) {
+      int b, z0, zlen, y0, ylen, x;
+      decode(st, b, z0, zlen, y0, ylen, x);
+      const uint32_t q = acc & 1;
+      tc::mbar_wait(&tm_full[q], (acc >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(p.nacc * MT * p.N);
+      for (int a = 0; a < p.nacc; ++a) {
+        const int px = (a >> 2) & 1, py = (a >> 1) & 1, pz = a & 1;
+        const int ox = p.out_scale * x + px;
+        for (int mt = 0; mt < MT; ++mt) {
+          const int r = mt * 128 + warp * 32 + lane;
+          const int gy = r / p.Zh, gz = r - gy * p.Zh;
+          const int oy = p.out_scale * (y0 + gy) + py, oz = p.out_scale * (z0 + gz) + pz;
+          const bool valid = gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo;
+          bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.N;
+          const uint32_t taddr = d_base + (uint32_t)(a * MT + mt) * p.N;
+          for (int c0 = 0; c0 < p.N; c0 += 16) {
+            uint32_t v[16];
+            tc::tmem_ld16(taddr + c0, v);
+            tc::tmem_ld_wait();
+            if (valid) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                pk[j] = *reinterpret_cast<uint32_t *>(&h);
+              }
+              uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
+              d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// [tap][Cb][Cs] (generic packed) -> resident tiles [tap][Cin/8][N][8]; gather: Cin=Cb,N=Cs; scatter: Cin=Cs,N=Cb
+__global__ void repack_prog_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int taps, int scatter) {
+  const int Cin = scatter ? Cs : Cb, N = scatter ? Cb : Cs;
+  const int64_t total = (int64_t)taps * Cin * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i & 7);
+    int64_t t = i >> 3;
+    const int n = (int)(t % N); t /= N;
+    const int cc = (int)(t % (Cin >> 3));
+    const int tap = (int)(t / (Cin >> 3));
+    const int ci = cc * 8 + c8;
+    const int cb = scatter ? n : ci, cs = scatter ? ci : n;
+    wb[i] = wp[((int64_t)tap * Cb + cb) * Cs + cs];
+  }
+}
+
+// ---------------------------------------------------------------- host: program + tiling
+static bool build_program(const cgan3d_conv_geom &g, int scatter, ProgPlan &p) {
+  const int k = g.k;
+  if (g.stride != 2 || g.pad != 1 || (k != 3 && k != 4)) return false;
+  int ne = 0, nt = 0;
+  if (!scatter) {
+    // classes by parity of (d - pad): class 0 <-> even offset (slab starts at 2*o), class 1 <-> odd offset (starts at 2*o-1)
+    auto cls = [&](int d) { return (d - 1) & 1; };
+    auto shift = [&](int d) { return (d - 1 + cls(d)) / 2; };  // rows of the sub-slab, >= 0
+    bool first = true;
+    for (int dx = 0; dx < k; ++dx)
+      for (int q = 0; q < 2; ++q)
+        for (int r = 0; r < 2; ++r) {
+          ProgEntry E{};
+          E.cx = (int8_t)(dx - 1); E.cy = (int8_t)(-q); E.cz = (int8_t)(-r);
+          E.tap0 = (uint8_t)nt; E.ntaps = 0;
+          for (int dy = 0; dy < k; ++dy)
+            for (int dz = 0; dz < k; ++dz) {
+              if (cls(dy) != q || cls(dz) != r) continue;
+              if (nt >= kMaxTaps) return false;
+              ProgTap T{};
+              T.row_shift = (uint16_t)(shift(dy) * p.Zh + shift(dz));
+              T.btile = (uint8_t)((dx * k + dy) * k + dz);
+              T.acc = 0; T.first = first ? 1 : 0;
+              first = false;
+              p.taps[nt++] = T; E.ntaps++;
+            }
+          if (E.ntaps == 0) continue;
+          if (ne >= kMaxEntries) return false;
+          p.entries[ne++] = E;
+        }
+    p.nacc = 1;
+  } else {
+    // big index I = 2*i + ph receives small index i + off through tap d iff (ph + 1 - d) is even, off = (ph + 1 - d) / 2
+    int offmin = 0, offmax = 0;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int d = 0; d < k; ++d)
+        if (((ph + 1 - d) & 1) == 0) { const int o = (ph + 1 - d) / 2; offmin = min(offmin, o); offmax = max(offmax, o); }
+    bool seen[8] = {false, false, false, false, false, false, false, false};
+    for (int xo = offmin; xo <= offmax; ++xo) {
+      ProgEntry E{};
+      E.cx = (int8_t)xo; E.cy = (int8_t)offmin; E.cz = (int8_t)offmin;
+      E.tap0 = (uint8_t)nt; E.ntaps = 0;
+      for (int px = 0; px < 2; ++px)
+        for (int dx = 0; dx < k; ++dx) {
+          if (((px + 1 - dx) & 1) || (px + 1 - dx) / 2 != xo) continue;
+          for (int py = 0; py < 2; ++py)
+            for (int dy = 0; dy < k; ++dy) {
+              if ((py + 1 - dy) & 1) continue;
+              for (int pz = 0; pz < 2; ++pz)
+                for (int dz = 0; dz < k; ++dz) {
+                  if ((pz + 1 - dz) & 1) continue;
+                  if (nt >= kMaxTaps) return false;
+                  const int oy = (py + 1 - dy) / 2, oz = (pz + 1 - dz) / 2;
+                  ProgTap T{};
+                  T.row_shift = (uint16_t)((oy - offmin) * p.Zh + (oz - offmin));
+                  T.btile = (uint8_t)((dx * k + dy) * k + dz);
+                  T.acc = (uint8_t)((px * 2 + py) * 2 + pz);
+                  T.first = seen[T.acc] ? 0 : 1;
+                  seen[T.acc] = true;
+                  p.taps[nt++] = T; E.ntaps++;
+                }
+            }
+        }
+      if (E.ntaps == 0) continue;
+      if (ne >= kMaxEntries) return false;
+      p.entries[ne++] = E;
+    }
+    p.nacc = 8;
+  }
+  p.nentries = ne;
+  p.ntaps = nt;
+  return true;
+}
+
+static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best) {
+  if (g.stride != 2 || g.pad != 1 || (g.k != 3 && g.k != 4)) return false;
+  const int Cin = scatter ? g.Cs : g.Cb, N = scatter ? g.Cb : g.Cs;
+  if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
+  if (N % 16 || N < 16 || N > 256) return false;
+  const int nacc = scatter ? 8 : 1;
+  // every big-side voxel must belong to a phase of some small-grid row (holds for transposed convs and for the dgrad of
+  // convs over even extents; an odd extent with k = 4 has one more plane than 2*small)
+  if (scatter && (g.Xb > 2 * g.Xs || g.Yb > 2 * g.Ys || g.Zb > 2 * g.Zs)) return false;
+  const int halo = (scatter && g.k == 4) ? 2 : 1;  // extra rows/lines of the slab beyond the tile
+  const int taps = g.k * g.k * g.k;
+  ProgPlan p{};
+  p.B = g.B; p.Xg = g.Xs; p.Yg = g.Ys; p.Zg = g.Zs;
+  p.Xo = scatter ? g.Xb : g.Xs; p.Yo = scatter ? g.Yb : g.Ys; p.Zo = scatter ? g.Zb : g.Zs;
+  p.Cin = Cin; p.N = N; p.nacc = nacc;
+  p.in_scale = scatter ? 1 : 2; p.out_scale = scatter ? 2 : 1;
+  p.nbt = taps;
+  p.btile_bytes = (uint32_t)Cin * N * 2;
+  const uint32_t b_total = p.nbt * p.btile_bytes;
+  if (b_total + 40000 > kSmemLimitProg) return false;
+  double best_score = 0;
+  bool found = false;
+  for (int nzt = 1; nzt <= 4; ++nzt) {
+    const int Zt = (p.Zg + nzt - 1) / nzt, Zh = Zt + halo;
+    if (2 * (Zh - 1) + 1 > 256) continue;
+    for (int Yt = 1; Yt <= p.Yg; ++Yt) {
+      const int Yh = Yt + halo;
+      if (2 * (Yh - 1) + 1 > 256) break;
+      const int mt = (Yt * Zh + 127) / 128;
+      if (mt > 4 || 2 * nacc * mt * N > 512) break;
+      const int rows_alloc = ((mt * 128 + halo * Zh + halo) + 7) / 8 * 8;
+      if (rows_alloc > 16383 || Yh * Zh > rows_alloc) continue;
+      const uint32_t slot = (uint32_t)(Cin / 8) * rows_alloc * 16;
+      const int nslots = (int)mn<uint32_t>(8, (kSmemLimitProg - b_total - 512) / slot);
+      if (nslots < 3) break;
+      const int nslabs = (p.Yg + Yt - 1) / Yt;
+      const double eff = (double)p.Yg * p.Zg / ((double)nslabs * nzt * mt * 128);
+      const double halo_cost = (double)(Yh * Zh) / (Yt * Zt);
+      const double score = eff / (0.5 + 0.5 * halo_cost);
+      if (score > best_score + 1e-9) {
+        best_score = score; found = true;
+        best = p;
+        best.nzt = nzt; best.Zt = Zt; best.Zh = Zh; best.Yt = Yt; best.Yh = Yh; best.nslabs = nslabs; best.mtiles = mt;
+        best.rows_alloc = rows_alloc; best.slot_bytes = slot; best.nslots = nslots;
+      }
+    }
+  }
+  if (!found) return false;
+  ProgPlan &q = best;
+  const int es = q.in_scale;
+  q.box_bytes = 16u * q.Zh * q.Yh;
+  (void)es;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * nacc * q.mtiles * N)) cols <<= 1;
+  q.tmem_cols = cols;
+  q.smem_bytes = b_total + q.nslots * q.slot_bytes + 512;
+  return build_program(g, scatter, q);
+}
+
+bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (dtype != CGAN3D_BF16 || (op != 0 && op != 1)) return false;
+  ProgPlan p;
+  return plan_prog(g, op, p);
+}
+
+size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (dtype != CGAN3D_BF16 || (op != 0 && op != 1)) return 0;
+  return (size_t)g.k * g.k * g.k * g.Cb * g.Cs * 2 + 256;
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void *tc_encode_fn_ptr();  // conv_tc.cu
+
+int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
+                cudaStream_t st) {
+  ProgPlan p;
+  if (!plan_prog(g, scatter, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: no tiling for this shape");
+  const size_t need = (size_t)p.nbt * p.btile_bytes;
+  if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 strided conv: workspace %zu < %zu", ws_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
+    return fail(CGAN3D_E_ARG, "tcgen05 strided conv: pointers must be 16-byte aligned");
+  EncodeTiledFn2 enc = reinterpret_cast<EncodeTiledFn2>(tc_encode_fn_ptr());
+  if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  bf16 *wb = reinterpret_cast<bf16 *>(ws);
+  repack_prog_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, p.nbt, scatter);
+  CG_LAUNCH_CHECK("repack_prog");
+  // input tensor: gather reads the big side with element strides 2 on z and y; scatter reads the small side densely
+  const int Xi = scatter ? g.Xs : g.Xb, Yi = scatter ? g.Ys : g.Yb, Zi = scatter ? g.Zs : g.Zb, Ci = p.Cin;
+  const int es = p.in_scale;
+  CUtensorMap tm;
+  const cuuint64_t gdim[5] = {(cuuint64_t)Ci, (cuuint64_t)Zi, (cuuint64_t)Yi, (cuuint64_t)Xi, (cuuint64_t)g.B};
+  const cuuint64_t gstr[4] = {(cuuint64_t)Ci * 2, (cuuint64_t)Zi * Ci * 2, (cuuint64_t)Yi * Zi * Ci * 2,
+                              (cuuint64_t)Xi * Yi * Zi * Ci * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)(es * (p.Zh - 1) + 1), (cuuint32_t)(es * (p.Yh - 1) + 1), 1, 1};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (strided) failed with %d", (int)r);
+  const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
+  const int grid = (int)mn<long long>(total, (long long)num_sms());
+  auto launch = [&](auto ks_tag, auto mt_tag) -> int {
+    constexpr int KS = decltype(ks_tag)::value;
+    constexpr int MT = decltype(mt_tag)::value;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv_prog_tc_kernel<KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kSmemLimitProg + 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_prog_tc_kernel)");
+      attr_set = true;
+    }
+    conv_prog_tc_kernel<KS, MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
+    CG_LAUNCH_CHECK("conv_prog_tc_kernel");
+    return 0;
+  };
+  auto by_mt = [&](auto ks_tag) -> int {
+    switch (p.mtiles) {
+      case 1: return launch(ks_tag, std::integral_constant<int, 1>{});
+      case 2: return launch(ks_tag, std::integral_constant<int, 2>{});
+      case 3: return launch(ks_tag, std::integral_constant<int, 3>{});
+      case 4: return launch(ks_tag, std::integral_constant<int, 4>{});
+      default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: mtiles %d not built", p.mtiles);
+    }
+  };
+  switch (p.Cin >> 4) {
+    case 1: return by_mt(std::integral_constant<int, 1>{});
+    case 2: return by_mt(std::integral_constant<int, 2>{});
+    case 4: return by_mt(std::integral_constant<int, 4>{});
+    case 8: return by_mt(std::integral_constant<int, 8>{});
+    default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: Cin must be 16, 32, 64 or 128");
+  }
+}
+
+}  // namespace cg
