@@ -315,193 +315,12 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
 }
 
 
-// ================================================================================================================
-// Kernel 2: wgrad_s1_tc_kernel — weight gradient of the 3x3x3 stride-1 convolution (Cs == 64 output channels,
-// Cb % 16 == 0 input channels, Z <= 62).  dW[co][ci][tap] = sum_v dY[v][co] * X[v + tap][ci].
-//   * GEMM view per tap: D[co, ci] (M = 64, N = Cb) with K = voxels.  Both operands keep the channels-last
-//     activation layout [C/8][row][8 ch] in shared memory, i.e. they are MN-major UMMA operands (a core matrix is
-//     8 voxels x 8 channels); the tap is again a pure row shift of the X operand.
-//   * A CTA owns one dx (filter x-offset) and a contiguous range of (b, y-slab, x) steps; per step it TMA-loads the
-//     dY slab (rows = oy*Zh + oz, halo columns zero-filled by TMA OOB) and the X halo slab of plane x+dx-1, and issues
-//     9 taps x K/16 MMAs into 9 TMEM accumulators (M = 64 accumulators are interleaved two per 64 columns).
-//   * Split-K over CTAs: the partial 9 x 64 x Cb sums are added to the fp32 gradient with red.global.add.f32.
-struct WgPlan {
-  int B, X, Y, Z, Cb, Cs;
-  int Zh, Yt, Yh, nslabs;
-  int kpad, rowsA, rowsB;
-  int steps_per_dx;
-  uint32_t a_bytes, b_bytes, boxA_bytes, boxB_bytes, stage_bytes, smem_bytes, tmem_cols;
-  int stages;
-};
-
-__global__ void __launch_bounds__(192, 1)
-wgrad_s1_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, float *__restrict__ dw,
-                   const WgPlan p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *stage_mem = smem;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stage_mem + (size_t)p.stages * p.stage_bytes);
-  uint64_t *full = bars, *empty = bars + p.stages, *done = bars + 2 * p.stages;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(done + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // zero the staging buffers once: rows that TMA never writes (K padding, tail of the shifted reads) must read as 0
-  {
-    uint4 *z = reinterpret_cast<uint4 *>(stage_mem);
-    const uint32_t n16 = (uint32_t)p.stages * p.stage_bytes / 16;
-    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
-  }
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    tc::mbar_init(done, 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 5) {
-    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
-    tc::tmem_relinquish();
-  }
-  tc::fence_proxy_async();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // work split: blockIdx.x % 3 selects dx; the CTAs of one dx share its steps evenly
-  const int dx = blockIdx.x % 3;
-  const int grp = blockIdx.x / 3, ngrp = (gridDim.x - dx + 2) / 3;
-  const int s_begin = (int)((long long)p.steps_per_dx * grp / ngrp), s_end = (int)((long long)p.steps_per_dx * (grp + 1) / ngrp);
-  const int kch_a = p.Cs >> 3, kch_b = p.Cb >> 3;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      tc::tma_prefetch_desc(&tmY);
-      tc::tma_prefetch_desc(&tmX);
-      for (int st = s_begin, n = 0; st < s_end; ++st, ++n) {
-        int t = st;
-        const int x = t % p.X; t /= p.X;
-        const int sl = t % p.nslabs;
-        const int b = t / p.nslabs;
-        const int y0 = sl * p.Yt;
-        const uint32_t s = n % p.stages, use = n / p.stages;
-        if (use > 0) tc::mbar_wait(&empty[s], (use - 1) & 1);
-        tc::mbar_expect_tx(&full[s], p.boxA_bytes * kch_a + p.boxB_bytes * kch_b);
-        uint8_t *a = stage_mem + (size_t)s * p.stage_bytes, *bb = a + p.a_bytes;
-        for (int cc = 0; cc < kch_a; ++cc) tc::tma_load_5d(a + (size_t)cc * p.rowsA * 16, &tmY, &full[s], cc * 8, 0, y0, x, b);
-        for (int cc = 0; cc < kch_b; ++cc)
-          tc::tma_load_5d(bb + (size_t)cc * p.rowsB * 16, &tmX, &full[s], cc * 8, -1, y0 - 1, x + dx - 1, b);
-      }
-    }
-  } else if (warp == 5) {
-    const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(64, p.Cb, 1, 1);
-    const uint32_t a_sbo = (uint32_t)p.rowsA * 16, b_sbo = (uint32_t)p.rowsB * 16;
-    const uint64_t a_hi = tc::make_desc(0, 128, a_sbo), b_hi = tc::make_desc(0, 128, b_sbo);
-    const uint32_t stage0 = tc::smem_u32(stage_mem);
-    const int kblocks = p.kpad >> 4;
-    for (int st = s_begin, n = 0; st < s_end; ++st, ++n) {
-      const uint32_t s = n % p.stages;
-      tc::mbar_wait(&full[s], (n / p.stages) & 1);
-      tc::tc_fence_after();
-      const uint32_t a0 = (stage0 + s * p.stage_bytes) >> 4, b0 = (stage0 + s * p.stage_bytes + p.a_bytes) >> 4;
-      if (leader) {
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const uint64_t a_desc = a_hi | (uint64_t)((a0 + kb * 16) & 0x3FFF);
-          const uint32_t acc_on = (n | kb) != 0;
-#pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            const int dy = j / 3, dz = j % 3;
-            const uint64_t b_desc = b_hi | (uint64_t)((b0 + kb * 16 + dy * p.Zh + dz) & 0x3FFF);
-            const uint32_t d = tmem_base + (uint32_t)((j >> 1) * p.Cb) + ((uint32_t)((j & 1) * 16) << 16);
-            tc::umma_bf16(d, a_desc, b_desc, idesc, acc_on);
-          }
-        }
-        tc::umma_commit(&empty[s]);
-      }
-      __syncwarp();
-    }
-    if (leader) tc::umma_commit(done);
-    __syncwarp();
-  } else {
-    // epilogue: warps 0..3; lanes 0-15 hold accumulator 2g (row 16*warp + lane), lanes 16-31 accumulator 2g+1
-    if (s_end > s_begin) {
-      tc::mbar_wait(done, 0);
-      tc::tc_fence_after();
-      const int co = warp * 16 + (lane & 15);
-      for (int g2 = 0; g2 < 5; ++g2) {
-        const int j = g2 * 2 + (lane >> 4);
-        const int tap = dx * 9 + j;
-        for (int c0 = 0; c0 < p.Cb; c0 += 16) {
-          uint32_t v[16];
-          tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g2 * p.Cb + c0), v);
-          tc::tmem_ld_wait();
-          if (j < 9) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) atomicAdd(&dw[((size_t)co * p.Cb + (c0 + c)) * 27 + tap], __uint_as_float(v[c]));
-          }
-        }
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
-}
-
-static bool plan_wgrad(const cgan3d_conv_geom &g, WgPlan &p) {
-  if (g.k != 3 || g.stride != 1 || g.pad != 1) return false;
-  if (g.Cs != 64 || g.Cb % 16 || g.Cb < 16 || g.Cb > 64) return false;  // 5 column groups x Cb <= 512 TMEM columns
-  if (g.Zb > 62) return false;
-  p = WgPlan{};
-  p.B = g.B; p.X = g.Xb; p.Y = g.Yb; p.Z = g.Zb; p.Cb = g.Cb; p.Cs = g.Cs;
-  p.Zh = p.Z + 2;
-  p.stages = 2;
-  bool ok = false;
-  for (int Yt = mn(p.Y, 64); Yt >= 1; --Yt) {
-    const int kpad = (Yt * p.Zh + 15) / 16 * 16;
-    const int rowsA = kpad, rowsB = (kpad + 2 * p.Zh + 2 + 7) / 8 * 8;
-    const uint32_t a_bytes = (uint32_t)(g.Cs / 8) * rowsA * 16, b_bytes = (uint32_t)(g.Cb / 8) * rowsB * 16;
-    if (rowsB * 16 > 16383 * 16) continue;
-    if ((size_t)p.stages * (a_bytes + b_bytes) + 512 > kSmemLimit) continue;
-    // prefer slabs of equal height
-    p.Yt = Yt; p.Yh = Yt + 2; p.kpad = kpad; p.rowsA = rowsA; p.rowsB = rowsB; p.a_bytes = a_bytes; p.b_bytes = b_bytes;
-    ok = true;
-    break;
-  }
-  if (!ok) return false;
-  p.nslabs = (p.Y + p.Yt - 1) / p.Yt;
-  p.Yt = (p.Y + p.nslabs - 1) / p.nslabs;  // balance
-  p.Yh = p.Yt + 2;
-  p.kpad = (p.Yt * p.Zh + 15) / 16 * 16;
-  p.rowsA = p.kpad;
-  p.rowsB = (p.kpad + 2 * p.Zh + 2 + 7) / 8 * 8;
-  p.a_bytes = (uint32_t)(g.Cs / 8) * p.rowsA * 16;
-  p.b_bytes = (uint32_t)(g.Cb / 8) * p.rowsB * 16;
-  p.stage_bytes = p.a_bytes + p.b_bytes;
-  p.boxA_bytes = 16u * p.Zh * p.Yt;
-  p.boxB_bytes = 16u * p.Zh * p.Yh;
-  p.smem_bytes = p.stages * p.stage_bytes + 512;
-  p.steps_per_dx = p.B * p.nslabs * p.X;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(5 * g.Cb)) cols <<= 1;
-  p.tmem_cols = cols;
-  return true;
-}
-
-static int encode_act_map(CUtensorMap *tm, const void *ptr, int C, int Z, int Y, int X, int B, int boxZ, int boxY) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
-  const cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)B};
-  const cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)Z * C * 2, (cuuint64_t)Y * Z * C * 2, (cuuint64_t)X * Y * Z * C * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)boxZ, (cuuint32_t)boxY, 1, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return 0;
-}
+// wgrad_tc.cu
+bool tc_wgrad_supported(const cgan3d_conv_geom &g);
+int tc_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st);
 
 static bool s1_shape_ok(const cgan3d_conv_geom &g, int dtype, int op) {
-  if (dtype != CGAN3D_BF16 || op < 0 || op > 2) return false;
+  if (dtype != CGAN3D_BF16 || op < 0 || op > 1) return false;
   if (g.k != 3 || g.stride != 1 || g.pad != 1) return false;
   if (g.Xb != g.Xs || g.Yb != g.Ys || g.Zb != g.Zs) return false;
   return true;
@@ -509,19 +328,16 @@ static bool s1_shape_ok(const cgan3d_conv_geom &g, int dtype, int op) {
 
 bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
   if (!cgan3d_device_supports_tc() || encode_fn() == nullptr) return false;
+  if (op == 2) return dtype == CGAN3D_BF16 && tc_wgrad_supported(g);
   if (!s1_shape_ok(g, dtype, op)) return tc_prog_supported(g, dtype, op);
-  if (op == 2) {
-    WgPlan w;
-    return plan_wgrad(g, w);
-  }
   TcPlan p;
   const int Cin = op == 0 ? g.Cb : g.Cs, N = op == 0 ? g.Cs : g.Cb;
   return plan_s1(g.B, g.Xb, g.Yb, g.Zb, Cin, N, p);
 }
 
 size_t tc_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
-  if (!s1_shape_ok(g, dtype, op)) return tc_prog_workspace_bytes(g, dtype, op);
   if (op == 2) return 0;
+  if (!s1_shape_ok(g, dtype, op)) return tc_prog_workspace_bytes(g, dtype, op);
   return (size_t)27 * g.Cb * g.Cs * 2 + 256;
 }
 
@@ -598,29 +414,7 @@ int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, con
 
 int tc_wgrad(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *, size_t,
              cudaStream_t st) {
-  WgPlan p;
-  if (!plan_wgrad(g, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 wgrad: shape not supported");
-  if ((reinterpret_cast<uintptr_t>(big) & 15) || (reinterpret_cast<uintptr_t>(small) & 15))
-    return fail(CGAN3D_E_ARG, "tcgen05 wgrad: pointers must be 16-byte aligned");
-  if (beta == 0.f) {
-    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)g.Cs * g.Cb * 27 * sizeof(float), st);
-    if (e != cudaSuccess) return cuda_fail(e, "tcgen05 wgrad memset");
-  }
-  CUtensorMap tmY, tmX;
-  int r = encode_act_map(&tmY, small, g.Cs, p.Z, p.Y, p.X, p.B, p.Zh, p.Yt);
-  if (r) return r;
-  r = encode_act_map(&tmX, big, g.Cb, p.Z, p.Y, p.X, p.B, p.Zh, p.Yh);
-  if (r) return r;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_s1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit + 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(wgrad_s1_tc_kernel)");
-    attr_set = true;
-  }
-  const int grid = (int)mn<long long>((long long)3 * p.steps_per_dx, (long long)(num_sms() / 3) * 3);
-  wgrad_s1_tc_kernel<<<grid, 192, p.smem_bytes + 1024, st>>>(tmY, tmX, dw, p);
-  CG_LAUNCH_CHECK("wgrad_s1_tc_kernel");
-  return 0;
+  return tc_wgrad_run(g, big, small, dw, beta, st);
 }
 
 }  // namespace cg

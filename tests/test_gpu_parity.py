@@ -438,13 +438,13 @@ def test_tcgen05_conv3_s1_fprop_and_dgrad(case):
     xr = x.clone().requires_grad_(True)
     y_ref = F.conv3d(xr, w, padding=1)
     dx_ref, = torch.autograd.grad(y_ref, xr, gy)
-    if _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 2) == 2:  # tcgen05 wgrad (Cout == 64)
+    if _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 2) == 2:  # tcgen05 wgrad (Cout in {32, 64}, Cin <= 64)
         dw_tc = ops.conv_wgrad(g, xd, gyd, impl=_lib.IMPL_TC)
         wr = w.clone().requires_grad_(True)
         dw_ref, = torch.autograd.grad(F.conv3d(x, wr, padding=1), wr, gy)
         assert_close32(dw_tc, dw_ref, rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()), msg="wgrad vs ATen")
     else:
-        assert cout != 64
+        assert cout not in (32, 64) or cin > 64 or sp[2] > 62
     for got, gen_, ref, nm in ((y_tc, y_gen, y_ref, "fprop"), (dx_tc, dx_gen, dx_ref, "dgrad")):
         assert torch.isfinite(got.float()).all(), nm
         assert_close32(ncl(got), ref, rtol=8e-3, atol=2e-3, msg=nm + " vs ATen")
@@ -497,3 +497,15 @@ def test_tcgen05_strided_and_transposed_convs(case):
         assert_close32(ncl(got), ref, rtol=8e-3, atol=2e-3, msg=nm + " vs ATen")
         d = (got.float() - gen_.float()).abs()
         assert bool((d <= 2 ** -7 * gen_.float().abs() + 1e-3).all()), f"{nm} vs generic: {d.max().item()}"
+    # weight gradient (same formula for both module kinds: small side x big side)
+    wr = w.clone().requires_grad_(True)
+    yr = F.conv_transpose3d(x.detach(), wr, stride=2, padding=1, output_padding=op) if tr else F.conv3d(x.detach(), wr, stride=2, padding=1)
+    dw_ref, = torch.autograd.grad(yr, wr, gy)
+    big, small = (gyd, xd) if tr else (xd, gyd)
+    if _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 2) == 2:
+        dw_tc = ops.conv_wgrad(g, big, small, impl=_lib.IMPL_TC)
+        assert_close32(dw_tc, dw_ref, rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()), msg="strided wgrad (tcgen05) vs ATen")
+    else:
+        assert g.Cs not in (32, 64), "tcgen05 wgrad should cover Cs in {32, 64}"
+    dw_gen = ops.conv_wgrad(g, big, small, impl=_lib.IMPL_GENERIC)
+    assert_close32(dw_gen, dw_ref, rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()), msg="strided wgrad (generic) vs ATen")
