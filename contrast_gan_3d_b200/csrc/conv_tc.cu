@@ -315,6 +315,12 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
 }
 
 
+// conv_thin_tc.cu (7x7x7 thin-channel layers)
+bool thin_supported(const cgan3d_conv_geom &g, int dtype, int op);
+size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
+int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
+             cudaStream_t st);
+
 // wgrad_tc.cu
 bool tc_wgrad_supported(const cgan3d_conv_geom &g);
 int tc_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st);
@@ -328,6 +334,7 @@ static bool s1_shape_ok(const cgan3d_conv_geom &g, int dtype, int op) {
 
 bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
   if (!cgan3d_device_supports_tc() || encode_fn() == nullptr) return false;
+  if (thin_supported(g, dtype, op)) return true;
   if (op == 2) return dtype == CGAN3D_BF16 && tc_wgrad_supported(g);
   if (!s1_shape_ok(g, dtype, op)) return tc_prog_supported(g, dtype, op);
   TcPlan p;
@@ -336,6 +343,7 @@ bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
 }
 
 size_t tc_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (thin_supported(g, dtype, op)) return thin_workspace_bytes(g, dtype, op);
   if (op == 2) return 0;
   if (!s1_shape_ok(g, dtype, op)) return tc_prog_workspace_bytes(g, dtype, op);
   return (size_t)27 * g.Cb * g.Cs * 2 + 256;
@@ -401,6 +409,7 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
 int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const float *bias, void *small, void *ws,
               size_t ws_bytes, cudaStream_t st) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  if (thin_supported(g, CGAN3D_BF16, 0)) return thin_run(g, 0, big, wp, small, ws, ws_bytes, st);
   if (!s1_shape_ok(g, CGAN3D_BF16, 0)) return tc_prog_run(g, 0, big, wp, small, ws, ws_bytes, st);
   return run_s1(g, 0, big, wp, small, ws, ws_bytes, st);
 }
@@ -408,6 +417,7 @@ int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const 
 int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, const float *bias, void *big, void *ws,
                size_t ws_bytes, cudaStream_t st) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  if (thin_supported(g, CGAN3D_BF16, 1)) return thin_run(g, 1, small, wp, big, ws, ws_bytes, st);
   if (!s1_shape_ok(g, CGAN3D_BF16, 1)) return tc_prog_run(g, 1, small, wp, big, ws, ws_bytes, st);
   return run_s1(g, 1, small, wp, big, ws, ws_bytes, st);
 }

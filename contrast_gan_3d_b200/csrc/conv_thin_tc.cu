@@ -1,0 +1,362 @@
+// tcgen05 kernels for the 7x7x7 THIN-CHANNEL convolutions of the generator (bf16 operands, fp32 accumulation in TMEM):
+//   model.first      Conv3d(1 -> 16, k7, reflect)      reference model/generator.py:31-38
+//   model.last_conv  Conv3d(16 -> 1, k7, reflect)+bias reference model/generator.py:77-83
+// and their backward passes (aten::convolution_backward).  Together they hold 37 % of the generator's FLOPs
+//  but have GEMM N (or K) of 1, so none of the channel-GEMM kernels applies.  Each op gets its own
+// mapping onto M=128 UMMA tiles:
+//
+//  (A) 1 -> 16 channels (fprop of `first`, dgrad of `last_conv`): TOEPLITZ-IN-Z implicit GEMM.
+//      The 1-channel input is a scalar field with z contiguous, so a window of 16 consecutive z values of one (x,y)
+//      line is a 32-byte K-major operand row.  GEMM rows = flattened (x', y') positions of a halo slab (TMA box
+//      8z x Yh x Xh lands as [row][8 z] == the SWIZZLE_NONE core-matrix layout), K = 16 input z, N = 4 output z x 16
+//      channels = 64, and the B operand of tap (dx,dy) is the banded matrix T[zi][(zo,co)] = W[dx,dy,zi-zo,co].
+//      The 49 (dx,dy) taps are pure row shifts of the A descriptor (dx*Yh+dy rows), all 49 Toeplitz tiles (2 KB each)
+//      stay resident in shared memory, and a TMEM lane (= output (x,y)) ends up with 4 z x 16 channels = 128
+//      contiguous output bytes.  7 of every 16 K rows are non-zero: useful MMA fraction 44 %, no im2col, no expansion
+//      of the input in HBM.  Zero padding (dgrad) is TMA out-of-bounds fill.
+#include "common.cuh"
+#include "conv_internal.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace cg {
+
+using bf16 = __nv_bfloat16;
+
+constexpr uint32_t kSmemLimitThin = 232448 - 1024;
+constexpr int kTapTilesA = 49;
+constexpr uint32_t kTileBytesA = 2048;  // [2 z-chunks][64 n][8 z] bf16
+
+struct ThinAPlan {
+  int B, Xi, Yi, Zi;  // 1-channel input
+  int Xo, Yo, Zo;     // 16-channel output
+  int P;              // input coordinate = output coordinate + tap - P (P = 0: valid conv, P = 6: full correlation)
+  int Xt, Yt, Xh, Yh, nxt, nyt, nzb;
+  int mtiles, rows_alloc, nslots;
+  uint32_t slot_bytes, box_bytes, tmem_cols, smem_bytes;
+  int Zc;         // z extent of the two shifted copies: copy[s][row][c] = in[row][c - 8 + zshift[s]]
+  int zshift[2];
+  int debug;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(192, 1)
+conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wT, bf16 *__restrict__ out,
+                   const __grid_constant__ ThinAPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *bres = smem;                                    // 49 resident Toeplitz tiles
+  uint8_t *ring = bres + kTapTilesA * kTileBytesA;         // slab slots
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)p.nslots * p.slot_bytes);
+  uint64_t *b_ready = bars, *s_full = bars + 1, *s_empty = s_full + p.nslots;
+  uint64_t *tm_full = s_empty + p.nslots, *tm_empty = tm_full + 2;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tm_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(b_ready, 1);
+    for (int i = 0; i < p.nslots; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) {
+    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const long long total = (long long)p.B * p.nxt * p.nyt * p.nzb;
+  const int i_begin = (int)(total * blockIdx.x / gridDim.x), i_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  auto decode = [&](int it, int &b, int &x0, int &xlen, int &y0, int &ylen, int &z0) {
+    const int zb = it % p.nzb; it /= p.nzb;
+    const int yt = it % p.nyt; it /= p.nyt;
+    const int xt = it % p.nxt;
+    b = it / p.nxt;
+    x0 = xt * p.Xt; xlen = min(p.Xt, p.Xo - x0);
+    y0 = yt * p.Yt; ylen = min(p.Yt, p.Yo - y0);
+    z0 = zb * 4;
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmA);
+      tc::mbar_expect_tx(b_ready, kTapTilesA * kTileBytesA);
+      for (int t = 0; t < kTapTilesA; ++t)
+        tc::bulk_g2s(bres + (size_t)t * kTileBytesA, reinterpret_cast<const uint8_t *>(wT) + (size_t)t * kTileBytesA, kTileBytesA,
+                     b_ready);
+      uint32_t e = 0;
+      for (int it = i_begin; it < i_end; ++it, ++e) {
+        int b, x0, xlen, y0, ylen, z0;
+        decode(it, b, x0, xlen, y0, ylen, z0);
+        const uint32_t slot = e % p.nslots, use = e / p.nslots;
+        if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
+        uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
+        if (p.debug & 1) { tc::mbar_arrive(&s_full[slot]); continue; }
+        tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
+        // TMA needs a 16-byte aligned start along z: block parity selects the copy whose z shift makes it so
+        const int cp = (z0 >> 2) & 1;
+        const int c0 = z0 - p.P - p.zshift[cp] + 8;
+        tc::tma_load_5d(dst, &tmA, &s_full[slot], c0, y0 - p.P, x0 - p.P, b, cp);
+        tc::tma_load_5d(dst + (size_t)p.rows_alloc * 16, &tmA, &s_full[slot], c0 + 8, y0 - p.P, x0 - p.P, b, cp);
+      }
+    }
+  } else if (warp == 5) {
+    const bool leader = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
+    const uint64_t a_hi = tc::make_desc(0, (uint32_t)p.rows_alloc * 16, 128), b_hi = tc::make_desc(0, 64 * 16, 128);
+    tc::mbar_wait(b_ready, 0);
+    tc::tc_fence_after();
+    uint32_t e = 0;
+    for (int it = i_begin; it < i_end; ++it, ++e) {
+      const uint32_t q = e & 1, uq = e >> 1, slot = e % p.nslots;
+      if (uq > 0) tc::mbar_wait(&tm_empty[q], (uq - 1) & 1);
+      tc::mbar_wait(&s_full[slot], (e / p.nslots) & 1);
+      tc::tc_fence_after();
+      const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
+      const uint32_t d_base = tmem_base + q * (uint32_t)(MT * 64);
+      for (int dx = 0; dx < 7; ++dx) {
+        for (int dy = 0; dy < 7; ++dy) {
+          const int tap = dx * 7 + dy;
+          const uint64_t a0 = a_hi | (uint64_t)((a_slot + (uint32_t)(dx * p.Yh + dy)) & 0x3FFF);
+          const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)tap * kTileBytesA) >> 4) & 0x3FFF);
+          if (leader && !(p.debug & 2)) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 64, a0 + (uint64_t)(mt * 128), b0, idesc, (uint32_t)(tap != 0));
+          }
+          __syncwarp();
+        }
+      }
+      if (leader) {
+        tc::umma_commit(&s_empty[slot]);
+        tc::umma_commit(&tm_full[q]);
+      }
+      __syncwarp();
+    }
+  } else {
+    uint32_t e = 0;
+    for (int it = i_begin; it < i_end; ++it, ++e) {
+      int b, x0, xlen, y0, ylen, z0;
+      decode(it, b, x0, xlen, y0, ylen, z0);
+      const uint32_t q = e & 1;
+      tc::mbar_wait(&tm_full[q], (e >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(MT * 64);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int r = mt * 128 + warp * 32 + lane;
+        const int xx = r / p.Yh, yy = r - xx * p.Yh;
+        const bool valid = xx < xlen && yy < ylen;
+        bf16 *dst = out + ((((size_t)b * p.Xo + (x0 + xx)) * p.Yo + (y0 + yy)) * p.Zo + z0) * 16;
+#pragma unroll
+        for (int zo = 0; zo < 4; ++zo) {
+          uint32_t v[16];
+          tc::tmem_ld16(d_base + (uint32_t)(mt * 64 + zo * 16), v);
+          tc::tmem_ld_wait();
+          if (valid && z0 + zo < p.Zo) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + zo * 16);
+            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Toeplitz tiles: T[(dx,dy)][zi/8][n = zo*16 + co][zi%8] = w(dx,dy,zi-zo,co) for 0 <= zi-zo < 7, else 0.
+// wp is the packed filter [tap][Cb][Cs] with Cb*Cs == 16; flip = 1 reverses the taps (transposed convolution).
+__global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip) {
+  const int total = kTapTilesA * 2 * 64 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int z8 = i & 7;
+    int t = i >> 3;
+    const int n = t & 63; t >>= 6;
+    const int chunk = t & 1;
+    const int tile = t >> 1;
+    const int zi = chunk * 8 + z8, zo = n >> 4, co = n & 15, dz = zi - zo;
+    bf16 v = __float2bfloat16_rn(0.f);
+    if (dz >= 0 && dz < 7) {
+      const int tap = tile * 7 + dz;
+      v = wp[(size_t)(flip ? 342 - tap : tap) * 16 + co];
+    }
+    wt[i] = v;
+  }
+}
+
+// TMA needs 16-byte aligned row pitches AND a 16-byte aligned start coordinate along the contiguous axis, but the z
+// windows start every 4 voxels.  Two z-shifted, zero-margined copies of the 1-channel input make every window start
+// aligned in one of them:  copy[s][row][c] = in[row][c - 8 + shift_s]  (0 outside), c in [0, Zc), Zc % 8 == 0.
+__global__ void shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc, int s0,
+                                      int s1) {
+  const long long per = rows * Zc, total = 2 * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cp = i >= per;
+    const long long j = i - cp * per;
+    const long long r = j / Zc;
+    const int z = (int)(j - r * Zc) - 8 + (cp ? s1 : s0);
+    out[i] = (z >= 0 && z < Z) ? in[r * Z + z] : __float2bfloat16_rn(0.f);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFnT)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void *tc_encode_fn_ptr();  // conv_tc.cu
+
+static int encode_map(CUtensorMap *tm, const void *ptr, int rank, const cuuint64_t *gdim, const cuuint64_t *gstr,
+                      const cuuint32_t *box) {
+  EncodeTiledFnT enc = reinterpret_cast<EncodeTiledFnT>(tc_encode_fn_ptr());
+  if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (thin conv) failed with %d", (int)r);
+  return 0;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// op 0: gather with Cb == 1, Cs == 16 (valid conv, P = pad);  op 1: scatter with Cb == 16, Cs == 1 (P = 6 - pad)
+static bool thin_a_shape(const cgan3d_conv_geom &g, int op) {
+  if (g.k != 7 || g.stride != 1) return false;
+  if (op == 0) return g.Cb == 1 && g.Cs == 16;
+  if (op == 1) return g.Cb == 16 && g.Cs == 1;
+  return false;
+}
+
+static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
+  if (!thin_a_shape(g, op)) return false;
+  ThinAPlan p{};
+  p.B = g.B;
+  if (op == 0) { p.Xi = g.Xb; p.Yi = g.Yb; p.Zi = g.Zb; p.Xo = g.Xs; p.Yo = g.Ys; p.Zo = g.Zs; p.P = g.pad; }
+  else         { p.Xi = g.Xs; p.Yi = g.Ys; p.Zi = g.Zs; p.Xo = g.Xb; p.Yo = g.Yb; p.Zo = g.Zb; p.P = 6 - g.pad; }
+  p.nzb = (p.Zo + 3) / 4;
+  p.zshift[0] = ((0 - p.P) % 8 + 8) % 8;
+  p.zshift[1] = ((4 - p.P) % 8 + 8) % 8;
+  p.Zc = round_up(p.Zi + 16, 8);
+  const uint32_t fixed = kTapTilesA * kTileBytesA + 512;
+  double best_score = 0;
+  bool found = false;
+  for (int nyt = 1; nyt <= p.Yo; ++nyt) {
+    const int Yt = (p.Yo + nyt - 1) / nyt, Yh = Yt + 6;
+    if ((p.Yo + Yt - 1) / Yt != nyt) continue;
+    if (Yh > 256) continue;
+    for (int mt = 1; mt <= 4; ++mt) {
+      if (Yt > mt * 128) continue;
+      const int Xt = mn(p.Xo, (mt * 128 - Yt) / Yh + 1), Xh = Xt + 6;
+      if (Xh > 256) continue;
+      const int rows_alloc = round_up(mx(Xh * Yh, mt * 128 + 6 * Yh + 6), 8);
+      const uint32_t slot = 2u * rows_alloc * 16;
+      const int nslots = (int)mn<uint32_t>(6, (kSmemLimitThin - fixed) / slot);
+      if (nslots < 2) continue;
+      const int nxt = (p.Xo + Xt - 1) / Xt;
+      const double eff = (double)p.Xo * p.Yo / ((double)nxt * nyt * mt * 128);
+      const double halo = (double)(Xh * Yh) / (Xt * Yt);
+      const double score = eff / (1.0 + 0.02 * halo) * (nslots >= 3 ? 1.0 : 0.8);
+      if (score > best_score + 1e-9) {
+        best_score = score; found = true;
+        best = p;
+        best.Xt = Xt; best.Yt = Yt; best.Xh = Xh; best.Yh = Yh; best.nxt = nxt; best.nyt = nyt; best.mtiles = mt;
+        best.rows_alloc = rows_alloc; best.slot_bytes = slot; best.nslots = nslots;
+      }
+    }
+    if (nyt > 8 && found) break;
+  }
+  if (!found) return false;
+  best.box_bytes = 16u * best.Yh * best.Xh;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * best.mtiles * 64)) cols <<= 1;
+  best.tmem_cols = cols;
+  best.smem_bytes = fixed + best.nslots * best.slot_bytes;
+  return true;
+}
+
+bool thin_supported(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (dtype != CGAN3D_BF16) return false;
+  if (op == 0 || op == 1) {
+    ThinAPlan p;
+    return plan_thin_a(g, op, p);
+  }
+  return false;
+}
+
+static size_t thin_a_repitch_bytes(const ThinAPlan &p) { return (size_t)2 * p.B * p.Xi * p.Yi * p.Zc * 2; }
+
+size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (dtype != CGAN3D_BF16) return 0;
+  ThinAPlan p;
+  if ((op == 0 || op == 1) && plan_thin_a(g, op, p)) return (size_t)kTapTilesA * kTileBytesA + 256 + thin_a_repitch_bytes(p) + 256;
+  return 0;
+}
+
+static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
+                      cudaStream_t st) {
+  ThinAPlan p;
+  if (!plan_thin_a(g, op, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: shape not supported");
+  if (const char *dbg = getenv("CGAN3D_THIN_DEBUG")) p.debug = atoi(dbg);
+  const size_t need = thin_workspace_bytes(g, CGAN3D_BF16, op);
+  if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 thin conv: workspace %zu < %zu", ws_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255))
+    return fail(CGAN3D_E_ARG, "tcgen05 thin conv: pointers must be 16-byte aligned (workspace 256)");
+  bf16 *wt = reinterpret_cast<bf16 *>(ws);
+  toeplitz_a_kernel<<<49, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op);
+  CG_LAUNCH_CHECK("toeplitz_a");
+  bf16 *rp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kTapTilesA * kTileBytesA + 256);
+  const long long rows = (long long)p.B * p.Xi * p.Yi;
+  shifted_copies_kernel<<<num_sms() * 8, 256, 0, st>>>(reinterpret_cast<const bf16 *>(in), rp, rows, p.Zi, p.Zc, p.zshift[0],
+                                                      p.zshift[1]);
+  CG_LAUNCH_CHECK("shifted_copies");
+  CUtensorMap tm;
+  const cuuint64_t zc = (cuuint64_t)p.Zc;
+  const cuuint64_t gdim[5] = {zc, (cuuint64_t)p.Yi, (cuuint64_t)p.Xi, (cuuint64_t)p.B, 2};
+  const cuuint64_t gstr[4] = {zc * 2, (cuuint64_t)p.Yi * zc * 2, (cuuint64_t)p.Xi * p.Yi * zc * 2, (cuuint64_t)rows * zc * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)p.Yh, (cuuint32_t)p.Xh, 1, 1};
+  int r = encode_map(&tm, rp, 5, gdim, gstr, box);
+  if (r) return r;
+  const long long total = (long long)p.B * p.nxt * p.nyt * p.nzb;
+  const int grid = (int)mn<long long>(total, (long long)num_sms());
+  auto launch = [&](auto mt_tag) -> int {
+    constexpr int MT = decltype(mt_tag)::value;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv7_c1_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv7_c1_tc_kernel)");
+      attr_set = true;
+    }
+    conv7_c1_tc_kernel<MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p);
+    CG_LAUNCH_CHECK("conv7_c1_tc_kernel");
+    return 0;
+  };
+  switch (p.mtiles) {
+    case 1: return launch(std::integral_constant<int, 1>{});
+    case 2: return launch(std::integral_constant<int, 2>{});
+    case 3: return launch(std::integral_constant<int, 3>{});
+    case 4: return launch(std::integral_constant<int, 4>{});
+    default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: mtiles %d not built", p.mtiles);
+  }
+}
+
+int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
+             cudaStream_t st) {
+  if (op == 0 || op == 1) return run_thin_a(g, op, in, wp, outp, ws, ws_bytes, st);
+  return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: op %d not built", op);
+}
+
+}  // namespace cg

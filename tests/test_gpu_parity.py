@@ -509,3 +509,54 @@ def test_tcgen05_strided_and_transposed_convs(case):
         assert g.Cs not in (32, 64), "tcgen05 wgrad should cover Cs in {32, 64}"
     dw_gen = ops.conv_wgrad(g, big, small, impl=_lib.IMPL_GENERIC)
     assert_close32(dw_gen, dw_ref, rtol=2e-3, atol=2e-3 * float(dw_ref.abs().max()), msg="strided wgrad (generic) vs ATen")
+
+
+THIN_CASES = [
+    # (name, B, spatial_in, pad)   7x7x7 stride-1 thin-channel layers of the generator
+    ("thin_small_valid", 2, (10, 9, 12), 0),
+    ("thin_zeropad", 1, (9, 16, 8), 3),
+    ("thin_tiled", 2, (20, 150, 37), 0),
+    ("thin_c1_like", 1, (38, 38, 38), 0),
+]
+
+
+@pytest.mark.parametrize("case", THIN_CASES, ids=[c[0] for c in THIN_CASES])
+def test_tcgen05_thin_7x7x7_layers(case):
+    """tcgen05 kernels of model.first (1->16) and model.last_conv (16->1): fprop, dgrad and wgrad vs the generic
+    kernels (same bf16 operands) and vs ATen fp32."""
+    _lib, ops = _ops()
+    name, B, sp, pad = case
+    gen = torch.Generator().manual_seed(len(name) + 3)
+    for cin, cout in ((1, 16), (16, 1)):
+        x = torch.randn((B, cin, *sp), generator=gen).bfloat16().float().requires_grad_(True)
+        w = (torch.randn((cout, cin, 7, 7, 7), generator=gen) / (cin * 343) ** 0.5).bfloat16().float().requires_grad_(True)
+        y = F.conv3d(x, w, padding=pad)
+        gy = torch.randn(y.shape, generator=gen).bfloat16().float()
+        gx_ref, gw_ref = torch.autograd.grad(y, (x, w), gy)
+        spec = ops.ConvSpec(transposed=False, cin=cin, cout=cout, k=7, stride=1, pad=pad)
+        g, _ = spec.geometry(B, sp)
+        xd = cl(x.detach()).to(DEV, torch.bfloat16)
+        gyd = cl(gy).to(DEV, torch.bfloat16)
+        wp = ops.pack_weights(w.detach().to(DEV), torch.bfloat16)
+        sel = [_lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, op) for op in range(3)]
+        checks = []
+        if sel[0] == 2:
+            checks.append((ops.conv_gather(g, xd, wp, impl=_lib.IMPL_TC), ops.conv_gather(g, xd, wp, impl=_lib.IMPL_GENERIC), y.detach(), "fprop"))
+        if sel[1] == 2:
+            checks.append((ops.conv_scatter(g, gyd, wp, impl=_lib.IMPL_TC), ops.conv_scatter(g, gyd, wp, impl=_lib.IMPL_GENERIC), gx_ref, "dgrad"))
+        torch.cuda.synchronize()
+        for got, gen_, ref, nm in checks:
+            assert torch.isfinite(got.float()).all(), f"{cin}->{cout} {nm}"
+            assert_close32(ncl(got), ref, rtol=8e-3, atol=2e-3, msg=f"{cin}->{cout} {nm} vs ATen")
+            d = (got.float() - gen_.float()).abs()
+            assert bool((d <= 2 ** -7 * gen_.float().abs() + 1e-3).all()), f"{cin}->{cout} {nm} vs generic: {d.max().item()}"
+        if sel[2] == 2:
+            dw = ops.conv_wgrad(g, xd, gyd, impl=_lib.IMPL_TC)
+            assert_close32(dw, gw_ref, rtol=2e-3, atol=2e-3 * float(gw_ref.abs().max()), msg=f"{cin}->{cout} wgrad vs ATen")
+    # which ops the tcgen05 path must cover for these layers (extended as kernels land)
+    spec = ops.ConvSpec(transposed=False, cin=1, cout=16, k=7, stride=1, pad=pad)
+    g, _ = spec.geometry(B, sp)
+    assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 0) == 2
+    spec = ops.ConvSpec(transposed=False, cin=16, cout=1, k=7, stride=1, pad=pad)
+    g, _ = spec.geometry(B, sp)
+    assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 1) == 2
