@@ -213,6 +213,205 @@ __global__ void shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+//  (B) 16 -> 1 channels (fprop of `last_conv`, dgrad of `first`): filter x-offsets STACKED ON N + register window.
+//      GEMM rows = flattened (y', z') positions of one input x-plane slab (as in conv_tc.cu), K = 16 input channels,
+//      and the 49 (dy,dz) taps are row shifts accumulated by the tensor core.  The GEMM N dimension carries the 7
+//      filter x-offsets: D_xi[row, dx] is the contribution of input plane xi to output plane xi + P - dx.  Every input
+//      plane is streamed through shared memory exactly once; the epilogue thread that owns a row keeps a 7-deep
+//      register window of partial outputs, adds the 7 columns of each new plane and retires one finished output
+//      plane per input plane (coalesced along z).  N = 16 is the smallest M=128 tile, so this shape is bound by the
+//      shared-memory read of A (4 KB per MMA).
+constexpr int kTapTilesB = 49;
+constexpr uint32_t kTileBytesB = 512;  // [2 ci-chunks][16 n = dx][8 ci] bf16
+
+struct ThinBPlan {
+  int B, Xi, Yi, Zi;  // 16-channel input
+  int Xo, Yo, Zo;     // 1-channel output
+  int P;
+  int Zt, nzt, Zh, Yt, nyt, Yh;
+  int mtiles, rows_alloc, nslots;
+  uint32_t slot_bytes, box_bytes, tmem_cols, smem_bytes;
+};
+
+struct SegIter {
+  long long idx, end;
+  int Xo;
+  __device__ __forceinline__ SegIter(long long ncols, int Xo_) : Xo(Xo_) {
+    const long long total = ncols * Xo;
+    idx = total * blockIdx.x / gridDim.x;
+    end = total * (blockIdx.x + 1) / gridDim.x;
+  }
+  __device__ __forceinline__ bool next(int &col, int &x0, int &xlen) {
+    if (idx >= end) return false;
+    col = (int)(idx / Xo);
+    x0 = (int)(idx - (long long)col * Xo);
+    xlen = (int)mn<long long>(Xo - x0, end - idx);
+    idx += xlen;
+    return true;
+  }
+};
+
+template <int MT>
+__global__ void __launch_bounds__(192, 1)
+conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wT, bf16 *__restrict__ out,
+                    const __grid_constant__ ThinBPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *bres = smem;
+  uint8_t *ring = bres + 25600;  // 49 * 512 rounded up to a multiple of 1024
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)p.nslots * p.slot_bytes);
+  uint64_t *b_ready = bars, *s_full = bars + 1, *s_empty = s_full + p.nslots;
+  uint64_t *tm_full = s_empty + p.nslots, *tm_empty = tm_full + 2;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tm_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(b_ready, 1);
+    for (int i = 0; i < p.nslots; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) {
+    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const long long ncols = (long long)p.B * p.nyt * p.nzt;
+  auto decode = [&](int col, int &b, int &y0, int &ylen, int &z0, int &zlen) {
+    const int zt = col % p.nzt; col /= p.nzt;
+    const int yt = col % p.nyt;
+    b = col / p.nyt;
+    y0 = yt * p.Yt; ylen = min(p.Yt, p.Yo - y0);
+    z0 = zt * p.Zt; zlen = min(p.Zt, p.Zo - z0);
+  };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmA);
+      tc::mbar_expect_tx(b_ready, kTapTilesB * kTileBytesB);
+      tc::bulk_g2s(bres, wT, kTapTilesB * kTileBytesB, b_ready);
+      uint32_t e = 0;
+      int col, x0, xlen;
+      for (SegIter it(ncols, p.Xo); it.next(col, x0, xlen);) {
+        int b, y0, ylen, z0, zlen;
+        decode(col, b, y0, ylen, z0, zlen);
+        for (int i = 0; i < xlen + 6; ++i, ++e) {
+          const uint32_t slot = e % p.nslots, use = e / p.nslots;
+          if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
+          tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
+          uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
+          const int xi = x0 - p.P + i;
+          tc::tma_load_5d(dst, &tmA, &s_full[slot], 0, z0 - p.P, y0 - p.P, xi, b);
+          tc::tma_load_5d(dst + (size_t)p.rows_alloc * 16, &tmA, &s_full[slot], 8, z0 - p.P, y0 - p.P, xi, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    const bool leader = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_bf16(128, 16, 0, 0);
+    const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
+    const uint64_t a_hi = tc::make_desc(0, (uint32_t)p.rows_alloc * 16, 128), b_hi = tc::make_desc(0, 16 * 16, 128);
+    tc::mbar_wait(b_ready, 0);
+    tc::tc_fence_after();
+    uint32_t e = 0;
+    int col, x0, xlen;
+    for (SegIter it(ncols, p.Xo); it.next(col, x0, xlen);) {
+      for (int i = 0; i < xlen + 6; ++i, ++e) {
+        const uint32_t q = e & 1, uq = e >> 1, slot = e % p.nslots;
+        if (uq > 0) tc::mbar_wait(&tm_empty[q], (uq - 1) & 1);
+        tc::mbar_wait(&s_full[slot], (e / p.nslots) & 1);
+        tc::tc_fence_after();
+        const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
+        const uint32_t d_base = tmem_base + q * (uint32_t)(MT * 16);
+        for (int dy = 0; dy < 7; ++dy) {
+          for (int dz = 0; dz < 7; ++dz) {
+            const int tap = dy * 7 + dz;
+            const uint64_t a0 = a_hi | (uint64_t)((a_slot + (uint32_t)(dy * p.Zh + dz)) & 0x3FFF);
+            const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)tap * kTileBytesB) >> 4) & 0x3FFF);
+            if (leader) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 16, a0 + (uint64_t)(mt * 128), b0, idesc, (uint32_t)(tap != 0));
+            }
+            __syncwarp();
+          }
+        }
+        if (leader) {
+          tc::umma_commit(&s_empty[slot]);
+          tc::umma_commit(&tm_full[q]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    uint32_t e = 0;
+    int col, x0, xlen;
+    for (SegIter it(ncols, p.Xo); it.next(col, x0, xlen);) {
+      int b, y0, ylen, z0, zlen;
+      decode(col, b, y0, ylen, z0, zlen);
+      float win[MT][7];
+      bool valid[MT];
+      size_t off[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) win[mt][j] = 0.f;
+        const int r = mt * 128 + warp * 32 + lane;
+        const int yy = r / p.Zh, zz = r - yy * p.Zh;
+        valid[mt] = yy < ylen && zz < zlen;
+        off[mt] = ((size_t)(y0 + yy)) * p.Zo + (z0 + zz);
+      }
+      for (int i = 0; i < xlen + 6; ++i, ++e) {
+        const uint32_t q = e & 1;
+        tc::mbar_wait(&tm_full[q], (e >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(MT * 16);
+        bf16 *plane = out + ((size_t)b * p.Xo + (x0 + i - 6)) * p.Yo * p.Zo;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint32_t v[8];
+          tc::tmem_ld8(d_base + (uint32_t)(mt * 16), v);
+          tc::tmem_ld_wait();
+          // column dx feeds output plane (this input plane) + P - dx == window slot 6 - dx
+#pragma unroll
+          for (int j = 0; j < 7; ++j) win[mt][j] += __uint_as_float(v[6 - j]);
+          if (i >= 6 && valid[mt]) plane[off[mt]] = __float2bfloat16_rn(win[mt][0]);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) win[mt][j] = win[mt][j + 1];
+          win[mt][6] = 0.f;
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// T[(dy,dz)][ci/8][n = dx][ci%8] = w(dx,dy,dz,ci) for dx < 7, else 0 (same flip convention as toeplitz_a_kernel)
+__global__ void stack_b_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip) {
+  const int total = kTapTilesB * 2 * 16 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c8 = i & 7;
+    int t = i >> 3;
+    const int n = t & 15; t >>= 4;
+    const int chunk = t & 1;
+    const int tile = t >> 1;  // dy*7 + dz
+    bf16 v = __float2bfloat16_rn(0.f);
+    if (n < 7) {
+      const int tap = n * 49 + tile;
+      v = wp[(size_t)(flip ? 342 - tap : tap) * 16 + chunk * 8 + c8];
+    }
+    wt[i] = v;
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFnT)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -288,11 +487,61 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
   return true;
 }
 
+// op 0: gather with Cb == 16, Cs == 1;  op 1: scatter with Cb == 1, Cs == 16
+static bool thin_b_shape(const cgan3d_conv_geom &g, int op) {
+  if (g.k != 7 || g.stride != 1) return false;
+  if (op == 0) return g.Cb == 16 && g.Cs == 1;
+  if (op == 1) return g.Cb == 1 && g.Cs == 16;
+  return false;
+}
+
+static bool plan_thin_b(const cgan3d_conv_geom &g, int op, ThinBPlan &best) {
+  if (!thin_b_shape(g, op)) return false;
+  ThinBPlan p{};
+  p.B = g.B;
+  if (op == 0) { p.Xi = g.Xb; p.Yi = g.Yb; p.Zi = g.Zb; p.Xo = g.Xs; p.Yo = g.Ys; p.Zo = g.Zs; p.P = g.pad; }
+  else         { p.Xi = g.Xs; p.Yi = g.Ys; p.Zi = g.Zs; p.Xo = g.Xb; p.Yo = g.Yb; p.Zo = g.Zb; p.P = 6 - g.pad; }
+  p.nzt = (p.Zo + 249) / 250;
+  p.Zt = (p.Zo + p.nzt - 1) / p.nzt;
+  p.Zh = p.Zt + 6;
+  const uint32_t fixed = 25600 + 512;
+  double best_score = 0;
+  bool found = false;
+  for (int Yt = 1; Yt <= p.Yo && Yt + 6 <= 256; ++Yt) {
+    const int Yh = Yt + 6;
+    const int mt = ((Yt - 1) * p.Zh + p.Zt + 127) / 128;
+    if (mt > 8) break;
+    const int rows_alloc = round_up(mx(Yh * p.Zh, mt * 128 + 6 * p.Zh + 6), 8);
+    if (rows_alloc > 16383) break;
+    const uint32_t slot = 2u * rows_alloc * 16;
+    const int nslots = (int)mn<uint32_t>(4, (kSmemLimitThin - fixed) / slot);
+    if (nslots < 2) break;
+    const int nyt = (p.Yo + Yt - 1) / Yt;
+    const double eff = (double)p.Yo * p.Zo / ((double)nyt * p.nzt * mt * 128);
+    const double score = eff * (nslots >= 3 ? 1.0 : 0.85);
+    if (score > best_score + 1e-9) {
+      best_score = score; found = true;
+      best = p;
+      best.Yt = Yt; best.Yh = Yh; best.nyt = nyt; best.mtiles = mt; best.rows_alloc = rows_alloc; best.slot_bytes = slot;
+      best.nslots = nslots;
+    }
+  }
+  if (!found) return false;
+  best.box_bytes = 16u * best.Zh * best.Yh;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * best.mtiles * 16)) cols <<= 1;
+  best.tmem_cols = cols;
+  best.smem_bytes = fixed + best.nslots * best.slot_bytes;
+  return true;
+}
+
 bool thin_supported(const cgan3d_conv_geom &g, int dtype, int op) {
   if (dtype != CGAN3D_BF16) return false;
   if (op == 0 || op == 1) {
-    ThinAPlan p;
-    return plan_thin_a(g, op, p);
+    ThinAPlan pa;
+    if (plan_thin_a(g, op, pa)) return true;
+    ThinBPlan pb;
+    return plan_thin_b(g, op, pb);
   }
   return false;
 }
@@ -303,6 +552,8 @@ size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   if (dtype != CGAN3D_BF16) return 0;
   ThinAPlan p;
   if ((op == 0 || op == 1) && plan_thin_a(g, op, p)) return (size_t)kTapTilesA * kTileBytesA + 256 + thin_a_repitch_bytes(p) + 256;
+  ThinBPlan pb;
+  if ((op == 0 || op == 1) && plan_thin_b(g, op, pb)) return (size_t)kTapTilesB * kTileBytesB + 256;
   return 0;
 }
 
@@ -353,8 +604,53 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   }
 }
 
+static int run_thin_b(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
+                      cudaStream_t st) {
+  ThinBPlan p;
+  if (!plan_thin_b(g, op, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv (16->1): shape not supported");
+  const size_t need = (size_t)kTapTilesB * kTileBytesB;
+  if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 thin conv: workspace %zu < %zu", ws_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
+    return fail(CGAN3D_E_ARG, "tcgen05 thin conv: pointers must be 16-byte aligned");
+  bf16 *wt = reinterpret_cast<bf16 *>(ws);
+  stack_b_kernel<<<13, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op);
+  CG_LAUNCH_CHECK("stack_b");
+  CUtensorMap tm;
+  const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zi, (cuuint64_t)p.Yi, (cuuint64_t)p.Xi, (cuuint64_t)p.B};
+  const cuuint64_t gstr[4] = {32, (cuuint64_t)p.Zi * 32, (cuuint64_t)p.Yi * p.Zi * 32, (cuuint64_t)p.Xi * p.Yi * p.Zi * 32};
+  const cuuint32_t box[5] = {8, (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
+  int r = encode_map(&tm, in, 5, gdim, gstr, box);
+  if (r) return r;
+  const long long total = (long long)p.B * p.nyt * p.nzt * p.Xo;
+  const int grid = (int)mn<long long>(total, (long long)num_sms());
+  auto launch = [&](auto mt_tag) -> int {
+    constexpr int MT = decltype(mt_tag)::value;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv7_to1_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv7_to1_tc_kernel)");
+      attr_set = true;
+    }
+    conv7_to1_tc_kernel<MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p);
+    CG_LAUNCH_CHECK("conv7_to1_tc_kernel");
+    return 0;
+  };
+  switch (p.mtiles) {
+    case 1: return launch(std::integral_constant<int, 1>{});
+    case 2: return launch(std::integral_constant<int, 2>{});
+    case 3: return launch(std::integral_constant<int, 3>{});
+    case 4: return launch(std::integral_constant<int, 4>{});
+    case 5: return launch(std::integral_constant<int, 5>{});
+    case 6: return launch(std::integral_constant<int, 6>{});
+    case 7: return launch(std::integral_constant<int, 7>{});
+    case 8: return launch(std::integral_constant<int, 8>{});
+    default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: mtiles %d not built", p.mtiles);
+  }
+}
+
 int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
              cudaStream_t st) {
+  if ((op == 0 || op == 1) && thin_b_shape(g, op)) return run_thin_b(g, op, in, wp, outp, ws, ws_bytes, st);
   if (op == 0 || op == 1) return run_thin_a(g, op, in, wp, outp, ws, ws_bytes, st);
   return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: op %d not built", op);
 }

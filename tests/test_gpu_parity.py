@@ -554,9 +554,8 @@ def test_tcgen05_thin_7x7x7_layers(case):
             dw = ops.conv_wgrad(g, xd, gyd, impl=_lib.IMPL_TC)
             assert_close32(dw, gw_ref, rtol=2e-3, atol=2e-3 * float(gw_ref.abs().max()), msg=f"{cin}->{cout} wgrad vs ATen")
     # which ops the tcgen05 path must cover for these layers (extended as kernels land)
-    spec = ops.ConvSpec(transposed=False, cin=1, cout=16, k=7, stride=1, pad=pad)
-    g, _ = spec.geometry(B, sp)
-    assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 0) == 2
-    spec = ops.ConvSpec(transposed=False, cin=16, cout=1, k=7, stride=1, pad=pad)
-    g, _ = spec.geometry(B, sp)
-    assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 1) == 2
+    for cin, cout in ((1, 16), (16, 1)):
+        spec = ops.ConvSpec(transposed=False, cin=cin, cout=cout, k=7, stride=1, pad=pad)
+        g, _ = spec.geometry(B, sp)
+        assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 0) == 2
+        assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 1) == 2
