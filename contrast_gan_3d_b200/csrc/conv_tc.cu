@@ -320,6 +320,8 @@ bool thin_supported(const cgan3d_conv_geom &g, int dtype, int op);
 size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
 int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
              cudaStream_t st);
+int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
+                   cudaStream_t st);
 
 // wgrad_tc.cu
 bool tc_wgrad_supported(const cgan3d_conv_geom &g);
@@ -422,8 +424,9 @@ int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, con
   return run_s1(g, 1, small, wp, big, ws, ws_bytes, st);
 }
 
-int tc_wgrad(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *, size_t,
+int tc_wgrad(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
              cudaStream_t st) {
+  if (thin_supported(g, CGAN3D_BF16, 2)) return thin_wgrad_run(g, big, small, dw, beta, ws, ws_bytes, st);
   return tc_wgrad_run(g, big, small, dw, beta, st);
 }
 

@@ -302,11 +302,10 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         for (int i = 0; i < xlen + 6; ++i, ++e) {
           const uint32_t slot = e % p.nslots, use = e / p.nslots;
           if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
-          tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
+          tc::mbar_expect_tx(&s_full[slot], p.box_bytes);
           uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
           const int xi = x0 - p.P + i;
           tc::tma_load_5d(dst, &tmA, &s_full[slot], 0, z0 - p.P, y0 - p.P, xi, b);
-          tc::tma_load_5d(dst + (size_t)p.rows_alloc * 16, &tmA, &s_full[slot], 8, z0 - p.P, y0 - p.P, xi, b);
         }
       }
     }
@@ -314,7 +313,7 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::make_idesc_bf16(128, 16, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
-    const uint64_t a_hi = tc::make_desc(0, (uint32_t)p.rows_alloc * 16, 128), b_hi = tc::make_desc(0, 16 * 16, 128);
+    const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc_sw(0, 256, 32);
     tc::mbar_wait(b_ready, 0);
     tc::tc_fence_after();
     uint32_t e = 0;
@@ -330,11 +329,11 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         for (int dy = 0; dy < 7; ++dy) {
           for (int dz = 0; dz < 7; ++dz) {
             const int tap = dy * 7 + dz;
-            const uint64_t a0 = a_hi | (uint64_t)((a_slot + (uint32_t)(dy * p.Zh + dz)) & 0x3FFF);
+            const uint64_t a0 = a_hi | (uint64_t)((a_slot + 2u * (uint32_t)(dy * p.Zh + dz)) & 0x3FFF);  // 32 B rows
             const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)tap * kTileBytesB) >> 4) & 0x3FFF);
             if (leader) {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 16, a0 + (uint64_t)(mt * 128), b0, idesc, (uint32_t)(tap != 0));
+              for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 16, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(tap != 0));
             }
             __syncwarp();
           }
@@ -394,21 +393,228 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// T[(dy,dz)][ci/8][n = dx][ci%8] = w(dx,dy,dz,ci) for dx < 7, else 0 (same flip convention as toeplitz_a_kernel)
+// T[(dy,dz)][n = dx][ci] = w(dx,dy,dz,ci) for dx < 7, else 0 (same flip convention as toeplitz_a_kernel), stored as a
+// K-major SWIZZLE_32B operand: 32-byte rows, 16-byte chunk c of row n lives at chunk c ^ ((n >> 2) & 1).
 __global__ void stack_b_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip) {
   const int total = kTapTilesB * 2 * 16 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c8 = i & 7;
     int t = i >> 3;
-    const int n = t & 15; t >>= 4;
-    const int chunk = t & 1;
-    const int tile = t >> 1;  // dy*7 + dz
+    const int pchunk = t & 1; t >>= 1;
+    const int n = t & 15;
+    const int tile = t >> 4;  // dy*7 + dz
+    const int chunk = pchunk ^ ((n >> 2) & 1);
     bf16 v = __float2bfloat16_rn(0.f);
     if (n < 7) {
       const int tap = n * 49 + tile;
       v = wp[(size_t)(flip ? 342 - tap : tap) * 16 + chunk * 8 + c8];
     }
     wt[i] = v;
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+//  (C) weight gradient of both layers:  R[c][dx,dy,dz] = sum_v S16[v, c] * Q1[v + (dx,dy,dz) - P]
+//      (S16 = the 16-channel tensor, Q1 = the 1-channel one; `first`: S16 = dY, Q1 = padded input, P = pad;
+//       `last_conv`: S16 = padded input, Q1 = dY, P = 6 - pad and the taps come out flipped).
+//      GEMM per K-block of 16 voxels (rows = flattened (y,z) of one x-plane, both operands MN-major):
+//        A: the z-EXPANDED 1-channel tensor E[v][j] = Q1[v + j*ez - P] (8 x 2 B = one 16-byte row, built by a pre-pass in
+//           the workspace).  M = 64 = 8 dy line-shifts (operand chunks one slab line apart) x 8 dz (the expansion).
+//        B: S16 planes.  N = 64 = 16 channels x 4 consecutive x-planes that sit in adjacent ring slots, i.e. one MMA
+//           produces 4 filter x-offsets at once.  The ring has 8 slots; the 7 live planes x'-6..x' fall into 2-3 aligned
+//           groups of 4, each group is one MMA whose accumulator column block is (plane - x' + 9); blocks 3..9 are the
+//           7 real dx accumulators, blocks 0..2 / 10..12 are guard columns that soak up planes outside the window.
+//      Split-K over CTAs (contiguous runs of x-planes of one (b, y-tile, z-tile) column), fp32 atomics at the end.
+struct ThinCPlan {
+  int B, Xs, Ys, Zs;  // S16 extents
+  int Xe, Ye;         // planes / lines of E (= Xs + 6, Ys + 6); E rows per line = Zs
+  int P, flip;
+  int Zt, nzt, Yt, nyt;
+  int rowsB, kblocks, e_slots;
+  uint32_t slotB_bytes, slotA_bytes, boxA_bytes, boxB_bytes, smem_bytes;
+};
+constexpr int kRingC = 8;
+
+__global__ void __launch_bounds__(192, 1)
+wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmS, float *__restrict__ dw,
+                      const __grid_constant__ ThinCPlan p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *ringB = smem;                                    // 8 S16 plane slots, each [2 chunks][rowsB][8 ch]
+  uint8_t *ringA = ringB + (size_t)kRingC * p.slotB_bytes;  // E slabs, [rowsA][8 j]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ringA + (size_t)p.e_slots * p.slotA_bytes);
+  uint64_t *b_full = bars, *b_empty = bars + kRingC, *a_full = b_empty + kRingC, *a_empty = a_full + p.e_slots;
+  uint64_t *done = a_empty + p.e_slots;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRingC; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.e_slots; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
+    tc::mbar_init(done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) {
+    tc::tmem_alloc(tmem_ptr, 256);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  // every MMA accumulates (column blocks are first touched at different times), so the accumulators start at zero
+  if (warp < 4) {
+    for (int c0 = 0; c0 < 256; c0 += 16) tc::tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0);
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  const long long ncols = (long long)p.B * p.nyt * p.nzt;
+  auto decode = [&](int col, int &b, int &y0, int &z0) {
+    const int zt = col % p.nzt; col /= p.nzt;
+    const int yt = col % p.nyt;
+    b = col / p.nyt;
+    y0 = yt * p.Yt;
+    z0 = zt * p.Zt;
+  };
+  bool any = false;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmE);
+      tc::tma_prefetch_desc(&tmS);
+      // S16 plane xs lives in ring slot (xs & 7); every segment re-loads its 6 warm-up planes
+      uint32_t useB[kRingC];
+#pragma unroll
+      for (int i = 0; i < kRingC; ++i) useB[i] = 0;
+      auto load_plane = [&](int xs, int b, int y0, int z0) {
+        const uint32_t slot = (uint32_t)(xs & 7);
+        uint32_t n = 0;
+#pragma unroll
+        for (int i = 0; i < kRingC; ++i) if ((uint32_t)i == slot) { n = useB[i]; useB[i] = n + 1; }
+        if (n > 0) tc::mbar_wait(&b_empty[slot], (n - 1) & 1);
+        tc::mbar_expect_tx(&b_full[slot], 2 * p.boxB_bytes);
+        uint8_t *dst = ringB + (size_t)slot * p.slotB_bytes;
+        tc::tma_load_5d(dst, &tmS, &b_full[slot], 0, z0, y0, xs, b);
+        tc::tma_load_5d(dst + (size_t)p.rowsB * 16, &tmS, &b_full[slot], 8, z0, y0, xs, b);
+      };
+      uint32_t ea = 0;
+      int col, x0, xlen;
+      for (SegIter it(ncols, p.Xe); it.next(col, x0, xlen);) {
+        int b, y0, z0;
+        decode(col, b, y0, z0);
+        for (int xs = x0 - 6; xs < x0; ++xs) load_plane(xs, b, y0, z0);
+        for (int i = 0; i < xlen; ++i, ++ea) {
+          load_plane(x0 + i, b, y0, z0);
+          const uint32_t slot = ea % p.e_slots, use = ea / p.e_slots;
+          if (use > 0) tc::mbar_wait(&a_empty[slot], (use - 1) & 1);
+          tc::mbar_expect_tx(&a_full[slot], p.boxA_bytes);
+          tc::tma_load_5d(ringA + (size_t)slot * p.slotA_bytes, &tmE, &a_full[slot], 0, z0, y0, x0 + i, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    const bool leader = tc::elect_one();
+    const uint32_t idesc = tc::make_idesc_bf16(64, 64, 1, 1);
+    const uint64_t a_hi = tc::make_desc(0, 128, (uint32_t)p.Zt * 16), b_hi = tc::make_desc(0, 128, (uint32_t)p.rowsB * 16);
+    const uint32_t ringA_u32 = tc::smem_u32(ringA), ringB_u32 = tc::smem_u32(ringB);
+    uint32_t useB[kRingC];
+#pragma unroll
+    for (int i = 0; i < kRingC; ++i) useB[i] = 0;
+    auto wait_plane = [&](int xs) {  // mirrors the producer's per-slot use count
+      const uint32_t slot = (uint32_t)(xs & 7);
+      uint32_t n = 0;
+#pragma unroll
+      for (int i = 0; i < kRingC; ++i) if ((uint32_t)i == slot) { n = useB[i]; useB[i] = n + 1; }
+      tc::mbar_wait(&b_full[slot], n & 1);
+    };
+    uint32_t ea = 0;
+    int col, x0, xlen;
+    for (SegIter it(ncols, p.Xe); it.next(col, x0, xlen);) {
+      any = true;
+      for (int xs = x0 - 6; xs < x0; ++xs) wait_plane(xs);
+      for (int i = 0; i < xlen; ++i, ++ea) {
+        const int xe = x0 + i;
+        wait_plane(xe);
+        const uint32_t slotA = ea % p.e_slots;
+        tc::mbar_wait(&a_full[slotA], (ea / p.e_slots) & 1);
+        tc::tc_fence_after();
+        const uint32_t a0 = (ringA_u32 + slotA * p.slotA_bytes) >> 4;
+        const int g_lo = (xe - 6) >> 2, g_hi = xe >> 2;  // aligned groups of 4 planes overlapping [xe-6, xe]
+        for (int g4 = g_lo; g4 <= g_hi; ++g4) {
+          const uint32_t slot0 = (uint32_t)((g4 * 4) & 7);
+          const uint32_t b0 = (ringB_u32 + slot0 * p.slotB_bytes) >> 4;
+          const uint32_t d = tmem_base + (uint32_t)((g4 * 4 - xe + 9) * 16);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const uint64_t a_desc = a_hi | (uint64_t)((a0 + (uint32_t)kb * 16) & 0x3FFF);
+            const uint64_t b_desc = b_hi | (uint64_t)((b0 + (uint32_t)kb * 16) & 0x3FFF);
+            if (leader) tc::umma_bf16(d, a_desc, b_desc, idesc, 1u);
+          }
+          __syncwarp();
+        }
+        if (leader) {
+          tc::umma_commit(&a_empty[slotA]);
+          tc::umma_commit(&b_empty[(uint32_t)((xe - 6) & 7)]);  // plane xe-6 is not needed by later steps
+        }
+        __syncwarp();
+      }
+      // the last 6 planes of the segment are still loaded: release their slots for the next segment
+      if (leader)
+        for (int xs = x0 + xlen - 6; xs < x0 + xlen; ++xs) tc::umma_commit(&b_empty[(uint32_t)(xs & 7)]);
+      __syncwarp();
+    }
+    if (leader) tc::umma_commit(done);
+    __syncwarp();
+  } else {
+    // epilogue (warps 0..3): M = 64 accumulator rows 16w..16w+15 live in TMEM lanes 32w..32w+15
+    SegIter it(ncols, p.Xe);
+    if (it.idx < it.end) {
+      tc::mbar_wait(done, 0);
+      tc::tc_fence_after();
+      const int m = warp * 16 + (lane & 15), dy = m >> 3, j = m & 7;
+      for (int blk = 3; blk <= 9; ++blk) {
+        uint32_t v[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * 16), v);
+        tc::tmem_ld_wait();
+        if (lane < 16 && dy < 7 && j < 7) {
+          int tap = (9 - blk) * 49 + dy * 7 + j;
+          if (p.flip) tap = 342 - tap;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) atomicAdd(&dw[(size_t)c * 343 + tap], __uint_as_float(v[c]));
+        }
+      }
+    }
+  }
+  (void)any;
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc(tmem_base, 256);
+}
+
+// E[b][xe][ye][z][j] = Q1[b][xe - P][ye - P][z + j - P]  (0 outside Q1), j = 0..7: one 16-byte row per (xe, ye, z)
+__global__ void expand_z_kernel(const bf16 *__restrict__ q, bf16 *__restrict__ e, int B, int Xq, int Yq, int Zq, int Xe, int Ye, int Ze,
+                                int P) {
+  const long long total = (long long)B * Xe * Ye * Ze;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int z = (int)(t % Ze); t /= Ze;
+    const int ye = (int)(t % Ye); t /= Ye;
+    const int xe = (int)(t % Xe);
+    const int b = (int)(t / Xe);
+    const int xq = xe - P, yq = ye - P;
+    uint32_t pk[4] = {0, 0, 0, 0};
+    if (xq >= 0 && xq < Xq && yq >= 0 && yq < Yq) {
+      const bf16 *line = q + (((size_t)b * Xq + xq) * Yq + yq) * Zq;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int zq = z + j - P;
+        const uint16_t h = (zq >= 0 && zq < Zq) ? __bfloat16_as_ushort(line[zq]) : (uint16_t)0;
+        pk[j >> 1] |= (uint32_t)h << ((j & 1) * 16);
+      }
+    }
+    reinterpret_cast<uint4 *>(e)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -419,12 +625,12 @@ typedef CUresult (*EncodeTiledFnT)(CUtensorMap *, CUtensorMapDataType, cuuint32_
 void *tc_encode_fn_ptr();  // conv_tc.cu
 
 static int encode_map(CUtensorMap *tm, const void *ptr, int rank, const cuuint64_t *gdim, const cuuint64_t *gstr,
-                      const cuuint32_t *box) {
+                      const cuuint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE) {
   EncodeTiledFnT enc = reinterpret_cast<EncodeTiledFnT>(tc_encode_fn_ptr());
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (thin conv) failed with %d", (int)r);
   return 0;
@@ -487,6 +693,9 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
   return true;
 }
 
+static bool plan_thin_c(const cgan3d_conv_geom &g, ThinCPlan &p);
+static size_t thin_c_workspace(const ThinCPlan &p);
+
 // op 0: gather with Cb == 16, Cs == 1;  op 1: scatter with Cb == 1, Cs == 16
 static bool thin_b_shape(const cgan3d_conv_geom &g, int op) {
   if (g.k != 7 || g.stride != 1) return false;
@@ -512,7 +721,7 @@ static bool plan_thin_b(const cgan3d_conv_geom &g, int op, ThinBPlan &best) {
     const int mt = ((Yt - 1) * p.Zh + p.Zt + 127) / 128;
     if (mt > 8) break;
     const int rows_alloc = round_up(mx(Yh * p.Zh, mt * 128 + 6 * p.Zh + 6), 8);
-    if (rows_alloc > 16383) break;
+    if (rows_alloc * 2 > 16383) break;
     const uint32_t slot = 2u * rows_alloc * 16;
     const int nslots = (int)mn<uint32_t>(4, (kSmemLimitThin - fixed) / slot);
     if (nslots < 2) break;
@@ -527,7 +736,7 @@ static bool plan_thin_b(const cgan3d_conv_geom &g, int op, ThinBPlan &best) {
     }
   }
   if (!found) return false;
-  best.box_bytes = 16u * best.Zh * best.Yh;
+  best.box_bytes = 32u * best.Zh * best.Yh;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * best.mtiles * 16)) cols <<= 1;
   best.tmem_cols = cols;
@@ -543,6 +752,10 @@ bool thin_supported(const cgan3d_conv_geom &g, int dtype, int op) {
     ThinBPlan pb;
     return plan_thin_b(g, op, pb);
   }
+  if (op == 2) {
+    ThinCPlan pc;
+    return plan_thin_c(g, pc);
+  }
   return false;
 }
 
@@ -554,6 +767,8 @@ size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   if ((op == 0 || op == 1) && plan_thin_a(g, op, p)) return (size_t)kTapTilesA * kTileBytesA + 256 + thin_a_repitch_bytes(p) + 256;
   ThinBPlan pb;
   if ((op == 0 || op == 1) && plan_thin_b(g, op, pb)) return (size_t)kTapTilesB * kTileBytesB + 256;
+  ThinCPlan pc;
+  if (op == 2 && plan_thin_c(g, pc)) return thin_c_workspace(pc);
   return 0;
 }
 
@@ -618,8 +833,8 @@ static int run_thin_b(const cgan3d_conv_geom &g, int op, const void *in, const v
   CUtensorMap tm;
   const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zi, (cuuint64_t)p.Yi, (cuuint64_t)p.Xi, (cuuint64_t)p.B};
   const cuuint64_t gstr[4] = {32, (cuuint64_t)p.Zi * 32, (cuuint64_t)p.Yi * p.Zi * 32, (cuuint64_t)p.Xi * p.Yi * p.Zi * 32};
-  const cuuint32_t box[5] = {8, (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
-  int r = encode_map(&tm, in, 5, gdim, gstr, box);
+  const cuuint32_t box[5] = {16, (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
+  int r = encode_map(&tm, in, 5, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_32B);
   if (r) return r;
   const long long total = (long long)p.B * p.nyt * p.nzt * p.Xo;
   const int grid = (int)mn<long long>(total, (long long)num_sms());
@@ -646,6 +861,84 @@ static int run_thin_b(const cgan3d_conv_geom &g, int op, const void *in, const v
     case 8: return launch(std::integral_constant<int, 8>{});
     default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: mtiles %d not built", p.mtiles);
   }
+}
+
+
+// wgrad of the thin layers: `first` (Cb == 1, Cs == 16): S16 = small, Q1 = big;  `last_conv` (Cb == 16, Cs == 1): S16 = big
+static bool plan_thin_c(const cgan3d_conv_geom &g, ThinCPlan &p) {
+  if (g.k != 7 || g.stride != 1) return false;
+  const bool first = g.Cb == 1 && g.Cs == 16, last = g.Cb == 16 && g.Cs == 1;
+  if (!first && !last) return false;
+  p = ThinCPlan{};
+  p.B = g.B;
+  if (first) { p.Xs = g.Xs; p.Ys = g.Ys; p.Zs = g.Zs; p.P = g.pad; p.flip = 0; }
+  else       { p.Xs = g.Xb; p.Ys = g.Yb; p.Zs = g.Zb; p.P = 6 - g.pad; p.flip = 1; }
+  p.Xe = p.Xs + 6; p.Ye = p.Ys + 6;
+  p.nzt = (p.Zs + 255) / 256;
+  p.Zt = round_up((p.Zs + p.nzt - 1) / p.nzt, 16);
+  if (p.Zt > 256) { p.nzt += 1; p.Zt = round_up((p.Zs + p.nzt - 1) / p.nzt, 16); }
+  p.Yt = mx(1, mn(p.Ys, 512 / p.Zt));
+  if (p.Yt + 7 > 256) return false;
+  p.nyt = (p.Ys + p.Yt - 1) / p.Yt;
+  p.rowsB = p.Yt * p.Zt;
+  p.kblocks = p.rowsB / 16;
+  p.slotB_bytes = 2u * p.rowsB * 16;
+  p.slotA_bytes = (uint32_t)(p.Yt + 7) * p.Zt * 16;
+  p.boxB_bytes = 16u * p.Zt * p.Yt;
+  p.boxA_bytes = p.slotA_bytes;
+  const uint32_t fixed = kRingC * p.slotB_bytes + 512;
+  if (fixed + 2 * p.slotA_bytes > kSmemLimitThin) return false;
+  p.e_slots = (int)mn<uint32_t>(4, (kSmemLimitThin - fixed) / p.slotA_bytes);
+  p.smem_bytes = fixed + p.e_slots * p.slotA_bytes;
+  return true;
+}
+
+static size_t thin_c_workspace(const ThinCPlan &p) { return (size_t)p.B * p.Xe * p.Ye * p.Zs * 16 + 256; }
+
+int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  ThinCPlan p;
+  if (!plan_thin_c(g, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin wgrad: shape not supported");
+  const size_t need = thin_c_workspace(p);
+  if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 thin wgrad: workspace %zu < %zu", ws_bytes, need);
+  const bool first = p.flip == 0;
+  const void *s16 = first ? small : big, *q1 = first ? big : small;
+  const int Xq = first ? g.Xb : g.Xs, Yq = first ? g.Yb : g.Ys, Zq = first ? g.Zb : g.Zs;
+  if ((reinterpret_cast<uintptr_t>(s16) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
+    return fail(CGAN3D_E_ARG, "tcgen05 thin wgrad: pointers must be 16-byte aligned");
+  if (beta == 0.f) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)16 * 343 * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_fail(e, "tcgen05 thin wgrad memset");
+  }
+  bf16 *E = reinterpret_cast<bf16 *>(ws);
+  expand_z_kernel<<<num_sms() * 16, 256, 0, st>>>(reinterpret_cast<const bf16 *>(q1), E, p.B, Xq, Yq, Zq, p.Xe, p.Ye, p.Zs, p.P);
+  CG_LAUNCH_CHECK("expand_z");
+  CUtensorMap tmE, tmS;
+  {
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)p.Zs, (cuuint64_t)p.Ye, (cuuint64_t)p.Xe, (cuuint64_t)p.B};
+    const cuuint64_t gstr[4] = {16, (cuuint64_t)p.Zs * 16, (cuuint64_t)p.Ye * p.Zs * 16, (cuuint64_t)p.Xe * p.Ye * p.Zs * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)p.Zt, (cuuint32_t)(p.Yt + 7), 1, 1};
+    int r = encode_map(&tmE, E, 5, gdim, gstr, box);
+    if (r) return r;
+  }
+  {
+    const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zs, (cuuint64_t)p.Ys, (cuuint64_t)p.Xs, (cuuint64_t)p.B};
+    const cuuint64_t gstr[4] = {32, (cuuint64_t)p.Zs * 32, (cuuint64_t)p.Ys * p.Zs * 32, (cuuint64_t)p.Xs * p.Ys * p.Zs * 32};
+    const cuuint32_t box[5] = {8, (cuuint32_t)p.Zt, (cuuint32_t)p.Yt, 1, 1};
+    int r = encode_map(&tmS, s16, 5, gdim, gstr, box);
+    if (r) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad7_thin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(wgrad7_thin_tc_kernel)");
+    attr_set = true;
+  }
+  const long long total = (long long)p.B * p.nyt * p.nzt * p.Xe;
+  const int grid = (int)mn<long long>(total, (long long)num_sms());
+  wgrad7_thin_tc_kernel<<<grid, 192, p.smem_bytes + 1024, st>>>(tmE, tmS, dw, p);
+  CG_LAUNCH_CHECK("wgrad7_thin_tc_kernel");
+  return 0;
 }
 
 int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,

@@ -119,6 +119,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr)
                : "memory");
 }
+// zero 32 lanes x 16 consecutive columns (warp w owns lanes 32*(w%4)..+31)
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
@@ -130,6 +139,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Swizzled K-major operand (rows of `swz_bytes` = 32 / 64 / 128 bytes of K, written by TMA with the matching
+// CU_TENSOR_MAP_SWIZZLE mode): 8-row groups are sbo_bytes apart; LBO is unused for K-major swizzled layouts.
+// The XOR pattern is a function of the shared-memory address bits, so a descriptor may start at any row.
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t sbo_bytes, uint32_t swz_bytes) {
+  const uint64_t layout = swz_bytes == 128 ? 2ull : (swz_bytes == 64 ? 4ull : 6ull);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+         (layout << 61);
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.  a_mn / b_mn: 1 = MN-major operand.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
