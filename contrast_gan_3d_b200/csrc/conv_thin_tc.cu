@@ -547,10 +547,14 @@ wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
           const uint32_t slot0 = (uint32_t)((g4 * 4) & 7);
           const uint32_t b0 = (ringB_u32 + slot0 * p.slotB_bytes) >> 4;
           const uint32_t d = tmem_base + (uint32_t)((g4 * 4 - xe + 9) * 16);
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            const uint64_t a_desc = a_hi | (uint64_t)((a0 + (uint32_t)kb * 16) & 0x3FFF);
-            const uint64_t b_desc = b_hi | (uint64_t)((b0 + (uint32_t)kb * 16) & 0x3FFF);
-            if (leader) tc::umma_bf16(d, a_desc, b_desc, idesc, 1u);
+          if (leader) {
+            uint64_t a_desc = a_hi | (uint64_t)(a0 & 0x3FFF), b_desc = b_hi | (uint64_t)(b0 & 0x3FFF);
+#pragma unroll 4
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              tc::umma_bf16(d, a_desc, b_desc, idesc, 1u);
+              a_desc += 16;
+              b_desc += 16;
+            }
           }
           __syncwarp();
         }

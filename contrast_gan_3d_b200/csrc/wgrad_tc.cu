@@ -113,14 +113,20 @@ wgrad_prog_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       tc::mbar_wait(&full[s], (n / p.stages) & 1);
       tc::tc_fence_after();
       const uint32_t a0 = (stage0 + s * p.stage_bytes) >> 4, b0 = (stage0 + s * p.stage_bytes + p.a_bytes) >> 4;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const uint64_t a_desc = a_hi | (uint64_t)((a0 + kb * 16) & 0x3FFF);
-        const uint32_t acc_on = (n | kb) != 0;
+      if (leader) {
+        // tap-major order: the per-tap constants stay in registers and the K loop is two descriptor adds per MMA
         for (int j = 0; j < p.nmma; ++j) {
           const WgMma &M = p.mma[j];
-          const uint64_t b_desc = b_hi | (uint64_t)((b0 + (uint32_t)M.src * kch_b * p.rowsB + kb * 16 + M.row_shift) & 0x3FFF);
           const uint32_t d = tmem_base + (uint32_t)((M.acc >> 1) * p.Cb) + ((uint32_t)((M.acc & 1) * 16) << 16);
-          if (leader) tc::umma_bf16(d, a_desc, b_desc, idesc, acc_on);
+          uint64_t a_desc = a_hi | (uint64_t)(a0 & 0x3FFF);
+          uint64_t b_desc = b_hi | (uint64_t)((b0 + (uint32_t)M.src * kch_b * p.rowsB + M.row_shift) & 0x3FFF);
+          tc::umma_bf16(d, a_desc, b_desc, idesc, n != 0 ? 1u : 0u);
+#pragma unroll 4
+          for (int kb = 1; kb < kblocks; ++kb) {
+            a_desc += 16;
+            b_desc += 16;
+            tc::umma_bf16(d, a_desc, b_desc, idesc, 1u);
+          }
         }
       }
       if (leader) tc::umma_commit(&empty[s]);
