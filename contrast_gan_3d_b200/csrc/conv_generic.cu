@@ -755,7 +755,77 @@ __global__ void reflect_pad_bwd_kernel(const T *__restrict__ gp, T *__restrict__
   }
 }
 
+// 16-byte-chunk versions (C * sizeof(T) % 16 == 0): one thread moves VEC = 16 / sizeof(T) channels of one voxel
+template <typename T>
+__global__ void reflect_pad_vec_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int X, int Y, int Z, int cpv,
+                                       int p) {
+  const int Xp = X + 2 * p, Yp = Y + 2 * p, Zp = Z + 2 * p;
+  const int64_t total = (int64_t)B * Xp * Yp * Zp * cpv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t line = i / (Zp * cpv);  // (b, x, y)
+    const int rem = (int)(i - line * (Zp * cpv));
+    const int z = rem / cpv, c = rem - z * cpv;
+    const int y = (int)(line % Yp);
+    const int64_t t = line / Yp;
+    const int x = (int)(t % Xp);
+    const int b = (int)(t / Xp);
+    const int sx = reflect_idx(x - p, X), sy = reflect_idx(y - p, Y), sz = reflect_idx(z - p, Z);
+    out[i] = in[((((int64_t)b * X + sx) * Y + sy) * Z + sz) * cpv + c];
+  }
+}
+
+template <typename T>
+__global__ void reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *__restrict__ gi, int B, int X, int Y, int Z, int cpv,
+                                           int p) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const int Yp = Y + 2 * p, Zp = Z + 2 * p, Xp = X + 2 * p;
+  const int64_t total = (int64_t)B * X * Y * Z * cpv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t line = i / (Z * cpv);
+    const int rem = (int)(i - line * (Z * cpv));
+    const int z = rem / cpv, c = rem - z * cpv;
+    const int y = (int)(line % Y);
+    const int64_t t = line / Y;
+    const int x = (int)(t % X);
+    const int b = (int)(t / X);
+    int sx[3], sy[3], sz[3];
+    const int nx = reflect_sources(x, X, p, sx), ny = reflect_sources(y, Y, p, sy), nz = reflect_sources(z, Z, p, sz);
+    if (nx == 1 && ny == 1 && nz == 1) {  // interior voxel: plain copy
+      gi[i] = gp[((((int64_t)b * Xp + sx[0]) * Yp + sy[0]) * Zp + sz[0]) * cpv + c];
+      continue;
+    }
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int a = 0; a < nx; ++a)
+      for (int bb = 0; bb < ny; ++bb)
+        for (int cc = 0; cc < nz; ++cc) {
+          const uint4 v = gp[((((int64_t)b * Xp + sx[a]) * Yp + sy[bb]) * Zp + sz[cc]) * cpv + c];
+          const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] += to_f(e[k]);
+        }
+    uint4 o;
+    T *e = reinterpret_cast<T *>(&o);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) e[k] = from_f<T>(acc[k]);
+    gi[i] = o;
+  }
+}
+
 int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z, int C, int pad, cudaStream_t st) {
+  const int esz = dtype == CGAN3D_F32 ? 4 : 2;
+  if ((C * esz) % 16 == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15)) {
+    const int cpv = C * esz / 16;
+    const int64_t tv = (int64_t)B * (X + 2 * pad) * (Y + 2 * pad) * (Z + 2 * pad) * cpv;
+    const int bl = (int)mn<int64_t>((tv + 255) / 256, (int64_t)num_sms() * 16);
+    if (dtype == CGAN3D_F32)
+      reflect_pad_vec_kernel<float><<<bl, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, B, X, Y, Z, cpv, pad);
+    else
+      reflect_pad_vec_kernel<__nv_bfloat16><<<bl, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, B, X, Y, Z, cpv, pad);
+    CG_LAUNCH_CHECK("reflect_pad_vec");
+    return 0;
+  }
   const int64_t total = (int64_t)B * (X + 2 * pad) * (Y + 2 * pad) * (Z + 2 * pad) * C;
   const int blocks = (int)mn<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == CGAN3D_F32)
@@ -769,6 +839,18 @@ int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z
 
 int reflect_pad_backward(const void *gp, void *gi, int dtype, int B, int X, int Y, int Z, int C, int pad,
                          cudaStream_t st) {
+  const int esz = dtype == CGAN3D_F32 ? 4 : 2;
+  if ((C * esz) % 16 == 0 && !((uintptr_t)gp & 15) && !((uintptr_t)gi & 15)) {
+    const int cpv = C * esz / 16;
+    const int64_t tv = (int64_t)B * X * Y * Z * cpv;
+    const int bl = (int)mn<int64_t>((tv + 255) / 256, (int64_t)num_sms() * 16);
+    if (dtype == CGAN3D_F32)
+      reflect_pad_bwd_vec_kernel<float><<<bl, 256, 0, st>>>((const uint4 *)gp, (uint4 *)gi, B, X, Y, Z, cpv, pad);
+    else
+      reflect_pad_bwd_vec_kernel<__nv_bfloat16><<<bl, 256, 0, st>>>((const uint4 *)gp, (uint4 *)gi, B, X, Y, Z, cpv, pad);
+    CG_LAUNCH_CHECK("reflect_pad_bwd_vec");
+    return 0;
+  }
   const int64_t total = (int64_t)B * X * Y * Z * C;
   const int blocks = (int)mn<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
   if (dtype == CGAN3D_F32)

@@ -12,6 +12,9 @@
 //   * scatter (big = conv_s2^T(small)): the 8 output parity phases (p,q,r) are 8 accumulators over the same small-grid
 //     rows; each (phase, tap) pair that exists is one row-shifted MMA group on the small-side slab of plane i+xo.
 //     The epilogue writes phase (p,q,r) of row (i,j,k) to big voxel (2i+p, 2j+q, 2k+r).
+//   * Thin critic layers: Cin == 8 (gather) forms K = 16 from TWO z-adjacent taps of a parity class -- the second
+//     8-channel K chunk is the same slab one row later (A-descriptor LBO = 16 bytes) and the filter tile holds the two
+//     taps back to back; N (output channels) < 16 is padded to 16 with zero filter columns and only Nout channels are stored.
 //   * All filter tiles ([Cin/8][N][8] bf16 each) stay RESIDENT in shared memory for the whole kernel (<= 108 KB for
 //     the layers of this model), so the only streamed operand is the activation slab; each slab is released as soon
 //     as its taps are issued (ring of slots, no cross-plane reuse: these layers are L2/HBM-bound).
@@ -41,7 +44,10 @@ struct ProgEntry {
 struct ProgPlan {
   int B, Xg, Yg, Zg;     // small ("grid") side extents: rows of every MMA live on this grid
   int Xo, Yo, Zo;        // output tensor extents
-  int Cin, N, nacc;
+  int Cin, N, nacc;      // N = MMA N (multiple of 16)
+  int Nout;              // channels actually stored (<= N)
+  int paired;            // 1: Cin == 8, K = 16 is two z-adjacent taps (tile t holds filter taps tile_tap[t][0..1])
+  uint32_t a_lbo_bytes;
   int in_scale;          // 2: gather from the big side (strided TMA), 1: scatter from the small side
   int out_scale;         // 1: gather, 2: scatter (output voxel = out_scale*grid + phase)
   int Zt, nzt, Zh, Yt, nslabs, Yh;
@@ -50,6 +56,7 @@ struct ProgPlan {
   uint32_t slot_bytes, btile_bytes, box_bytes, tmem_cols, smem_bytes;
   ProgEntry entries[kMaxEntries];
   ProgTap taps[kMaxTaps];
+  int8_t tile_tap[kMaxTaps][2];  // paired mode: filter taps of the two K chunks of tile t (-1 = zero)
 };
 
 template <int KSTEPS, int MT>
@@ -83,7 +90,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   // contiguous, balanced range of steps (column-major over (b, z-tile, y-slab) x output plane)
   const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
   const int s_begin = (int)(total * blockIdx.x / gridDim.x), s_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
-  const int kch = p.Cin >> 3;
+  const int kch = p.paired ? 1 : (p.Cin >> 3);
   auto decode = [&](int st, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x) {
     x = st % p.Xg; st /= p.Xg;
     const int sl = st % p.nslabs; st /= p.nslabs;
@@ -122,7 +129,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::make_idesc_bf16(128, p.N, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
-    const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16, b_lbo = (uint32_t)p.N * 16;
+    const uint32_t a_lbo = p.a_lbo_bytes, b_lbo = (uint32_t)p.N * 16;
     const uint64_t a_hi = tc::make_desc(0, a_lbo, 128), b_hi = tc::make_desc(0, b_lbo, 128);
     const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
     tc::mbar_wait(b_ready, 0);
@@ -180,9 +187,9 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           const int gy = r / p.Zh, gz = r - gy * p.Zh;
           const int oy = p.out_scale * (y0 + gy) + py, oz = p.out_scale * (z0 + gz) + pz;
           const bool valid = gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo;
-          bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.N;
+          bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.Nout;
           const uint32_t taddr = d_base + (uint32_t)(a * MT + mt) * p.N;
-          for (int c0 = 0; c0 < p.N; c0 += 16) {
+          for (int c0 = 0; c0 < p.Nout; c0 += 16) {
             uint32_t v[16];
             tc::tmem_ld16(taddr + c0, v);
             tc::tmem_ld_wait();
@@ -195,7 +202,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
               }
               uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
               d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              if (c0 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
           }
         }
@@ -210,19 +217,27 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// [tap][Cb][Cs] (generic packed) -> resident tiles [tap][Cin/8][N][8]; gather: Cin=Cb,N=Cs; scatter: Cin=Cs,N=Cb
-__global__ void repack_prog_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int taps, int scatter) {
-  const int Cin = scatter ? Cs : Cb, N = scatter ? Cb : Cs;
-  const int64_t total = (int64_t)taps * Cin * N;
+// [tap][Cb][Cs] (generic packed) -> resident tiles [tile][K/8][N][8]; gather: Cin=Cb, Nout=Cs; scatter: Cin=Cs, Nout=Cb.
+// Normal mode: tile == filter tap, K = Cin.  Paired mode (Cin == 8): K chunk h of tile t holds filter tap tile_tap[t][h].
+// Columns n >= Nout are zero.
+__global__ void repack_prog_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int scatter,
+                                   const __grid_constant__ ProgPlan p) {
+  const int K = p.paired ? 16 : p.Cin, N = p.N;
+  const int64_t total = (int64_t)p.nbt * K * N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i & 7);
     int64_t t = i >> 3;
     const int n = (int)(t % N); t /= N;
-    const int cc = (int)(t % (Cin >> 3));
-    const int tap = (int)(t / (Cin >> 3));
-    const int ci = cc * 8 + c8;
-    const int cb = scatter ? n : ci, cs = scatter ? ci : n;
-    wb[i] = wp[((int64_t)tap * Cb + cb) * Cs + cs];
+    const int cc = (int)(t % (K >> 3));
+    const int tile = (int)(t / (K >> 3));
+    const int tap = p.paired ? p.tile_tap[tile][cc] : tile;
+    const int ci = p.paired ? c8 : cc * 8 + c8;
+    bf16 v = __float2bfloat16_rn(0.f);
+    if (n < p.Nout && tap >= 0) {
+      const int cb = scatter ? n : ci, cs = scatter ? ci : n;
+      v = wp[((int64_t)tap * Cb + cb) * Cs + cs];
+    }
+    wb[i] = v;
   }
 }
 
@@ -242,9 +257,27 @@ static bool build_program(const cgan3d_conv_geom &g, int scatter, ProgPlan &p) {
           ProgEntry E{};
           E.cx = (int8_t)(dx - 1); E.cy = (int8_t)(-q); E.cz = (int8_t)(-r);
           E.tap0 = (uint8_t)nt; E.ntaps = 0;
-          for (int dy = 0; dy < k; ++dy)
+          for (int dy = 0; dy < k; ++dy) {
+            if (cls(dy) != q) continue;
+            if (p.paired) {
+              // the (1 or 2) z taps of this class become the two K chunks of one MMA: rows r + shift and r + shift + 1
+              int dzs[2] = {-1, -1}, nz = 0;
+              for (int dz = 0; dz < k; ++dz)
+                if (cls(dz) == r) dzs[nz++] = dz;
+              if (nz == 2 && shift(dzs[1]) != shift(dzs[0]) + 1) return false;
+              if (nt >= kMaxTaps) return false;
+              ProgTap T{};
+              T.row_shift = (uint16_t)(shift(dy) * p.Zh + shift(dzs[0]));
+              T.btile = (uint8_t)nt;
+              p.tile_tap[nt][0] = (int8_t)((dx * k + dy) * k + dzs[0]);
+              p.tile_tap[nt][1] = (int8_t)(nz == 2 ? (dx * k + dy) * k + dzs[1] : -1);
+              T.acc = 0; T.first = first ? 1 : 0;
+              first = false;
+              p.taps[nt++] = T; E.ntaps++;
+              continue;
+            }
             for (int dz = 0; dz < k; ++dz) {
-              if (cls(dy) != q || cls(dz) != r) continue;
+              if (cls(dz) != r) continue;
               if (nt >= kMaxTaps) return false;
               ProgTap T{};
               T.row_shift = (uint16_t)(shift(dy) * p.Zh + shift(dz));
@@ -253,6 +286,7 @@ static bool build_program(const cgan3d_conv_geom &g, int scatter, ProgPlan &p) {
               first = false;
               p.taps[nt++] = T; E.ntaps++;
             }
+          }
           if (E.ntaps == 0) continue;
           if (ne >= kMaxEntries) return false;
           p.entries[ne++] = E;
@@ -303,9 +337,11 @@ static bool build_program(const cgan3d_conv_geom &g, int scatter, ProgPlan &p) {
 
 static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best) {
   if (g.stride != 2 || g.pad != 1 || (g.k != 3 && g.k != 4)) return false;
-  const int Cin = scatter ? g.Cs : g.Cb, N = scatter ? g.Cb : g.Cs;
-  if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
-  if (N % 16 || N < 16 || N > 256) return false;
+  const int Cin = scatter ? g.Cs : g.Cb, Nout = scatter ? g.Cb : g.Cs;
+  const int paired = (!scatter && Cin == 8) ? 1 : 0;
+  if (!paired && Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
+  if (Nout % 8 || Nout < 8 || Nout > 256 || (Nout > 8 && Nout % 16)) return false;
+  const int N = Nout < 16 ? 16 : Nout;
   const int nacc = scatter ? 8 : 1;
   // every big-side voxel must belong to a phase of some small-grid row (holds for transposed convs and for the dgrad of
   // convs over even extents; an odd extent with k = 4 has one more plane than 2*small)
@@ -315,10 +351,10 @@ static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best) {
   ProgPlan p{};
   p.B = g.B; p.Xg = g.Xs; p.Yg = g.Ys; p.Zg = g.Zs;
   p.Xo = scatter ? g.Xb : g.Xs; p.Yo = scatter ? g.Yb : g.Ys; p.Zo = scatter ? g.Zb : g.Zs;
-  p.Cin = Cin; p.N = N; p.nacc = nacc;
+  p.Cin = Cin; p.N = N; p.nacc = nacc; p.Nout = Nout; p.paired = paired;
   p.in_scale = scatter ? 1 : 2; p.out_scale = scatter ? 2 : 1;
-  p.nbt = taps;
-  p.btile_bytes = (uint32_t)Cin * N * 2;
+  p.nbt = paired ? taps / 2 + (g.k == 3 ? 9 : 0) : taps;  // upper bound; build_program fixes the exact count
+  p.btile_bytes = (uint32_t)(paired ? 16 : Cin) * N * 2;
   const uint32_t b_total = p.nbt * p.btile_bytes;
   if (b_total + 40000 > kSmemLimitProg) return false;
   double best_score = 0;
@@ -333,7 +369,7 @@ static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best) {
       if (mt > 4 || 2 * nacc * mt * N > 512) break;
       const int rows_alloc = ((mt * 128 + halo * Zh + halo) + 7) / 8 * 8;
       if (rows_alloc > 16383 || Yh * Zh > rows_alloc) continue;
-      const uint32_t slot = (uint32_t)(Cin / 8) * rows_alloc * 16;
+      const uint32_t slot = (uint32_t)(paired ? 1 : Cin / 8) * rows_alloc * 16;
       const int nslots = (int)mn<uint32_t>(8, (kSmemLimitProg - b_total - 512) / slot);
       if (nslots < 3) break;
       const int nslabs = (p.Yg + Yt - 1) / Yt;
@@ -357,7 +393,13 @@ static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best) {
   while (cols < (uint32_t)(2 * nacc * q.mtiles * N)) cols <<= 1;
   q.tmem_cols = cols;
   q.smem_bytes = b_total + q.nslots * q.slot_bytes + 512;
-  return build_program(g, scatter, q);
+  q.a_lbo_bytes = paired ? 16u : (uint32_t)q.rows_alloc * 16;
+  if (!build_program(g, scatter, q)) return false;
+  if (paired) {
+    if ((uint32_t)q.ntaps * q.btile_bytes > b_total) return false;
+    q.nbt = q.ntaps;
+  }
+  return true;
 }
 
 bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op) {
@@ -368,7 +410,7 @@ bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op) {
 
 size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   if (dtype != CGAN3D_BF16 || (op != 0 && op != 1)) return 0;
-  return (size_t)g.k * g.k * g.k * g.Cb * g.Cs * 2 + 256;
+  return (size_t)g.k * g.k * g.k * mx(g.Cb, 16) * mx(g.Cs, 16) * 2 + 256;
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -387,10 +429,11 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
   EncodeTiledFn2 enc = reinterpret_cast<EncodeTiledFn2>(tc_encode_fn_ptr());
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   bf16 *wb = reinterpret_cast<bf16 *>(ws);
-  repack_prog_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, p.nbt, scatter);
+  repack_prog_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, scatter, p);
   CG_LAUNCH_CHECK("repack_prog");
   // input tensor: gather reads the big side with element strides 2 on z and y; scatter reads the small side densely
   const int Xi = scatter ? g.Xs : g.Xb, Yi = scatter ? g.Ys : g.Yb, Zi = scatter ? g.Zs : g.Zb, Ci = p.Cin;
+  if ((reinterpret_cast<uintptr_t>(outp) & 15) || (p.Nout * 2) % 16) return fail(CGAN3D_E_ARG, "tcgen05 strided conv: output rows must be 16-byte aligned");
   const int es = p.in_scale;
   CUtensorMap tm;
   const cuuint64_t gdim[5] = {(cuuint64_t)Ci, (cuuint64_t)Zi, (cuuint64_t)Yi, (cuuint64_t)Xi, (cuuint64_t)g.B};
@@ -427,7 +470,7 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
       default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: mtiles %d not built", p.mtiles);
     }
   };
-  switch (p.Cin >> 4) {
+  switch (p.paired ? 1 : (p.Cin >> 4)) {
     case 1: return by_mt(std::integral_constant<int, 1>{});
     case 2: return by_mt(std::integral_constant<int, 2>{});
     case 4: return by_mt(std::integral_constant<int, 4>{});

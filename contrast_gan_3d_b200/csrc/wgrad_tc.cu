@@ -11,6 +11,7 @@
 //   * Cs == 64: M = 64 rows are the 64 channels.  Cs == 32: the small-side slab is loaded TWICE, the second copy one
 //     row (one voxel along z) later, so that rows 32..63 of D pair dY[r-1] with X[r+s] == the tap with shift s+1:
 //     one MMA then produces two z-adjacent taps.
+//     Cs == 16: four copies, shifted by (0|1 line, 0|1 voxel): one MMA produces a 2x2 block of (dy, dz) taps.
 //   * A CTA owns one dx (filter x-offset) and a contiguous range of (b, y-slab, x) steps; M = 64 accumulators are
 //     interleaved two per N TMEM columns; split-K over CTAs, partial sums added with red.global.add.f32.
 #include "common.cuh"
@@ -32,12 +33,12 @@ struct WgPlan {
   int Cb, Cs, k, stride, taps;
   int Zh, Yt, Yh, nslabs;
   int kpad, rowsA, rowsB;
-  int ncopies;          // 1 (Cs == 64) or 2 (Cs == 32, second copy shifted by one row)
+  int ncopies;          // 1 (Cs == 64), 2 (Cs == 32: second copy one row later) or 4 (Cs == 16: 2x2 line/row shifts)
   int nsrc, nmma, nacc;
   int steps_per_dx, stages;
   int8_t src_cy[kMaxWgSrc], src_cz[kMaxWgSrc];
   WgMma mma[kMaxWgMma];
-  int8_t acc_tap[kMaxWgMma][2];  // (dy*k+dz) produced by rows 0..31 / 32..63 (or both == same tap when ncopies == 1); -1 = discard
+  int8_t acc_tap[kMaxWgMma][4];  // (dy*k+dz) produced by each 64/ncopies-row group of D (all equal when ncopies == 1); -1 = discard
   uint32_t a_bytes, b_bytes, boxA_bytes, boxB_bytes, stage_bytes, smem_bytes, tmem_cols;
 };
 
@@ -94,7 +95,7 @@ wgrad_prog_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         uint8_t *a = stage_mem + (size_t)s * p.stage_bytes, *bb = a + p.a_bytes;
         for (int c = 0; c < p.ncopies; ++c)
           for (int cc = 0; cc < kch_a; ++cc)
-            tc::tma_load_5d(a + (size_t)(c * kch_a + cc) * p.rowsA * 16, &tmY, &full[s], cc * 8, -c, y0, x, b);
+            tc::tma_load_5d(a + (size_t)(c * kch_a + cc) * p.rowsA * 16, &tmY, &full[s], cc * 8, -(c & 1), y0 - (c >> 1), x, b);
         for (int sr = 0; sr < p.nsrc; ++sr)
           for (int cc = 0; cc < kch_b; ++cc)
             tc::tma_load_5d(bb + (size_t)(sr * kch_b + cc) * p.rowsB * 16, &tmX, &full[s], cc * 8, p.src_cz[sr],
@@ -140,8 +141,8 @@ wgrad_prog_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       tc::mbar_wait(done, 0);
       tc::tc_fence_after();
       const int m = warp * 16 + (lane & 15);                       // row of D
-      const int cs = p.ncopies == 2 ? (m & 31) : m;
-      const int half = p.ncopies == 2 ? (m >> 5) : 0;
+      const int cs = m % p.Cs;
+      const int half = m / p.Cs;                                   // which shifted copy this row belongs to
       const int ngroups = (p.nacc + 1) >> 1;
       for (int g2 = 0; g2 < ngroups; ++g2) {
         const int j = g2 * 2 + (lane >> 4);
@@ -153,7 +154,8 @@ wgrad_prog_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
           tc::tmem_ld_wait();
           if (t2 >= 0) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) atomicAdd(&dw[((size_t)cs * p.Cb + (c0 + c)) * p.taps + tap], __uint_as_float(v[c]));
+            for (int c = 0; c < 16; ++c)
+              if (c0 + c < p.Cb) atomicAdd(&dw[((size_t)cs * p.Cb + (c0 + c)) * p.taps + tap], __uint_as_float(v[c]));
           }
         }
       }
@@ -168,30 +170,38 @@ static bool plan_wgrad(const cgan3d_conv_geom &g, WgPlan &p) {
   const int k = g.k, s = g.stride;
   if (g.pad != 1) return false;
   if (!((s == 1 && k == 3) || (s == 2 && (k == 3 || k == 4)))) return false;
-  if (g.Cs != 64 && g.Cs != 32) return false;
-  if (g.Cb % 16 || g.Cb < 16 || g.Cb > 64) return false;
+  if (g.Cs != 64 && g.Cs != 32 && g.Cs != 16) return false;
+  if (g.Cb % 8 || g.Cb < 8 || g.Cb > 64) return false;
   if (s == 1 && (g.Xb != g.Xs || g.Yb != g.Ys || g.Zb != g.Zs)) return false;
   p = WgPlan{};
   p.B = g.B; p.X = g.Xs; p.Y = g.Ys; p.Z = g.Zs; p.Cb = g.Cb; p.Cs = g.Cs; p.k = k; p.stride = s; p.taps = k * k * k;
   const int halo = s == 1 ? 2 : 1;
   p.Zh = p.Z + halo;
   if (s * (p.Zh - 1) + 1 > 256) return false;
-  p.ncopies = g.Cs == 64 ? 1 : 2;
+  p.ncopies = 64 / g.Cs;
   p.stages = 2;
   // ---- MMA program for one (dx) plane
   int nm = 0, na = 0;
-  auto add = [&](int src, int shift, int tap0, int tap1) {
+  auto add4 = [&](int src, int shift, int t0, int t1, int t2, int t3) {
+    if (nm >= kMaxWgMma) { ++nm; return; }
     p.mma[nm].src = (uint8_t)src; p.mma[nm].row_shift = (uint16_t)shift; p.mma[nm].acc = (uint8_t)na;
-    p.acc_tap[na][0] = (int8_t)tap0; p.acc_tap[na][1] = (int8_t)tap1;
+    p.acc_tap[na][0] = (int8_t)t0; p.acc_tap[na][1] = (int8_t)t1; p.acc_tap[na][2] = (int8_t)t2; p.acc_tap[na][3] = (int8_t)t3;
     ++nm; ++na;
   };
+  auto add = [&](int src, int shift, int tap0, int tap1) { add4(src, shift, tap0, tap1, tap0, tap1); };
   if (s == 1) {
     p.nsrc = 1; p.src_cy[0] = -1; p.src_cz[0] = -1;
     if (p.ncopies == 1) {
       for (int dy = 0; dy < 3; ++dy)
         for (int dz = 0; dz < 3; ++dz) add(0, dy * p.Zh + dz, dy * 3 + dz, dy * 3 + dz);
-    } else {  // pairs (dz, dz+1): (0,1) and (2,-)
+    } else if (p.ncopies == 2) {  // pairs (dz, dz+1): (0,1) and (2,-)
       for (int dy = 0; dy < 3; ++dy) { add(0, dy * p.Zh + 0, dy * 3 + 0, dy * 3 + 1); add(0, dy * p.Zh + 2, dy * 3 + 2, -1); }
+    } else {  // 2x2 blocks of (dy, dz): copy (cy, cz) yields tap (dy0 + cy, dz0 + cz)
+      for (int dy0 = 0; dy0 < 3; dy0 += 2)
+        for (int dz0 = 0; dz0 < 3; dz0 += 2) {
+          auto t = [&](int cy, int cz) { return (dy0 + cy < 3 && dz0 + cz < 3) ? (dy0 + cy) * 3 + dz0 + cz : -1; };
+          add4(0, dy0 * p.Zh + dz0, t(0, 0), t(0, 1), t(1, 0), t(1, 1));
+        }
     }
   } else {
     // parity classes as in conv_tc_prog.cu: class c of tap d = (d-1)&1, row shift = (d - 1 + c) / 2, slab start = 2*o - c
@@ -202,6 +212,14 @@ static bool plan_wgrad(const cgan3d_conv_geom &g, WgPlan &p) {
       for (int r = 0; r < 2; ++r) {
         const int src = q * 2 + r;
         p.src_cy[src] = (int8_t)(-q); p.src_cz[src] = (int8_t)(-r);
+        if (p.ncopies == 4) {
+          // taps of this class along each axis, ordered by shift (1 or 2 of them); copy (cy, cz) <-> (dys[cy], dzs[cz])
+          int dys[2], ny = 0, dzs4[2], nz4 = 0;
+          for (int d = 0; d < k; ++d) { if (cls(d) == q) dys[ny++] = d; if (cls(d) == r) dzs4[nz4++] = d; }
+          auto t = [&](int cy, int cz) { return (cy < ny && cz < nz4) ? dys[cy] * k + dzs4[cz] : -1; };
+          add4(src, shf(dys[0]) * p.Zh + shf(dzs4[0]), t(0, 0), t(0, 1), t(1, 0), t(1, 1));
+          continue;
+        }
         for (int dy = 0; dy < k; ++dy) {
           if (cls(dy) != q) continue;
           // z taps of this class, ordered by shift
@@ -239,8 +257,10 @@ static bool plan_wgrad(const cgan3d_conv_geom &g, WgPlan &p) {
     break;
   }
   if (!ok) return false;
-  p.nslabs = (p.Y + p.Yt - 1) / p.Yt;
-  p.Yt = (p.Y + p.nslabs - 1) / p.nslabs;  // balance the slabs
+  // with line-shifted copies the copy that starts one line earlier covers lines y0-1 .. y0+Yt-2: tile Y+1 lines
+  const int ylines = p.Y + (p.ncopies == 4 ? 1 : 0);
+  p.nslabs = (ylines + p.Yt - 1) / p.Yt;
+  p.Yt = (ylines + p.nslabs - 1) / p.nslabs;  // balance the slabs
   p.Yh = p.Yt + yh_extra;
   p.kpad = (p.Yt * p.Zh + 15) / 16 * 16;
   p.rowsA = p.kpad;
