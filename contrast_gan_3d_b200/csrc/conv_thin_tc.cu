@@ -215,16 +215,18 @@ __global__ void shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restr
 
 
 // ---------------------------------------------------------------------------------------------------------------
-//  (B) 16 -> 1 channels (fprop of `last_conv`, dgrad of `first`): filter x-offsets STACKED ON N + register window.
-//      GEMM rows = flattened (y', z') positions of one input x-plane slab (as in conv_tc.cu), K = 16 input channels,
-//      and the 49 (dy,dz) taps are row shifts accumulated by the tensor core.  The GEMM N dimension carries the 7
-//      filter x-offsets: D_xi[row, dx] is the contribution of input plane xi to output plane xi + P - dx.  Every input
-//      plane is streamed through shared memory exactly once; the epilogue thread that owns a row keeps a 7-deep
-//      register window of partial outputs, adds the 7 columns of each new plane and retires one finished output
-//      plane per input plane (coalesced along z).  N = 16 is the smallest M=128 tile, so this shape is bound by the
-//      shared-memory read of A (4 KB per MMA).
-constexpr int kTapTilesB = 49;
-constexpr uint32_t kTileBytesB = 512;  // [2 ci-chunks][16 n = dx][8 ci] bf16
+//  (B) 16 -> 1 channels (fprop of `last_conv`, dgrad of `first`): filter x- AND z-offsets STACKED ON N.
+//      GEMM rows = flattened (y', z') positions of one input x-plane slab (pitch Zh = Zt + 6, as in conv_tc.cu),
+//      K = 16 input channels (one 32-byte SWIZZLE_32B row per voxel, one TMA per slab), and only the 7 dy taps are row
+//      shifts accumulated by the tensor core.  N = 64 carries (dx, dz): D_xi[row, (dx,dz)] is the contribution of input
+//      plane xi, input row `row`, to output plane xi + P - dx, output row `row - dz`.  An SS-mode tcgen05.mma costs
+//      >= 72 cycles whatever its N (measured, tools/micro/mma_bench.cu), so 7 MMAs of N = 64 replace 49 of N = 16.
+//      Epilogue: the slab pitch is exactly 32 rows per y-line (26 outputs + 6 halo voxels along z), so a line is one
+//      32-lane TMEM group and the z shift is undone with warp shuffles alone; the x shift is undone with a 7-deep
+//      register window of partial output planes per thread; one finished output plane is retired per input plane.
+constexpr int kTapTilesB = 7;
+constexpr uint32_t kTileBytesB = 2048;  // [64 n = dx*8 + dz][16 ci] bf16, SWIZZLE_32B rows
+constexpr int kPitchB = 32, kZtB = 26;    // rows per slab line / outputs per line
 
 struct ThinBPlan {
   int B, Xi, Yi, Zi;  // 16-channel input
@@ -233,6 +235,7 @@ struct ThinBPlan {
   int Zt, nzt, Zh, Yt, nyt, Yh;
   int mtiles, rows_alloc, nslots;
   uint32_t slot_bytes, box_bytes, tmem_cols, smem_bytes;
+  int debug;  // CGAN3D_THIN_DEBUG (profiling aid): 1 = skip the MMAs, 2 = skip the epilogue math
 };
 
 struct SegIter {
@@ -254,12 +257,12 @@ struct SegIter {
 };
 
 template <int MT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wT, bf16 *__restrict__ out,
                     const __grid_constant__ ThinBPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *bres = smem;
-  uint8_t *ring = bres + 25600;  // 49 * 512 rounded up to a multiple of 1024
+  uint8_t *bres = smem;                                                   // 7 resident filter tiles (14 KB)
+  uint8_t *ring = smem + 14336;                                            // slab slots (multiple of 256 B)
   uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)p.nslots * p.slot_bytes);
   uint64_t *b_ready = bars, *s_full = bars + 1, *s_empty = s_full + p.nslots;
   uint64_t *tm_full = s_empty + p.nslots, *tm_empty = tm_full + 2;
@@ -269,10 +272,10 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   if (threadIdx.x == 0) {
     tc::mbar_init(b_ready, 1);
     for (int i = 0; i < p.nslots; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 8); }
     tc::fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tc::tmem_alloc(tmem_ptr, p.tmem_cols);
     tc::tmem_relinquish();
   }
@@ -289,7 +292,7 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
     z0 = zt * p.Zt; zlen = min(p.Zt, p.Zo - z0);
   };
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmA);
       tc::mbar_expect_tx(b_ready, kTapTilesB * kTileBytesB);
@@ -303,15 +306,13 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           const uint32_t slot = e % p.nslots, use = e / p.nslots;
           if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
           tc::mbar_expect_tx(&s_full[slot], p.box_bytes);
-          uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
-          const int xi = x0 - p.P + i;
-          tc::tma_load_5d(dst, &tmA, &s_full[slot], 0, z0 - p.P, y0 - p.P, xi, b);
+          tc::tma_load_5d(ring + (size_t)slot * p.slot_bytes, &tmA, &s_full[slot], 0, z0 - p.P, y0 - p.P, x0 - p.P + i, b);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(128, 16, 0, 0);
+    const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
     const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc_sw(0, 256, 32);
     tc::mbar_wait(b_ready, 0);
@@ -325,20 +326,16 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         tc::mbar_wait(&s_full[slot], (e / p.nslots) & 1);
         tc::tc_fence_after();
         const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
-        const uint32_t d_base = tmem_base + q * (uint32_t)(MT * 16);
-        for (int dy = 0; dy < 7; ++dy) {
-          for (int dz = 0; dz < 7; ++dz) {
-            const int tap = dy * 7 + dz;
-            const uint64_t a0 = a_hi | (uint64_t)((a_slot + 2u * (uint32_t)(dy * p.Zh + dz)) & 0x3FFF);  // 32 B rows
-            const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)tap * kTileBytesB) >> 4) & 0x3FFF);
-            if (leader) {
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 16, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(tap != 0));
-            }
-            __syncwarp();
-          }
-        }
+        const uint32_t d_base = tmem_base + q * (uint32_t)(MT * 64);
         if (leader) {
+#pragma unroll
+          for (int dy = 0; dy < 7; ++dy) {
+            if (p.debug & 1) continue;
+            const uint64_t a0 = a_hi | (uint64_t)((a_slot + 2u * (uint32_t)(dy * kPitchB)) & 0x3FFF);  // 32-byte rows
+            const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)dy * kTileBytesB) >> 4) & 0x3FFF);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 64, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(dy != 0));
+          }
           tc::umma_commit(&s_empty[slot]);
           tc::umma_commit(&tm_full[q]);
         }
@@ -346,41 +343,57 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
       }
     }
   } else {
+    // 8 epilogue warps: TMEM lane quadrant qd = warp & 3 (= y-line qd of every M-tile, lane = z within the line);
+    // warps 0-3 own the even M-tiles, warps 4-7 the odd ones
+    constexpr int NK = (MT + 1) / 2;
+    const int qd = warp & 3, grp = warp >> 2;
     uint32_t e = 0;
     int col, x0, xlen;
     for (SegIter it(ncols, p.Xo); it.next(col, x0, xlen);) {
       int b, y0, ylen, z0, zlen;
       decode(col, b, y0, ylen, z0, zlen);
-      float win[MT][7];
-      bool valid[MT];
-      size_t off[MT];
+      float win[NK][7];
+      bool valid[NK];
+      uint32_t off[NK];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int k = 0; k < NK; ++k) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) win[mt][j] = 0.f;
-        const int r = mt * 128 + warp * 32 + lane;
-        const int yy = r / p.Zh, zz = r - yy * p.Zh;
-        valid[mt] = yy < ylen && zz < zlen;
-        off[mt] = ((size_t)(y0 + yy)) * p.Zo + (z0 + zz);
+        for (int j = 0; j < 7; ++j) win[k][j] = 0.f;
+        const int mt = 2 * k + grp;
+        const int yy = mt * 4 + qd;
+        valid[k] = mt < MT && yy < ylen && lane < zlen;
+        off[k] = (uint32_t)((y0 + yy) * p.Zo + (z0 + lane));
       }
       for (int i = 0; i < xlen + 6; ++i, ++e) {
         const uint32_t q = e & 1;
         tc::mbar_wait(&tm_full[q], (e >> 1) & 1);
         tc::tc_fence_after();
-        const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(MT * 16);
+        const uint32_t d_base = tmem_base + ((uint32_t)(qd * 32) << 16) + q * (uint32_t)(MT * 64);
         bf16 *plane = out + ((size_t)b * p.Xo + (x0 + i - 6)) * p.Yo * p.Zo;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          uint32_t v[8];
-          tc::tmem_ld8(d_base + (uint32_t)(mt * 16), v);
+        for (int k = 0; k < NK; ++k) {
+          const int mt = 2 * k + grp;
+          if (mt >= MT || (p.debug & 2)) continue;
+          uint32_t v[7][8];
+#pragma unroll
+          for (int dx = 0; dx < 7; ++dx) tc::tmem_ld8(d_base + (uint32_t)(mt * 64 + dx * 8), v[dx]);
           tc::tmem_ld_wait();
-          // column dx feeds output plane (this input plane) + P - dx == window slot 6 - dx
+          // out[z] = sum_dz D[z + dz][(dx, dz)]: lanes z >= 26 read past the line, they are halo rows and never stored
+          float t[7];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) win[mt][j] += __uint_as_float(v[6 - j]);
-          if (i >= 6 && valid[mt]) plane[off[mt]] = __float2bfloat16_rn(win[mt][0]);
+          for (int dx = 0; dx < 7; ++dx) {
+            float acc = __uint_as_float(v[dx][0]);
 #pragma unroll
-          for (int j = 0; j < 6; ++j) win[mt][j] = win[mt][j + 1];
-          win[mt][6] = 0.f;
+            for (int dz = 1; dz < 7; ++dz) acc += __shfl_down_sync(0xffffffffu, __uint_as_float(v[dx][dz]), dz);
+            t[dx] = acc;
+          }
+          // column block dx feeds output plane (this input plane) + P - dx == window slot 6 - dx
+#pragma unroll
+          for (int j = 0; j < 7; ++j) win[k][j] += t[6 - j];
+          if (i >= 6 && valid[k]) plane[off[k]] = __float2bfloat16_rn(win[k][0]);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) win[k][j] = win[k][j + 1];
+          win[k][6] = 0.f;
         }
         tc::tc_fence_before();
         __syncwarp();
@@ -390,29 +403,29 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 9) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// T[(dy,dz)][n = dx][ci] = w(dx,dy,dz,ci) for dx < 7, else 0 (same flip convention as toeplitz_a_kernel), stored as a
-// K-major SWIZZLE_32B operand: 32-byte rows, 16-byte chunk c of row n lives at chunk c ^ ((n >> 2) & 1).
+// T[dy][n = dx*8 + dz][ci] = w(dx,dy,dz,ci) for dx, dz < 7, else 0 (same flip convention as toeplitz_a_kernel), stored as
+// a K-major SWIZZLE_32B operand: 32-byte rows, 16-byte chunk c of row n lives at chunk c ^ ((n >> 2) & 1).
 __global__ void stack_b_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip) {
-  const int total = kTapTilesB * 2 * 16 * 8;
+  const int total = kTapTilesB * 64 * 16;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c8 = i & 7;
     int t = i >> 3;
     const int pchunk = t & 1; t >>= 1;
-    const int n = t & 15;
-    const int tile = t >> 4;  // dy*7 + dz
+    const int n = t & 63;
+    const int dy = t >> 6;
     const int chunk = pchunk ^ ((n >> 2) & 1);
+    const int dx = n >> 3, dz = n & 7;
     bf16 v = __float2bfloat16_rn(0.f);
-    if (n < 7) {
-      const int tap = n * 49 + tile;
+    if (dx < 7 && dz < 7) {
+      const int tap = (dx * 7 + dy) * 7 + dz;
       v = wp[(size_t)(flip ? 342 - tap : tap) * 16 + chunk * 8 + c8];
     }
     wt[i] = v;
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 //  (C) weight gradient of both layers:  R[c][dx,dy,dz] = sum_v S16[v, c] * Q1[v + (dx,dy,dz) - P]
@@ -708,43 +721,27 @@ static bool thin_b_shape(const cgan3d_conv_geom &g, int op) {
   return false;
 }
 
-static bool plan_thin_b(const cgan3d_conv_geom &g, int op, ThinBPlan &best) {
+static bool plan_thin_b(const cgan3d_conv_geom &g, int op, ThinBPlan &p) {
   if (!thin_b_shape(g, op)) return false;
-  ThinBPlan p{};
+  p = ThinBPlan{};
   p.B = g.B;
   if (op == 0) { p.Xi = g.Xb; p.Yi = g.Yb; p.Zi = g.Zb; p.Xo = g.Xs; p.Yo = g.Ys; p.Zo = g.Zs; p.P = g.pad; }
   else         { p.Xi = g.Xs; p.Yi = g.Ys; p.Zi = g.Zs; p.Xo = g.Xb; p.Yo = g.Yb; p.Zo = g.Zb; p.P = 6 - g.pad; }
-  p.nzt = (p.Zo + 249) / 250;
-  p.Zt = (p.Zo + p.nzt - 1) / p.nzt;
-  p.Zh = p.Zt + 6;
-  const uint32_t fixed = 25600 + 512;
-  double best_score = 0;
-  bool found = false;
-  for (int Yt = 1; Yt <= p.Yo && Yt + 6 <= 256; ++Yt) {
-    const int Yh = Yt + 6;
-    const int mt = ((Yt - 1) * p.Zh + p.Zt + 127) / 128;
-    if (mt > 8) break;
-    const int rows_alloc = round_up(mx(Yh * p.Zh, mt * 128 + 6 * p.Zh + 6), 8);
-    if (rows_alloc * 2 > 16383) break;
-    const uint32_t slot = 2u * rows_alloc * 16;
-    const int nslots = (int)mn<uint32_t>(4, (kSmemLimitThin - fixed) / slot);
-    if (nslots < 2) break;
-    const int nyt = (p.Yo + Yt - 1) / Yt;
-    const double eff = (double)p.Yo * p.Zo / ((double)nyt * p.nzt * mt * 128);
-    const double score = eff * (nslots >= 3 ? 1.0 : 0.85);
-    if (score > best_score + 1e-9) {
-      best_score = score; found = true;
-      best = p;
-      best.Yt = Yt; best.Yh = Yh; best.nyt = nyt; best.mtiles = mt; best.rows_alloc = rows_alloc; best.slot_bytes = slot;
-      best.nslots = nslots;
-    }
-  }
-  if (!found) return false;
-  best.box_bytes = 32u * best.Zh * best.Yh;
+  // one y-line of the slab = 32 rows = one TMEM lane group: 26 output voxels + 6 halo voxels along z
+  p.Zt = kZtB; p.Zh = kPitchB;
+  p.nzt = (p.Zo + kZtB - 1) / kZtB;
+  p.mtiles = mn(4, (p.Yo + 3) / 4);
+  p.Yt = 4 * p.mtiles; p.Yh = p.Yt + 6;
+  p.nyt = (p.Yo + p.Yt - 1) / p.Yt;
+  p.rows_alloc = p.Yh * kPitchB;
+  p.slot_bytes = (uint32_t)p.rows_alloc * 32;
+  p.nslots = (int)mn<uint32_t>(6, (kSmemLimitThin - 14336 - 512) / p.slot_bytes);
+  if (p.nslots < 2) return false;
+  p.box_bytes = p.slot_bytes;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * best.mtiles * 16)) cols <<= 1;
-  best.tmem_cols = cols;
-  best.smem_bytes = fixed + best.nslots * best.slot_bytes;
+  while (cols < (uint32_t)(2 * p.mtiles * 64)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.smem_bytes = 14336 + 512 + p.nslots * p.slot_bytes;
   return true;
 }
 
@@ -827,12 +824,16 @@ static int run_thin_b(const cgan3d_conv_geom &g, int op, const void *in, const v
                       cudaStream_t st) {
   ThinBPlan p;
   if (!plan_thin_b(g, op, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv (16->1): shape not supported");
+  if (const char *dbg = getenv("CGAN3D_THIN_DEBUG")) p.debug = atoi(dbg);
+  if (getenv("CGAN3D_THIN_VERBOSE"))
+    fprintf(stderr, "thinB plan: Zt %d nzt %d Yt %d nyt %d mt %d rows_alloc %d nslots %d smem %u\n", p.Zt, p.nzt, p.Yt, p.nyt, p.mtiles,
+            p.rows_alloc, p.nslots, p.smem_bytes);
   const size_t need = (size_t)kTapTilesB * kTileBytesB;
   if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 thin conv: workspace %zu < %zu", ws_bytes, need);
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
     return fail(CGAN3D_E_ARG, "tcgen05 thin conv: pointers must be 16-byte aligned");
   bf16 *wt = reinterpret_cast<bf16 *>(ws);
-  stack_b_kernel<<<13, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op);
+  stack_b_kernel<<<28, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op);
   CG_LAUNCH_CHECK("stack_b");
   CUtensorMap tm;
   const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zi, (cuuint64_t)p.Yi, (cuuint64_t)p.Xi, (cuuint64_t)p.B};
@@ -850,7 +851,7 @@ static int run_thin_b(const cgan3d_conv_geom &g, int op, const void *in, const v
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv7_to1_tc_kernel)");
       attr_set = true;
     }
-    conv7_to1_tc_kernel<MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p);
+    conv7_to1_tc_kernel<MT><<<grid, 320, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p);
     CG_LAUNCH_CHECK("conv7_to1_tc_kernel");
     return 0;
   };
@@ -859,10 +860,6 @@ static int run_thin_b(const cgan3d_conv_geom &g, int op, const void *in, const v
     case 2: return launch(std::integral_constant<int, 2>{});
     case 3: return launch(std::integral_constant<int, 3>{});
     case 4: return launch(std::integral_constant<int, 4>{});
-    case 5: return launch(std::integral_constant<int, 5>{});
-    case 6: return launch(std::integral_constant<int, 6>{});
-    case 7: return launch(std::integral_constant<int, 7>{});
-    case 8: return launch(std::integral_constant<int, 8>{});
     default: return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: mtiles %d not built", p.mtiles);
   }
 }
