@@ -323,6 +323,13 @@ int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, 
 int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
                    cudaStream_t st);
 
+// conv_d1_tc.cu (first critic layer: 1 -> 8 channels, k4 s2)
+bool d1_supported(const cgan3d_conv_geom &g, int dtype, int op);
+size_t d1_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
+int d1_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes, cudaStream_t st);
+int d1_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
+                 cudaStream_t st);
+
 // wgrad_tc.cu
 bool tc_wgrad_supported(const cgan3d_conv_geom &g);
 int tc_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st);
@@ -336,7 +343,7 @@ static bool s1_shape_ok(const cgan3d_conv_geom &g, int dtype, int op) {
 
 bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
   if (!cgan3d_device_supports_tc() || encode_fn() == nullptr) return false;
-  if (thin_supported(g, dtype, op)) return true;
+  if (thin_supported(g, dtype, op) || d1_supported(g, dtype, op)) return true;
   if (op == 2) return dtype == CGAN3D_BF16 && tc_wgrad_supported(g);
   if (!s1_shape_ok(g, dtype, op)) return tc_prog_supported(g, dtype, op);
   TcPlan p;
@@ -346,6 +353,7 @@ bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
 
 size_t tc_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   if (thin_supported(g, dtype, op)) return thin_workspace_bytes(g, dtype, op);
+  if (d1_supported(g, dtype, op)) return d1_workspace_bytes(g, dtype, op);
   if (op == 2) return 0;
   if (!s1_shape_ok(g, dtype, op)) return tc_prog_workspace_bytes(g, dtype, op);
   return (size_t)27 * g.Cb * g.Cs * 2 + 256;
@@ -412,6 +420,7 @@ int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const 
               size_t ws_bytes, cudaStream_t st) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
   if (thin_supported(g, CGAN3D_BF16, 0)) return thin_run(g, 0, big, wp, small, ws, ws_bytes, st);
+  if (d1_supported(g, CGAN3D_BF16, 0)) return d1_run(g, 0, big, wp, small, ws, ws_bytes, st);
   if (!s1_shape_ok(g, CGAN3D_BF16, 0)) return tc_prog_run(g, 0, big, wp, small, ws, ws_bytes, st);
   return run_s1(g, 0, big, wp, small, ws, ws_bytes, st);
 }
@@ -420,6 +429,7 @@ int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, con
                size_t ws_bytes, cudaStream_t st) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
   if (thin_supported(g, CGAN3D_BF16, 1)) return thin_run(g, 1, small, wp, big, ws, ws_bytes, st);
+  if (d1_supported(g, CGAN3D_BF16, 1)) return d1_run(g, 1, small, wp, big, ws, ws_bytes, st);
   if (!s1_shape_ok(g, CGAN3D_BF16, 1)) return tc_prog_run(g, 1, small, wp, big, ws, ws_bytes, st);
   return run_s1(g, 1, small, wp, big, ws, ws_bytes, st);
 }
@@ -427,6 +437,7 @@ int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, con
 int tc_wgrad(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
              cudaStream_t st) {
   if (thin_supported(g, CGAN3D_BF16, 2)) return thin_wgrad_run(g, big, small, dw, beta, ws, ws_bytes, st);
+  if (d1_supported(g, CGAN3D_BF16, 2)) return d1_wgrad_run(g, big, small, dw, beta, ws, ws_bytes, st);
   return tc_wgrad_run(g, big, small, dw, beta, st);
 }
 
