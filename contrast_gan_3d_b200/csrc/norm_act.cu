@@ -2,6 +2,8 @@
 // HBM-bound row-major [n_rows][C] kernels (channels-last activations).
 // Replaces aten::native_batch_norm(+backward), relu_/leaky_relu_/tanh, add
 // (reference model/blocks.py:45,50,52-53,87-88; generator.py:85; trainer/Trainer.py:171).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cg {
@@ -159,47 +161,56 @@ struct V8<__nv_bfloat16> {
   }
 };
 
-// vectorised column reduction: thread (lane, c8) owns 8 adjacent channels; f(row, c0, out[NS][8])
-template <int NS, typename F>
-__device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, int rows_per_block, double *sums, F f) {
+// vectorised column reduction: thread (lane, c8) owns 8 adjacent channels and walks the rows grid-strided (row =
+// first + i * lanes_in_grid), so every iteration of the whole grid reads one contiguous span.  load(row, raw[]) fetches
+// the row's 16-byte chunks WITHOUT consuming them, so U of them are in flight per thread before eval(raw, v) runs;
+// fp32 runs of 32 rows feed fp64 totals.
+template <int NS, int U, int NRAW, typename FL, typename FE>
+__device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, double *sums, FL load, FE eval) {
   extern __shared__ double sh[];  // [lanes][NS][C]
   const int C8 = C >> 3;
   const int lanes = blockDim.x / C8;
   const int lane = threadIdx.x / C8;
   const int c0 = (threadIdx.x % C8) * 8;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(n_rows, r0 + rows_per_block);
+  const int64_t gl = (int64_t)gridDim.x * lanes;  // lanes in the grid
   double tot[NS][8];
 #pragma unroll
   for (int s = 0; s < NS; ++s)
 #pragma unroll
     for (int k = 0; k < 8; ++k) tot[s][k] = 0.0;
   if (lane < lanes) {
-    float part[NS][8];
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) part[s][k] = 0.f;
-    int run = 0;
-    for (int64_t r = r0 + lane; r < r1; r += lanes) {
-      float v[NS][8];
-      f(r, c0, v);
+    for (int64_t rb = (int64_t)blockIdx.x * lanes + lane; rb < n_rows; rb += 32 * gl) {
+      float part[NS][8];
 #pragma unroll
       for (int s = 0; s < NS; ++s)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) part[s][k] += v[s][k];
-      if (++run == 32) {
+        for (int k = 0; k < 8; ++k) part[s][k] = 0.f;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += U) {
+        uint4 raw[U][NRAW];
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = rb + (int64_t)(i0 + u) * gl;
+          if (r < n_rows) load(r, raw[u]);
+        }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) { tot[s][k] += (double)part[s][k]; part[s][k] = 0.f; }
-        run = 0;
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = rb + (int64_t)(i0 + u) * gl;
+          if (r < n_rows) {
+            float v[NS][8];
+            eval(raw[u], v);
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) part[s][k] += v[s][k];
+          }
+        }
       }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot[s][k] += (double)part[s][k];
     }
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tot[s][k] += (double)part[s][k];
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -213,96 +224,164 @@ __device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, int rows
   }
 }
 
+// raw 16-byte chunk -> 8 floats
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4 *raw, float (&v)[8]);
+template <>
+__device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4 *raw, float (&v)[8]) {
+  const uint32_t w[4] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <>
+__device__ __forceinline__ void unpack8<float>(const uint4 *raw, float (&v)[8]) {
+  v[0] = __uint_as_float(raw[0].x); v[1] = __uint_as_float(raw[0].y); v[2] = __uint_as_float(raw[0].z); v[3] = __uint_as_float(raw[0].w);
+  v[4] = __uint_as_float(raw[1].x); v[5] = __uint_as_float(raw[1].y); v[6] = __uint_as_float(raw[1].z); v[7] = __uint_as_float(raw[1].w);
+}
+template <typename T>
+__device__ __forceinline__ void load8raw(const T *p, uint4 *raw) {
+  constexpr int NV = (int)sizeof(T) / 2;  // 16-byte vectors per 8 elements
+#pragma unroll
+  for (int i = 0; i < NV; ++i) raw[i] = reinterpret_cast<const uint4 *>(p)[i];
+}
+
 static bool vec8_ok(int C, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr) {
   auto al = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  return C % 8 == 0 && C <= 2048 && al(a) && al(b) && al(c) && al(d);
+  return C % 8 == 0 && C <= 2048 && 256 % (C >> 3) == 0 && al(a) && al(b) && al(c) && al(d);
 }
 static ColGrid col_grid8(int64_t n_rows, int C, int ns) {
   const int lanes = 256 / (C >> 3);
-  int64_t target_blocks = (int64_t)num_sms() * 8;
-  int64_t rpb = (n_rows + target_blocks - 1) / target_blocks;
-  rpb = mx<int64_t>(rpb, (int64_t)lanes * 4);
-  rpb = ((rpb + lanes - 1) / lanes) * lanes;
   ColGrid g;
-  g.rows_per_block = (int)mn<int64_t>(rpb, 1 << 30);
-  g.blocks = (int)((n_rows + g.rows_per_block - 1) / g.rows_per_block);
+  g.rows_per_block = 0;  // rows are walked grid-strided
+  g.blocks = (int)mx<int64_t>(1, mn<int64_t>((n_rows + lanes - 1) / lanes, (int64_t)num_sms() * 4));
   g.smem = (size_t)ns * lanes * C * sizeof(double);
   return g;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats8_kernel(const T *__restrict__ y, int64_t n_rows, int C, int rpb, double *sums) {
-  col_reduce8_body<2>(n_rows, C, rpb, sums, [&](int64_t r, int c0, float (&v)[2][8]) {
-    V8<T> x;
-    x.load(y + r * C + c0);
+  const int c0 = (threadIdx.x % (C >> 3)) * 8;
+  constexpr int NV = (int)sizeof(T) / 2;
+  col_reduce8_body<2, 8, NV>(
+      n_rows, C, sums, [&](int64_t r, uint4 *raw) { load8raw(y + r * C + c0, raw); },
+      [&](const uint4 *raw, float (&v)[2][8]) {
+        float x[8];
+        unpack8<T>(raw, x);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { v[0][k] = x.v[k]; v[1][k] = x.v[k] * x.v[k]; }
-  });
+        for (int k = 0; k < 8; ++k) { v[0][k] = x[k]; v[1][k] = x[k] * x[k]; }
+      });
 }
 
-template <typename T>
+// activation derivative with the activation known at compile time (ACT < 0: runtime switch)
+template <int ACT>
+__device__ __forceinline__ float act_bwd_t(float pre, int act, float slope) {
+  if (ACT == CGAN3D_ACT_NONE) return 1.f;
+  if (ACT == CGAN3D_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+  if (ACT == CGAN3D_ACT_LRELU) return pre > 0.f ? 1.f : slope;
+  return act_bwd(pre, act, slope);
+}
+
+// per-thread channel constants of the 8 channels a thread owns (hoisted out of the streaming loops: the per-element
+// loads of mean/invstd/gamma/beta made these kernels LSU-bound instead of HBM-bound)
+struct BnC8 {
+  float a[8], b[8], mean[8], invstd[8], gamma[8], beta[8], nm[8];
+  __device__ __forceinline__ void load(const float *mi, const float *g, const float *bt, int C, int c0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mean[k] = mi[c0 + k]; invstd[k] = mi[C + c0 + k]; gamma[k] = g[c0 + k]; beta[k] = bt[c0 + k];
+      a[k] = gamma[k] * invstd[k];
+      b[k] = beta[k] - mean[k] * a[k];
+      nm[k] = -mean[k] * invstd[k];
+    }
+  }
+};
+
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t n_rows, int C, int rpb,
                       const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
                       float slope, double *sums) {
-  col_reduce8_body<2>(n_rows, C, rpb, sums, [&](int64_t r, int c0, float (&v)[2][8]) {
-    V8<T> yy, dd;
-    yy.load(y + r * C + c0);
-    dd.load(dz + r * C + c0);
+  const int c0 = (threadIdx.x % (C >> 3)) * 8;
+  BnC8 k8;
+  k8.load(mi, gamma, beta, C, c0);
+  constexpr int NV = (int)sizeof(T) / 2;
+  col_reduce8_body<2, 4, 2 * NV>(
+      n_rows, C, sums,
+      [&](int64_t r, uint4 *raw) { load8raw(y + r * C + c0, raw); load8raw(dz + r * C + c0, raw + NV); },
+      [&](const uint4 *raw, float (&v)[2][8]) {
+        float yy[8], dd[8];
+        unpack8<T>(raw, yy);
+        unpack8<T>(raw + NV, dd);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      const float xh = (yy.v[k] - mi[c]) * mi[C + c];
-      const float g = dd.v[k] * act_bwd(gamma[c] * xh + beta[c], act, slope);
-      v[0][k] = g;
-      v[1][k] = g * xh;
-    }
-  });
+        for (int k = 0; k < 8; ++k) {
+          const float xh = fmaf(yy[k], k8.invstd[k], k8.nm[k]);
+          const float g = dd[k] * act_bwd_t<ACT>(fmaf(k8.a[k], yy[k], k8.b[k]), act, slope);
+          v[0][k] = g;
+          v[1][k] = g * xh;
+        }
+      });
 }
 
+// The elementwise kernels walk the tensor with a stride that is a multiple of C, so a thread always sees the same 8 channels.
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply8_kernel(const T *__restrict__ y, T *__restrict__ z, int64_t total8, int C, const float *__restrict__ mi,
                  const float *__restrict__ gamma, const float *__restrict__ beta, int act, float slope,
                  const T *__restrict__ residual) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i * 8;
-    const int c0 = (int)(e % C);
-    V8<T> v, r;
-    v.load(y + e);
-    if (residual) r.load(residual + e);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)((i * 8) % C);
+  BnC8 k8;
+  k8.load(mi, gamma, beta, C, c0);
+  for (; i < total8; i += 2 * stride) {
+    const int64_t e0 = i * 8, e1 = (i + stride) * 8;
+    const bool two = i + stride < total8;
+    V8<T> v0, v1, r0, r1;
+    v0.load(y + e0);
+    if (two) v1.load(y + e1);
+    if (residual) { r0.load(residual + e0); if (two) r1.load(residual + e1); }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      float t = act_fwd(gamma[c] * ((v.v[k] - mi[c]) * mi[C + c]) + beta[c], act, slope);
-      if (residual) t += r.v[k];
-      v.v[k] = t;
+      float t0 = act_fwd(fmaf(k8.a[k], v0.v[k], k8.b[k]), act, slope);
+      float t1 = act_fwd(fmaf(k8.a[k], v1.v[k], k8.b[k]), act, slope);
+      if (residual) { t0 += r0.v[k]; t1 += r1.v[k]; }
+      v0.v[k] = t0; v1.v[k] = t1;
     }
-    v.store(z + e);
+    v0.store(z + e0);
+    if (two) v1.store(z + e1);
   }
 }
 
-template <typename T>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t total8, int C, double inv_n,
                      const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
                      float slope, const double *__restrict__ sums) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i * 8;
-    const int c0 = (int)(e % C);
-    V8<T> yy, dd;
-    yy.load(y + e);
-    dd.load(dz + e);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)((i * 8) % C);
+  BnC8 k8;
+  k8.load(mi, gamma, beta, C, c0);
+  float mg[8], mgx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mg[k] = (float)(sums[c0 + k] * inv_n); mgx[k] = (float)(sums[C + c0 + k] * inv_n); }
+  for (; i < total8; i += 2 * stride) {
+    const int64_t e0 = i * 8, e1 = (i + stride) * 8;
+    const bool two = i + stride < total8;
+    V8<T> y0, d0, y1, d1;
+    y0.load(y + e0);
+    d0.load(dz + e0);
+    if (two) { y1.load(y + e1); d1.load(dz + e1); }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      const float invstd = mi[C + c];
-      const float xh = (yy.v[k] - mi[c]) * invstd;
-      const float g = dd.v[k] * act_bwd(gamma[c] * xh + beta[c], act, slope);
-      const float mg = (float)(sums[c] * inv_n), mgx = (float)(sums[C + c] * inv_n);
-      dd.v[k] = gamma[c] * invstd * (g - mg - xh * mgx);
+      const float xh0 = fmaf(y0.v[k], k8.invstd[k], k8.nm[k]), xh1 = fmaf(y1.v[k], k8.invstd[k], k8.nm[k]);
+      const float g0 = d0.v[k] * act_bwd_t<ACT>(fmaf(k8.a[k], y0.v[k], k8.b[k]), act, slope);
+      const float g1 = d1.v[k] * act_bwd_t<ACT>(fmaf(k8.a[k], y1.v[k], k8.b[k]), act, slope);
+      d0.v[k] = k8.a[k] * (g0 - mg[k] - xh0 * mgx[k]);
+      d1.v[k] = k8.a[k] * (g1 - mg[k] - xh1 * mgx[k]);
     }
-    dd.store(dy + e);
+    d0.store(dy + e0);
+    if (two) d1.store(dy + e1);
   }
 }
 
@@ -554,12 +633,19 @@ int cgan3d_bn_backward_reduce(const void *dz, const void *y, int dtype, int64_t 
   if (e != cudaSuccess) return cuda_fail(e, "bn_backward_reduce memset");
   if (vec8_ok(C, dz, y)) {
     ColGrid g8 = col_grid8(n_rows, C, 2);
-    if (dtype == CGAN3D_F32)
-      bn_bwd_reduce8_kernel<float><<<g8.blocks, 256, g8.smem, st>>>((const float *)dz, (const float *)y, n_rows, C,
-                                                                   g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums);
-    else
-      bn_bwd_reduce8_kernel<__nv_bfloat16><<<g8.blocks, 256, g8.smem, st>>>(
-          (const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y, n_rows, C, g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums);
+    auto go = [&](auto act_tag) {
+      constexpr int A = decltype(act_tag)::value;
+      if (dtype == CGAN3D_F32)
+        bn_bwd_reduce8_kernel<float, A><<<g8.blocks, 256, g8.smem, st>>>((const float *)dz, (const float *)y, n_rows, C,
+                                                                         g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums);
+      else
+        bn_bwd_reduce8_kernel<__nv_bfloat16, A><<<g8.blocks, 256, g8.smem, st>>>(
+            (const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y, n_rows, C, g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums);
+    };
+    if (act == CGAN3D_ACT_RELU) go(std::integral_constant<int, CGAN3D_ACT_RELU>{});
+    else if (act == CGAN3D_ACT_LRELU) go(std::integral_constant<int, CGAN3D_ACT_LRELU>{});
+    else if (act == CGAN3D_ACT_NONE) go(std::integral_constant<int, CGAN3D_ACT_NONE>{});
+    else go(std::integral_constant<int, -1>{});
     CG_LAUNCH_CHECK("bn_backward_reduce(vec8)");
     return 0;
   }
@@ -586,13 +672,20 @@ int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype,
   const double inv_n = 1.0 / (double)n_rows;
   if (vec8_ok(C, dz, y, dy)) {
     const int64_t t8 = total / 8;
-    if (dtype == CGAN3D_F32)
-      bn_bwd_apply8_kernel<float><<<ew_blocks(t8), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, t8, C, inv_n,
-                                                                 mean_invstd, gamma, beta, act, slope, sums);
-    else
-      bn_bwd_apply8_kernel<__nv_bfloat16><<<ew_blocks(t8), 256, 0, st>>>((const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y,
-                                                                         (__nv_bfloat16 *)dy, t8, C, inv_n, mean_invstd, gamma,
-                                                                         beta, act, slope, sums);
+    auto go = [&](auto act_tag) {
+      constexpr int A = decltype(act_tag)::value;
+      if (dtype == CGAN3D_F32)
+        bn_bwd_apply8_kernel<float, A><<<ew_blocks(t8), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, t8, C, inv_n,
+                                                                      mean_invstd, gamma, beta, act, slope, sums);
+      else
+        bn_bwd_apply8_kernel<__nv_bfloat16, A><<<ew_blocks(t8), 256, 0, st>>>((const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y,
+                                                                              (__nv_bfloat16 *)dy, t8, C, inv_n, mean_invstd, gamma,
+                                                                              beta, act, slope, sums);
+    };
+    if (act == CGAN3D_ACT_RELU) go(std::integral_constant<int, CGAN3D_ACT_RELU>{});
+    else if (act == CGAN3D_ACT_LRELU) go(std::integral_constant<int, CGAN3D_ACT_LRELU>{});
+    else if (act == CGAN3D_ACT_NONE) go(std::integral_constant<int, CGAN3D_ACT_NONE>{});
+    else go(std::integral_constant<int, -1>{});
     CG_LAUNCH_CHECK("bn_backward_apply(vec8)");
   } else if (dtype == CGAN3D_F32)
     bn_bwd_apply_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, total, C,
