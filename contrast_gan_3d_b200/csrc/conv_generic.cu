@@ -169,11 +169,51 @@ gather_co1_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__rest
   }
 }
 
+// Cout == 1 on a SMALL output grid (the critic's logits map): one warp per output voxel, the lanes share the
+// K^3 x Cb/8 (tap, 8-channel chunk) units and shuffle-reduce -- the one-thread-per-8-outputs kernel above leaves
+// almost all SMs idle at this size.
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(128)
+gather_co1_warp_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict__ wp, const float *__restrict__ bias,
+                       T *__restrict__ small, int64_t total) {
+  const int64_t o = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= total) return;
+  int64_t t = o;
+  const int oz = (int)(t % g.Zs); t /= g.Zs;
+  const int oy = (int)(t % g.Ys); t /= g.Ys;
+  const int ox = (int)(t % g.Xs);
+  const int b = (int)(t / g.Xs);
+  const int c8n = g.Cb >> 3, units = K * K * K * c8n;
+  float acc = 0.f;
+  for (int u = lane; u < units; u += 32) {
+    const int tap = u / c8n, c0 = (u - tap * c8n) * 8;
+    const int kz = tap % K, ky = (tap / K) % K, kx = tap / (K * K);
+    const int ix = ox * S - g.pad + kx, iy = oy * S - g.pad + ky, iz = oz * S - g.pad + kz;
+    if ((unsigned)ix >= (unsigned)g.Xb || (unsigned)iy >= (unsigned)g.Yb || (unsigned)iz >= (unsigned)g.Zb) continue;
+    Vec8<T> xv, wv;
+    xv.load(big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * g.Zb + iz) * (int64_t)g.Cb + c0);
+    wv.load(wp + (int64_t)tap * g.Cb + c0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc = fmaf(xv.v[c], wv.v[c], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) small[o] = from_f<T>(acc + (bias ? bias[0] : 0.f));
+}
+
 template <typename T, int K, int S>
 static int launch_gather(const cgan3d_conv_geom &g, const T *big, const T *wp, const float *bias, T *small,
                          cudaStream_t st) {
   constexpr int VB = 4;
   const int nzg = (g.Zs + VB - 1) / VB;
+  const bool vec_ok = g.Cb % 8 == 0 && (reinterpret_cast<uintptr_t>(big) & (8 * sizeof(T) - 1)) == 0 &&
+                      (reinterpret_cast<uintptr_t>(wp) & (8 * sizeof(T) - 1)) == 0;
+  if (g.Cs == 1 && vec_ok && (int64_t)g.B * g.Xs * g.Ys * g.Zs <= (1 << 17)) {
+    const int64_t total = (int64_t)g.B * g.Xs * g.Ys * g.Zs;
+    gather_co1_warp_kernel<T, K, S><<<(int)((total * 32 + 127) / 128), 128, 0, st>>>(g, big, wp, bias, small, total);
+    CG_LAUNCH_CHECK("conv_gather(generic, Cout=1, warp per output)");
+    return 0;
+  }
   if (g.Cs == 1 && g.Cb % 8 == 0 && (reinterpret_cast<uintptr_t>(big) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0) {
     constexpr int VB1 = 8;
     const int64_t total = (int64_t)g.B * g.Xs * g.Ys * ((g.Zs + VB1 - 1) / VB1);

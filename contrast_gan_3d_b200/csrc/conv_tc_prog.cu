@@ -45,7 +45,9 @@ struct ProgPlan {
   int B, Xg, Yg, Zg;     // small ("grid") side extents: rows of every MMA live on this grid
   int Xo, Yo, Zo;        // output tensor extents
   int Cin, N, nacc;      // N = MMA N (multiple of 16)
-  int Nout;              // channels actually stored (<= N)
+  int Nout;              // channels actually stored by this launch (<= N)
+  int out_pitch, out_c0; // channels per output voxel / first channel of this launch (output-channel split: the filters of
+                         // wide critic layers do not fit in shared memory, so the channels are covered by 2 or 4 launches)
   int paired;            // 1: Cin == 8, K = 16 is two z-adjacent taps (tile t holds filter taps tile_tap[t][0..1])
   uint32_t a_lbo_bytes;
   int in_scale;          // 2: gather from the big side (strided TMA), 1: scatter from the small side
@@ -187,7 +189,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           const int gy = r / p.Zh, gz = r - gy * p.Zh;
           const int oy = p.out_scale * (y0 + gy) + py, oz = p.out_scale * (z0 + gz) + pz;
           const bool valid = gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo;
-          bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.Nout;
+          bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.out_pitch + p.out_c0;
           const uint32_t taddr = d_base + (uint32_t)(a * MT + mt) * p.N;
           for (int c0 = 0; c0 < p.Nout; c0 += 16) {
             uint32_t v[16];
@@ -234,7 +236,8 @@ __global__ void repack_prog_kernel(const bf16 *__restrict__ wp, bf16 *__restrict
     const int ci = p.paired ? c8 : cc * 8 + c8;
     bf16 v = __float2bfloat16_rn(0.f);
     if (n < p.Nout && tap >= 0) {
-      const int cb = scatter ? n : ci, cs = scatter ? ci : n;
+      const int no = n + p.out_c0;
+      const int cb = scatter ? no : ci, cs = scatter ? ci : no;
       v = wp[((int64_t)tap * Cb + cb) * Cs + cs];
     }
     wb[i] = v;
@@ -335,9 +338,23 @@ static bool build_program(const cgan3d_conv_geom &g, int scatter, ProgPlan &p) {
   return true;
 }
 
-static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best) {
+static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &best, int nsplit);
+
+// tries 1, 2, 4 output-channel splits; *nsplit_out receives the number of launches
+static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best, int *nsplit_out = nullptr) {
+  for (int ns = 1; ns <= 4; ns *= 2)
+    if (plan_prog_split(g, scatter, best, ns)) {
+      if (nsplit_out) *nsplit_out = ns;
+      return true;
+    }
+  return false;
+}
+
+static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &best, int nsplit) {
   if (g.stride != 2 || g.pad != 1 || (g.k != 3 && g.k != 4)) return false;
-  const int Cin = scatter ? g.Cs : g.Cb, Nout = scatter ? g.Cb : g.Cs;
+  const int Cin = scatter ? g.Cs : g.Cb, Nfull = scatter ? g.Cb : g.Cs;
+  if (Nfull % nsplit || (nsplit > 1 && (Nfull / nsplit) % 16)) return false;
+  const int Nout = Nfull / nsplit;
   const int paired = (!scatter && Cin == 8) ? 1 : 0;
   if (!paired && Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
   if (Nout % 8 || Nout < 8 || Nout > 256 || (Nout > 8 && Nout % 16)) return false;
@@ -351,7 +368,7 @@ static bool plan_prog(const cgan3d_conv_geom &g, int scatter, ProgPlan &best) {
   ProgPlan p{};
   p.B = g.B; p.Xg = g.Xs; p.Yg = g.Ys; p.Zg = g.Zs;
   p.Xo = scatter ? g.Xb : g.Xs; p.Yo = scatter ? g.Yb : g.Ys; p.Zo = scatter ? g.Zb : g.Zs;
-  p.Cin = Cin; p.N = N; p.nacc = nacc; p.Nout = Nout; p.paired = paired;
+  p.Cin = Cin; p.N = N; p.nacc = nacc; p.Nout = Nout; p.paired = paired; p.out_pitch = Nfull; p.out_c0 = 0;
   p.in_scale = scatter ? 1 : 2; p.out_scale = scatter ? 2 : 1;
   p.nbt = paired ? taps / 2 + (g.k == 3 ? 9 : 0) : taps;  // upper bound; build_program fixes the exact count
   p.btile_bytes = (uint32_t)(paired ? 16 : Cin) * N * 2;
@@ -410,7 +427,7 @@ bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op) {
 
 size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   if (dtype != CGAN3D_BF16 || (op != 0 && op != 1)) return 0;
-  return (size_t)g.k * g.k * g.k * mx(g.Cb, 16) * mx(g.Cs, 16) * 2 + 256;
+  return (size_t)g.k * g.k * g.k * mx(g.Cb, 16) * mx(g.Cs, 16) * 2 + 4 * 256 + 256;
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -421,19 +438,18 @@ void *tc_encode_fn_ptr();  // conv_tc.cu
 int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
                 cudaStream_t st) {
   ProgPlan p;
-  if (!plan_prog(g, scatter, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: no tiling for this shape");
-  const size_t need = (size_t)p.nbt * p.btile_bytes;
+  int nsplit = 1;
+  if (!plan_prog(g, scatter, p, &nsplit)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: no tiling for this shape");
+  const size_t part_bytes = ((size_t)p.nbt * p.btile_bytes + 255) / 256 * 256;
+  const size_t need = part_bytes * nsplit;
   if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 strided conv: workspace %zu < %zu", ws_bytes, need);
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
     return fail(CGAN3D_E_ARG, "tcgen05 strided conv: pointers must be 16-byte aligned");
   EncodeTiledFn2 enc = reinterpret_cast<EncodeTiledFn2>(tc_encode_fn_ptr());
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
-  bf16 *wb = reinterpret_cast<bf16 *>(ws);
-  repack_prog_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, scatter, p);
-  CG_LAUNCH_CHECK("repack_prog");
   // input tensor: gather reads the big side with element strides 2 on z and y; scatter reads the small side densely
   const int Xi = scatter ? g.Xs : g.Xb, Yi = scatter ? g.Ys : g.Yb, Zi = scatter ? g.Zs : g.Zb, Ci = p.Cin;
-  if ((reinterpret_cast<uintptr_t>(outp) & 15) || (p.Nout * 2) % 16) return fail(CGAN3D_E_ARG, "tcgen05 strided conv: output rows must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(outp) & 15) || (p.Nout * 2) % 16 || (p.out_pitch * 2) % 16) return fail(CGAN3D_E_ARG, "tcgen05 strided conv: output rows must be 16-byte aligned");
   const int es = p.in_scale;
   CUtensorMap tm;
   const cuuint64_t gdim[5] = {(cuuint64_t)Ci, (cuuint64_t)Zi, (cuuint64_t)Yi, (cuuint64_t)Xi, (cuuint64_t)g.B};
@@ -457,8 +473,14 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_prog_tc_kernel)");
       attr_set = true;
     }
-    conv_prog_tc_kernel<KS, MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
-    CG_LAUNCH_CHECK("conv_prog_tc_kernel");
+    for (int part = 0; part < nsplit; ++part) {  // output-channel parts (1 unless the filters exceed shared memory)
+      p.out_c0 = part * p.Nout;
+      bf16 *wb = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + part * part_bytes);
+      repack_prog_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, scatter, p);
+      CG_LAUNCH_CHECK("repack_prog");
+      conv_prog_tc_kernel<KS, MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
+      CG_LAUNCH_CHECK("conv_prog_tc_kernel");
+    }
     return 0;
   };
   auto by_mt = [&](auto ks_tag) -> int {

@@ -180,6 +180,27 @@ class Trainer:
         out[a.shape[0]:].copy_(b, non_blocking=True)
         return out
 
+    def _side_upload(self, parts: List[Tensor]):
+        """Host->device copy of `torch.cat(parts)` on a side stream, so that tensors that are only needed later in the step
+        (the real batch for the critic, the masks for the generator loss) cross PCIe while G's forward pass runs.
+        Returns (device tensor, event or None); the consumer stream must wait on the event."""
+        if all(t.device == self.device for t in parts):
+            return (parts[0] if len(parts) == 1 else torch.cat(parts)), None
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        n = sum(t.shape[0] for t in parts)
+        with torch.cuda.stream(self._copy_stream):
+            out = torch.empty((n, *parts[0].shape[1:]), dtype=parts[0].dtype, device=self.device)
+            o = 0
+            for t in parts:
+                out[o:o + t.shape[0]].copy_(t, non_blocking=True)
+                o += t.shape[0]
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        out.record_stream(main)
+        return out, ev
+
     def _generate(self, subopt: Tensor):
         if hasattr(self.generator, "forward_corrected"):
             return self.generator.forward_corrected(subopt)
@@ -188,17 +209,23 @@ class Trainer:
 
     def train_step(self, patches: List[dict], iteration: int) -> Dict[str, Tensor]:
         opt, low, high = patches
-        opt_t: Tensor = opt["data"].to(self.device, non_blocking=True)
-        subopt = self._upload_cat(low["data"], high["data"])
+        do_train_generator = iteration % self.train_generator_every == 0
+        do_train_critic = iteration % self.train_critic_every == 0
+        main = torch.cuda.current_stream(self.device)
+        subopt = self._upload_cat(low["data"], high["data"])  # needed first: on the compute stream
+        opt_t, opt_ev = self._side_upload([opt["data"]]) if do_train_critic else (None, None)
+        mask_t, mask_ev = self._side_upload([low["seg"], high["seg"]]) if do_train_generator else (None, None)
         attenuation, opt_hat = self._generate(subopt)
 
-        do_train_generator = iteration % self.train_generator_every == 0
         log_dict: Dict[str, Tensor] = {}
-        if iteration % self.train_critic_every == 0:
+        if do_train_critic:
+            if opt_ev is not None:
+                main.wait_event(opt_ev)
             log_dict = self.train_critic(opt_t, opt_hat, do_train_generator)
         if do_train_generator:
-            subopt_mask = self._upload_cat(low["seg"], high["seg"])
-            log_dict |= self.train_generator(subopt, opt_hat, subopt_mask)
+            if mask_ev is not None:
+                main.wait_event(mask_ev)
+            log_dict |= self.train_generator(subopt, opt_hat, mask_t)
 
         if self.log_every and iteration % self.log_every == 0:
             self.logger_interface.logger.log_loss({k: v.detach().mean() for k, v in log_dict.items()}, iteration, "train")

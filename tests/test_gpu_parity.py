@@ -470,6 +470,7 @@ S2_CASES = [
     ("critic_mid0_k4", False, 8, 16, 4, 0, 2, (12, 16, 8)),
     ("critic_mid0_big", False, 8, 16, 4, 0, 1, (20, 24, 40)),
     ("down_c8_k3", False, 8, 16, 3, 0, 2, (10, 12, 14)),
+    ("critic_mid2_k4", False, 32, 64, 4, 0, 2, (16, 16, 16)),
     ("up0_like", True, 64, 32, 3, 1, 1, (6, 8, 10)),
     ("up1_like", True, 32, 16, 3, 1, 2, (8, 6, 36)),
 ]

@@ -1,0 +1,36 @@
+"""Host-side cost of one train_step (Python + ctypes + allocator), measured without waiting for the GPU."""
+import sys, time
+from functools import partial
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from bench import synth_batch, HU_BOUNDS
+from contrast_gan_3d_b200 import _lib
+from contrast_gan_3d_b200.model import HULoss, PatchGANDiscriminator, ResnetGenerator
+from contrast_gan_3d_b200.optim import FusedAdam
+from contrast_gan_3d_b200.trainer.Trainer import NullLogger, Trainer
+
+dev = torch.device("cuda:0")
+patch = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+torch.manual_seed(0)
+tr = Trainer(10 ** 9, 2, None, 1, 1, 0, 0, partial(ResnetGenerator, 4, 2, 16, compute_dtype=torch.bfloat16),
+             partial(PatchGANDiscriminator, 1, 8, 3, negative_slope=0.2, compute_dtype=torch.bfloat16),
+             partial(FusedAdam, lr=2e-4, betas=(0.5, 0.999)), partial(FusedAdam, lr=2e-4, betas=(0.5, 0.999)),
+             HULoss(*HU_BOUNDS), NullLogger(), dev, weight_clip=0.01, checkpoint_every=None)
+gen = torch.Generator().manual_seed(1)
+host = synth_batch(gen, n, n // 2, n // 2, (patch,) * 3, pin=True)
+res = [dict(data=b["data"].to(dev), seg=None if b["seg"] is None else b["seg"].to(dev), name=[]) for b in host]
+for _ in range(3):
+    tr.train_step(res, 0)
+torch.cuda.synchronize()
+n0 = _lib.launch_count
+t0 = time.perf_counter()
+for _ in range(5):
+    tr.train_step(res, 0)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+print(f"patch {patch} pairs {n}: host {1e3 * (t1 - t0) / 5:.2f} ms/step, wall incl. GPU {1e3 * (t2 - t0) / 5:.2f} ms/step, "
+      f"{(_lib.launch_count - n0) / 5:.0f} lib calls/step")
