@@ -204,7 +204,7 @@ def main():
         for it in range(steps):
             logs = tr.train_step(batches, 0)  # iteration 0: critic AND generator are trained
             if read_loss:
-                _ = float(logs["G-full"])  # device->host read of the step's result
+                _ = float(logs["G-full"].detach())  # device->host read of the step's result
         e1.record()
         sync()
         ms = e0.elapsed_time(e1) / steps
@@ -224,6 +224,8 @@ def main():
     launches = _lib.launch_count - n0
     conv_t = ops.conv_timing_summary()
     ops.enable_conv_timing(False)
+    for _ in range(max(args.warmup, 5)):  # warm the end-to-end path too (side-stream upload pool, pinned-memory registration)
+        tr.train_step(host, 0)
     ms_e2e, logs = timed(host, args.steps, read_loss=True)
     value = pairs_per_step / (ms / 1e3)
     e2e = pairs_per_step / (ms_e2e / 1e3)
@@ -241,8 +243,15 @@ def main():
         ach = flops / (tot_ms / n * 1e-3) / 1e12
         conv_ms = sum(v[1] for v in conv_t.values()) / args.steps
         tc_ms = sum(v[1] for v in conv_t.values() if v[3] == 2) / args.steps
+        traffic = None
+        tfile = ROOT / "profiles" / "ncu_traffic.json"
+        if tfile.exists():
+            tj = json.loads(tfile.read_text())
+            rec = tj.get(f"{key[0]}:{','.join(str(v) for v in key[2:])}")
+            if rec:
+                traffic = rec["dram_bytes_per_launch"]
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                 "kernel": {"op": key[0], "impl": "tcgen05" if impl == 2 else "generic-cuda-core", "geom": list(key[2:]),
                            "launches_per_step": n / args.steps, "avg_ms": tot_ms / n},
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms, "tcgen05_ms_per_step": tc_ms,

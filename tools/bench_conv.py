@@ -25,9 +25,12 @@ CASES = {
     "c16_128": (False, 16, 16, 3, 1, 1, 0, 2, (128, 128, 128)),
     "c128_32": (False, 128, 128, 3, 1, 1, 0, 8, (32, 32, 32)),
     "down0": (False, 16, 32, 3, 2, 1, 0, 4, (128, 128, 128)),
+    "down0_c3": (False, 16, 32, 3, 2, 1, 0, 16, (128, 128, 128)),
     "down1": (False, 32, 64, 3, 2, 1, 0, 8, (64, 64, 64)),
     "up0": (True, 64, 32, 3, 2, 1, 1, 8, (32, 32, 32)),
     "up1": (True, 32, 16, 3, 2, 1, 1, 4, (64, 64, 64)),
+    "first_c3": (False, 1, 16, 7, 1, 0, 0, 16, (134, 134, 134)),
+    "last_c3": (False, 16, 1, 7, 1, 0, 0, 16, (134, 134, 134)),
     "first": (False, 1, 16, 7, 1, 0, 0, 2, (134, 134, 134)),
     "last": (False, 16, 1, 7, 1, 0, 0, 2, (134, 134, 134)),
     "d_first": (False, 1, 8, 4, 2, 1, 0, 16, (128, 128, 128)),

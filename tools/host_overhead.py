@@ -34,3 +34,21 @@ torch.cuda.synchronize()
 t2 = time.perf_counter()
 print(f"patch {patch} pairs {n}: host {1e3 * (t1 - t0) / 5:.2f} ms/step, wall incl. GPU {1e3 * (t2 - t0) / 5:.2f} ms/step, "
       f"{(_lib.launch_count - n0) / 5:.0f} lib calls/step")
+
+
+def timed(batches, read_loss, steps=5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        logs = tr.train_step(batches, 0)
+        if read_loss:
+            float(logs["G-full"].detach())
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+for name, b, rl in (("resident, no sync", res, False), ("resident, loss read each step", res, True),
+                    ("pinned host, no sync", host, False), ("pinned host, loss read each step (= e2e)", host, True)):
+    print(f"{name}: {timed(b, rl):.2f} ms/step")
