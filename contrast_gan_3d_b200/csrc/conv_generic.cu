@@ -814,24 +814,22 @@ __global__ void reflect_pad_vec_kernel(const uint4 *__restrict__ in, uint4 *__re
   }
 }
 
+// one block per interior (b, x, y) line: no per-element index division, the mirror sources of x and y are block-uniform
 template <typename T>
-__global__ void reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *__restrict__ gi, int B, int X, int Y, int Z, int cpv,
-                                           int p) {
+__global__ void __launch_bounds__(256)
+reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *__restrict__ gi, int B, int X, int Y, int Z, int cpv, int p) {
   constexpr int VEC = 16 / (int)sizeof(T);
   const int Yp = Y + 2 * p, Zp = Z + 2 * p, Xp = X + 2 * p;
-  const int64_t total = (int64_t)B * X * Y * Z * cpv;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t line = i / (Z * cpv);
-    const int rem = (int)(i - line * (Z * cpv));
-    const int z = rem / cpv, c = rem - z * cpv;
-    const int y = (int)(line % Y);
-    const int64_t t = line / Y;
-    const int x = (int)(t % X);
-    const int b = (int)(t / X);
-    int sx[3], sy[3], sz[3];
-    const int nx = reflect_sources(x, X, p, sx), ny = reflect_sources(y, Y, p, sy), nz = reflect_sources(z, Z, p, sz);
+  const int y = blockIdx.x, x = blockIdx.y, b = blockIdx.z;
+  int sx[3], sy[3];
+  const int nx = reflect_sources(x, X, p, sx), ny = reflect_sources(y, Y, p, sy);
+  uint4 *dst = gi + (((int64_t)b * X + x) * Y + y) * (int64_t)Z * cpv;
+  for (int i = threadIdx.x; i < Z * cpv; i += blockDim.x) {
+    const int z = i / cpv, c = i - z * cpv;
+    int sz[3];
+    const int nz = reflect_sources(z, Z, p, sz);
     if (nx == 1 && ny == 1 && nz == 1) {  // interior voxel: plain copy
-      gi[i] = gp[((((int64_t)b * Xp + sx[0]) * Yp + sy[0]) * Zp + sz[0]) * cpv + c];
+      dst[i] = gp[((((int64_t)b * Xp + sx[0]) * Yp + sy[0]) * Zp + sz[0]) * cpv + c];
       continue;
     }
     float acc[VEC];
@@ -849,7 +847,7 @@ __global__ void reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *
     T *e = reinterpret_cast<T *>(&o);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) e[k] = from_f<T>(acc[k]);
-    gi[i] = o;
+    dst[i] = o;
   }
 }
 
@@ -880,10 +878,9 @@ int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z
 int reflect_pad_backward(const void *gp, void *gi, int dtype, int B, int X, int Y, int Z, int C, int pad,
                          cudaStream_t st) {
   const int esz = dtype == CGAN3D_F32 ? 4 : 2;
-  if ((C * esz) % 16 == 0 && !((uintptr_t)gp & 15) && !((uintptr_t)gi & 15)) {
+  if ((C * esz) % 16 == 0 && !((uintptr_t)gp & 15) && !((uintptr_t)gi & 15) && X <= 65535 && B <= 65535) {
     const int cpv = C * esz / 16;
-    const int64_t tv = (int64_t)B * X * Y * Z * cpv;
-    const int bl = (int)mn<int64_t>((tv + 255) / 256, (int64_t)num_sms() * 16);
+    const dim3 bl((unsigned)Y, (unsigned)X, (unsigned)B);
     if (dtype == CGAN3D_F32)
       reflect_pad_bwd_vec_kernel<float><<<bl, 256, 0, st>>>((const uint4 *)gp, (uint4 *)gi, B, X, Y, Z, cpv, pad);
     else

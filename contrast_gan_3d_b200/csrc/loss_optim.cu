@@ -148,6 +148,49 @@ adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restric
   }
 }
 
+// multi-tensor variant: one launch updates up to kAdamBatch parameter tensors (blockIdx.y = tensor); the pointer table
+// travels in the kernel parameters, so there is no device-side table to upload
+constexpr int kAdamBatch = 48;
+struct AdamBatch {
+  float *p[kAdamBatch];
+  const float *g[kAdamBatch];
+  float *m[kAdamBatch];
+  float *v[kAdamBatch];
+  int64_t n[kAdamBatch];
+};
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamBatch t, float lr, float b1, float b2, float eps, int step, float clip) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    s_step_size = (float)((double)lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = 1.f - b1, w2 = 1.f - b2;
+  const int k = blockIdx.y;
+  float *__restrict__ p = t.p[k];
+  const float *__restrict__ g = t.g[k];
+  float *__restrict__ m = t.m[k];
+  float *__restrict__ v = t.v[k];
+  const int64_t n = t.n[k];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float mi = m[i];
+    mi = (w1 < 0.5f) ? mi + w1 * (gi - mi) : gi - (gi - mi) * (1.f - w1);  // torch lerp_
+    float vi = v[i] * b2;
+    vi = vi + (w2 * gi) * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    float pi = p[i] + (-step_size) * (mi / denom);
+    if (clip > 0.f) pi = fminf(fmaxf(pi, -clip), clip);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+  }
+}
+
 // ---------------------------------------------------------------- sampler / tiler
 __global__ void __launch_bounds__(256)
 crop_scale_kernel(const int16_t *__restrict__ vol, int X, int Y, int Z, int lbx, int lby, int lbz, int PX, int PY, int PZ,
@@ -273,6 +316,30 @@ int cgan3d_adam_step(float *param, const float *grad, float *exp_avg, float *exp
   adam_kernel<<<ew_blocks2(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step,
                                                             clip);
   CG_LAUNCH_CHECK("adam_step");
+  return 0;
+}
+
+int cgan3d_adam_step_multi(int count, float *const *params, const float *const *grads, float *const *exp_avgs,
+                           float *const *exp_avg_sqs, const int64_t *numels, float lr, float beta1, float beta2, float eps, int step,
+                           float clip, void *stream) {
+  CG_CHECK_ARG(count >= 0 && (count == 0 || (params && grads && exp_avgs && exp_avg_sqs && numels)), "adam_step_multi: NULL table");
+  CG_CHECK_ARG(step >= 1, "adam_step_multi: step must be >= 1");
+  for (int i0 = 0; i0 < count; i0 += kAdamBatch) {
+    AdamBatch t{};
+    const int nb = count - i0 < kAdamBatch ? count - i0 : kAdamBatch;
+    int64_t nmax = 0;
+    for (int i = 0; i < nb; ++i) {
+      CG_CHECK_ARG(params[i0 + i] && grads[i0 + i] && exp_avgs[i0 + i] && exp_avg_sqs[i0 + i] && numels[i0 + i] >= 0,
+                   "adam_step_multi: NULL tensor %d", i0 + i);
+      t.p[i] = params[i0 + i]; t.g[i] = grads[i0 + i]; t.m[i] = exp_avgs[i0 + i]; t.v[i] = exp_avg_sqs[i0 + i];
+      t.n[i] = numels[i0 + i];
+      nmax = nmax > t.n[i] ? nmax : t.n[i];
+    }
+    if (nmax == 0) continue;
+    const int bx = (int)((nmax + 255) / 256 < 64 ? (nmax + 255) / 256 : 64);
+    adam_multi_kernel<<<dim3(bx, nb), 256, 0, as_stream(stream)>>>(t, lr, beta1, beta2, eps, step, clip);
+    CG_LAUNCH_CHECK("adam_step_multi");
+  }
   return 0;
 }
 

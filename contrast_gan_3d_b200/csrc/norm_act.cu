@@ -198,7 +198,7 @@ __device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, double *
           const int64_t r = rb + (int64_t)(i0 + u) * gl;
           if (r < n_rows) {
             float v[NS][8];
-            eval(raw[u], v);
+            eval(r, raw[u], v);
 #pragma unroll
             for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) bn_stats8_kernel(const T *__restrict__ y,
   constexpr int NV = (int)sizeof(T) / 2;
   col_reduce8_body<2, 8, NV>(
       n_rows, C, sums, [&](int64_t r, uint4 *raw) { load8raw(y + r * C + c0, raw); },
-      [&](const uint4 *raw, float (&v)[2][8]) {
+      [&](int64_t, const uint4 *raw, float (&v)[2][8]) {
         float x[8];
         unpack8<T>(raw, x);
 #pragma unroll
@@ -308,7 +308,7 @@ bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t
   col_reduce8_body<2, 4, 2 * NV>(
       n_rows, C, sums,
       [&](int64_t r, uint4 *raw) { load8raw(y + r * C + c0, raw); load8raw(dz + r * C + c0, raw + NV); },
-      [&](const uint4 *raw, float (&v)[2][8]) {
+      [&](int64_t, const uint4 *raw, float (&v)[2][8]) {
         float yy[8], dd[8];
         unpack8<T>(raw, yy);
         unpack8<T>(raw + NV, dd);
@@ -383,6 +383,50 @@ bn_bwd_apply8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__res
     d0.store(dy + e0);
     if (two) d1.store(dy + e1);
   }
+}
+
+// bias + activation on 16-byte chunks (C % 8 == 0): a thread always owns the same 8 channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act8_kernel(const T *__restrict__ y, T *__restrict__ z, int64_t total8, int C, const float *__restrict__ bias, int act,
+                 float slope) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)((i * 8) % C);
+  float b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) b[k] = bias ? bias[c0 + k] : 0.f;
+  for (; i < total8; i += stride) {
+    V8<T> v;
+    v.load(y + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = act_fwd(v.v[k] + b[k], act, slope);
+    v.store(z + i * 8);
+  }
+}
+
+// dy = dz * act'(y + bias) and the dbias sums (fp64) in the same pass
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_bwd8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t n_rows, int C,
+                     const float *__restrict__ bias, int act, float slope, double *sums) {
+  const int c0 = (threadIdx.x % (C >> 3)) * 8;
+  float b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) b[k] = bias ? bias[c0 + k] : 0.f;
+  constexpr int NV = (int)sizeof(T) / 2;
+  col_reduce8_body<1, 4, 2 * NV>(
+      n_rows, C, sums,
+      [&](int64_t r, uint4 *raw) { load8raw(y + r * C + c0, raw); load8raw(dz + r * C + c0, raw + NV); },
+      [&](int64_t r, const uint4 *raw, float (&v)[1][8]) {
+        float yy[8], dd[8];
+        unpack8<T>(raw, yy);
+        unpack8<T>(raw + NV, dd);
+        V8<T> o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { o.v[k] = dd[k] * act_bwd(yy[k] + b[k], act, slope); v[0][k] = o.v[k]; }
+        o.store(dy + r * C + c0);
+      });
 }
 
 // ---------------------------------------------------------------- finalize
@@ -714,6 +758,16 @@ int cgan3d_bias_act(const void *y, void *z, int dtype, int64_t n_rows, int C, co
   const int64_t total = n_rows * C;
   if (total == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (vec8_ok(C, y, z)) {
+    const int64_t t8 = total / 8;
+    if (dtype == CGAN3D_F32)
+      bias_act8_kernel<float><<<ew_blocks(t8), 256, 0, st>>>((const float *)y, (float *)z, t8, C, bias, act, slope);
+    else
+      bias_act8_kernel<__nv_bfloat16><<<ew_blocks(t8), 256, 0, st>>>((const __nv_bfloat16 *)y, (__nv_bfloat16 *)z, t8, C, bias, act,
+                                                                     slope);
+    CG_LAUNCH_CHECK("bias_act(vec8)");
+    return 0;
+  }
   if (dtype == CGAN3D_F32)
     bias_act_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)y, (float *)z, total, C, bias, act, slope);
   else
@@ -731,6 +785,17 @@ int cgan3d_bias_act_backward(const void *dz, const void *y, void *dy, int dtype,
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(dbias_sums, 0, (size_t)C * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "bias_act_backward memset");
+  if (vec8_ok(C, dz, y, dy)) {
+    ColGrid g8 = col_grid8(n_rows, C, 1);
+    if (dtype == CGAN3D_F32)
+      bias_act_bwd8_kernel<float><<<g8.blocks, 256, g8.smem, st>>>((const float *)dz, (const float *)y, (float *)dy, n_rows, C, bias,
+                                                                   act, slope, dbias_sums);
+    else
+      bias_act_bwd8_kernel<__nv_bfloat16><<<g8.blocks, 256, g8.smem, st>>>((const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y,
+                                                                           (__nv_bfloat16 *)dy, n_rows, C, bias, act, slope, dbias_sums);
+    CG_LAUNCH_CHECK("bias_act_backward(vec8)");
+    return 0;
+  }
   ColGrid g = col_grid(n_rows, C, 1);
   if (dtype == CGAN3D_F32)
     bias_act_bwd_kernel<float><<<g.blocks, 256, g.smem, st>>>((const float *)dz, (const float *)y, (float *)dy, n_rows, C,

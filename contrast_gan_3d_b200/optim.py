@@ -1,11 +1,15 @@
 """FusedAdam: torch.optim.Adam's single-tensor math (defaults eps=1e-8, no weight decay, no amsgrad) as one
-libcgan3d kernel per parameter, with the WGAN weight clip of reference trainer/Trainer.py:136-138 fused in."""
+libcgan3d launch per 48 parameter tensors (pointer table in the kernel parameters), with the WGAN weight clip of
+reference trainer/Trainer.py:136-138 fused in."""
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 from torch.optim import Optimizer
 
 from . import ops
+from ._lib import call
 
 
 class FusedAdam(Optimizer):
@@ -22,6 +26,7 @@ class FusedAdam(Optimizer):
         for group in self.param_groups:
             b1, b2 = group["betas"]
             c = group["clip"] if clip is None else clip
+            by_step = {}  # tensors that share a step count go into one multi-tensor launch
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -34,6 +39,14 @@ class FusedAdam(Optimizer):
                 g = p.grad
                 if g.dtype != torch.float32 or not g.is_contiguous():
                     g = g.float().contiguous()
-                ops.adam_step(p.data, g, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"], st["step"],
-                              c or 0.0)
+                ops._need_cuda(p, g)
+                if not p.data.is_contiguous():
+                    raise RuntimeError("FusedAdam needs contiguous parameters")
+                by_step.setdefault(st["step"], []).append((p.data, g, st["exp_avg"], st["exp_avg_sq"]))
+            for step, items in by_step.items():
+                n = len(items)
+                tabs = [(C.c_void_p * n)(*[t[k].data_ptr() for t in items]) for k in range(4)]
+                numels = (C.c_int64 * n)(*[t[0].numel() for t in items])
+                call("cgan3d_adam_step_multi", n, tabs[0], tabs[1], tabs[2], tabs[3], numels, float(group["lr"]), float(b1),
+                     float(b2), float(group["eps"]), int(step), float(c or 0.0), ops._st())
         return loss

@@ -180,26 +180,45 @@ class Trainer:
         out[a.shape[0]:].copy_(b, non_blocking=True)
         return out
 
-    def _side_upload(self, parts: List[Tensor]):
+    def _side_upload(self, key: str, parts: List[Tensor]):
         """Host->device copy of `torch.cat(parts)` on a side stream, so that tensors that are only needed later in the step
         (the real batch for the critic, the masks for the generator loss) cross PCIe while G's forward pass runs.
-        Returns (device tensor, event or None); the consumer stream must wait on the event."""
+        The destination is a persistent per-key staging tensor (no cross-stream traffic through the caching allocator):
+        the copy waits for the previous step's consumers, the consumer stream must wait on the returned event.
+        Returns (device tensor, event or None)."""
         if all(t.device == self.device for t in parts):
             return (parts[0] if len(parts) == 1 else torch.cat(parts)), None
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging, self._staging_done = {}, {}
         main = torch.cuda.current_stream(self.device)
-        n = sum(t.shape[0] for t in parts)
+        shape = (sum(t.shape[0] for t in parts), *parts[0].shape[1:])
+        buf = self._staging.get(key)
+        if buf is None or tuple(buf.shape) != shape or buf.dtype != parts[0].dtype:
+            buf = self._staging[key] = torch.empty(shape, dtype=parts[0].dtype, device=self.device)
+            self._staging_done.pop(key, None)
+            self._copy_stream.wait_stream(main)  # order the copy after the allocation
+        done = self._staging_done.get(key)
+        if done is not None:
+            self._copy_stream.wait_event(done)
         with torch.cuda.stream(self._copy_stream):
-            out = torch.empty((n, *parts[0].shape[1:]), dtype=parts[0].dtype, device=self.device)
             o = 0
             for t in parts:
-                out[o:o + t.shape[0]].copy_(t, non_blocking=True)
+                buf[o:o + t.shape[0]].copy_(t, non_blocking=True)
                 o += t.shape[0]
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        out.record_stream(main)
-        return out, ev
+        return buf, ev
+
+    def _release_staging(self):
+        """Mark the staging tensors as consumed by everything enqueued so far on the compute stream."""
+        if getattr(self, "_copy_stream", None) is None:
+            return
+        main = torch.cuda.current_stream(self.device)
+        for key in self._staging:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._staging_done[key] = ev
 
     def _generate(self, subopt: Tensor):
         if hasattr(self.generator, "forward_corrected"):
@@ -213,8 +232,8 @@ class Trainer:
         do_train_critic = iteration % self.train_critic_every == 0
         main = torch.cuda.current_stream(self.device)
         subopt = self._upload_cat(low["data"], high["data"])  # needed first: on the compute stream
-        opt_t, opt_ev = self._side_upload([opt["data"]]) if do_train_critic else (None, None)
-        mask_t, mask_ev = self._side_upload([low["seg"], high["seg"]]) if do_train_generator else (None, None)
+        opt_t, opt_ev = self._side_upload("opt", [opt["data"]]) if do_train_critic else (None, None)
+        mask_t, mask_ev = self._side_upload("mask", [low["seg"], high["seg"]]) if do_train_generator else (None, None)
         attenuation, opt_hat = self._generate(subopt)
 
         log_dict: Dict[str, Tensor] = {}
@@ -226,6 +245,7 @@ class Trainer:
             if mask_ev is not None:
                 main.wait_event(mask_ev)
             log_dict |= self.train_generator(subopt, opt_hat, mask_t)
+        self._release_staging()
 
         if self.log_every and iteration % self.log_every == 0:
             self.logger_interface.logger.log_loss({k: v.detach().mean() for k, v in log_dict.items()}, iteration, "train")

@@ -171,6 +171,12 @@ int cgan3d_fill(void *x, int dtype, int64_t n, const float *value_dev, float sca
  *      reference trainer/Trainer.py:135-138,157) ------------------------------------------ */
 int cgan3d_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, int step, float clip /* <=0: none */, void *stream);
+/* Same update for `count` parameter tensors in one launch per 48 tensors (torch.optim.Adam's foreach path,
+ * reference trainer/Trainer.py:134,158 via optimizer.step()).  The five tables are HOST arrays of `count` device
+ * pointers / element counts; all tensors share lr, betas, eps, step and clip.                                  */
+int cgan3d_adam_step_multi(int count, float *const *params, const float *const *grads, float *const *exp_avgs,
+                           float *const *exp_avg_sqs, const int64_t *numels, float lr, float beta1, float beta2,
+                           float eps, int step, float clip, void *stream);
 
 /* ---- patch sampler (reference data/CCTADataLoader.py:76-95, data/Scaler.py:41-42) ----------
  * vol: int16 [X][Y][Z][2] (HU, centerline mask) on device.  Pads symmetrically with 0 up to the
