@@ -156,7 +156,16 @@ class Trainer:
 
     def train_generator(self, inputs: Tensor, reconstructions: Tensor, centerlines_masks: Tensor) -> Dict[str, Tensor]:
         self.optimizer_G.zero_grad(set_to_none=True)
-        loss_G = self.gan_loss_w * -self.loss_GAN(self.critic(reconstructions))
+        # The critic's parameter gradients of this pass are dead (the reference lets autograd compute them and zeroes them
+        # before their next use, Trainer.py:111): freeze the critic so that only its dgrad chain runs.
+        critic_params = [p for p in self.critic.parameters() if p.requires_grad]
+        for p in critic_params:
+            p.requires_grad_(False)
+        try:
+            loss_G = self.gan_loss_w * -self.loss_GAN(self.critic(reconstructions))
+        finally:
+            for p in critic_params:
+                p.requires_grad_(True)
         if isinstance(self.loss_HU, HULoss):
             loss_sim, loss_hu = fused_similarity_and_hu(reconstructions, inputs, centerlines_masks, self.loss_HU,
                                                         self.sim_loss_w, self.hu_loss_w)

@@ -571,3 +571,49 @@ def test_tcgen05_thin_7x7x7_layers(case):
         g, _ = spec.geometry(B, sp)
         assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 0) == 2
         assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, 1) == 2
+
+
+def test_train_step_bf16_full_patch_size_against_oracle():
+    """BASELINE patch size (128^3, the shape every tcgen05 tiling of bench.py runs at), 2 pairs, bf16 path: the four
+    logged losses of one full G+D step against the fp32 CPU oracle, rtol 2e-2 (atol as in the 32^3 test)."""
+    patch = (128, 128, 128)
+    st = O.StepState(seed=0)
+    tr = _make_trainer(torch.bfloat16)
+    gen = torch.Generator().manual_seed(5)
+    opt, low, high, ml, mh = _batches(gen, patch, 2, 1, 1)
+    ref = O.train_step(st, opt, low, high, ml, mh, 0)
+    logs = tr.train_step([dict(data=opt, seg=None, name=[]), dict(data=low, seg=ml, name=[]), dict(data=high, seg=mh, name=[])], 0)
+    atol = dict(zip(KEYS, (2e-3, 2e-3, 2e-3, 1e-3, 1e-3)))
+    for k in KEYS:
+        got = float(logs[k].detach())
+        assert abs(got - ref[k]) <= 2e-2 * abs(ref[k]) + atol[k], (k, got, ref[k])
+
+
+def test_full_size_layers_tcgen05_vs_generic():
+    """Every generator layer shape of BASELINE config C3 (B = 1): tcgen05 fprop vs the CUDA-core kernel on identical bf16
+    operands (<= 1 bf16 ulp), and linearity conv(2x) == 2 conv(x) bit-exactly (a power-of-two scale commutes with every
+    rounding step), which is size independent."""
+    _lib, ops = _ops()
+    layers = [  # (transposed, cin, cout, k, stride, pad, out_pad, spatial_in)
+        (False, 1, 16, 7, 1, 0, 0, (134, 134, 134)), (False, 16, 32, 3, 2, 1, 0, (128, 128, 128)),
+        (False, 32, 64, 3, 2, 1, 0, (64, 64, 64)), (False, 64, 64, 3, 1, 1, 0, (32, 32, 32)),
+        (True, 64, 32, 3, 2, 1, 1, (32, 32, 32)), (True, 32, 16, 3, 2, 1, 1, (64, 64, 64)),
+        (False, 16, 1, 7, 1, 0, 0, (134, 134, 134)),
+    ]
+    gen = torch.Generator().manual_seed(9)
+    for tr, cin, cout, k, s, p, op, sp in layers:
+        spec = ops.ConvSpec(transposed=tr, cin=cin, cout=cout, k=k, stride=s, pad=p, out_pad=op)
+        g, _ = spec.geometry(1, sp)
+        x = torch.randn((1, *sp, cin), generator=gen).to(DEV, torch.bfloat16)
+        wshape = (cin, cout, k, k, k) if tr else (cout, cin, k, k, k)
+        w = (torch.randn(wshape, generator=gen) / (cin * k ** 3) ** 0.5).to(DEV)
+        wp = ops.pack_weights(w, torch.bfloat16)
+        f = (lambda xx, impl: ops.conv_scatter(g, xx, wp, impl=impl)) if tr else (lambda xx, impl: ops.conv_gather(g, xx, wp, impl=impl))
+        opi = 1 if tr else 0
+        assert _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, opi) == 2, (cin, cout, k, s)
+        y_tc = f(x, _lib.IMPL_TC).float()
+        y_gen = f(x, _lib.IMPL_GENERIC).float()
+        d = (y_tc - y_gen).abs()
+        assert bool((d <= 2 ** -7 * y_gen.abs() + 1e-3).all()), f"{cin}->{cout} k{k} s{s}: {d.max().item()}"
+        y2 = f(x * 2, _lib.IMPL_TC).float()
+        assert torch.equal(y2, 2 * y_tc), f"{cin}->{cout} k{k} s{s}: linearity"
