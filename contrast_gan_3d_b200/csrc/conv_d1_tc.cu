@@ -26,13 +26,14 @@ typedef CUresult (*EncodeTiledFnD)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 void *tc_encode_fn_ptr();  // conv_tc.cu
+CUtensorMapL2promotion tc_l2_promo();  // conv_tc.cu
 
 static int encode_map_d1(CUtensorMap *tm, const void *ptr, int rank, const cuuint64_t *gdim, const cuuint64_t *gstr,
                          const cuuint32_t *box, const cuuint32_t *estr) {
   EncodeTiledFnD enc = reinterpret_cast<EncodeTiledFnD>(tc_encode_fn_ptr());
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (critic first layer) failed with %d", (int)r);
   return 0;

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "conv_internal.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace cg {
 
@@ -266,6 +267,17 @@ static EncodeTiledFn encode_fn() {
 
 void *tc_encode_fn_ptr() { return reinterpret_cast<void *>(encode_fn()); }
 
+// L2 fetch granularity of every TMA tensor map.  CGAN3D_L2PROMO = 0 (none) / 64 / 128 / 256 overrides the default.
+CUtensorMapL2promotion tc_l2_promo() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CGAN3D_L2PROMO");
+    v = e ? atoi(e) : 128;
+  }
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+}
+
 // conv_tc_prog.cu
 bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op);
 size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
@@ -330,6 +342,10 @@ int d1_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, vo
 int d1_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
                  cudaStream_t st);
 
+// wgrad_s2_tc.cu (stride-2 layers with Cs in {32, 64}, Cb in {16, 32}: swizzled whole-voxel operands, N = 4*Cb)
+bool tc_wgrad_s2_supported(const cgan3d_conv_geom &g);
+int tc_wgrad_s2_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st);
+
 // wgrad_tc.cu
 bool tc_wgrad_supported(const cgan3d_conv_geom &g);
 int tc_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st);
@@ -344,7 +360,7 @@ static bool s1_shape_ok(const cgan3d_conv_geom &g, int dtype, int op) {
 bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op) {
   if (!cgan3d_device_supports_tc() || encode_fn() == nullptr) return false;
   if (thin_supported(g, dtype, op) || d1_supported(g, dtype, op)) return true;
-  if (op == 2) return dtype == CGAN3D_BF16 && tc_wgrad_supported(g);
+  if (op == 2) return dtype == CGAN3D_BF16 && (tc_wgrad_s2_supported(g) || tc_wgrad_supported(g));
   if (!s1_shape_ok(g, dtype, op)) return tc_prog_supported(g, dtype, op);
   TcPlan p;
   const int Cin = op == 0 ? g.Cb : g.Cs, N = op == 0 ? g.Cs : g.Cb;
@@ -380,7 +396,7 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
   const cuuint32_t box[5] = {8, (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled failed with %d", (int)r);
   const int grid = (int)mn<long long>((long long)p.nitems * p.X, (long long)num_sms());
@@ -438,6 +454,7 @@ int tc_wgrad(const cgan3d_conv_geom &g, const void *big, const void *small, floa
              cudaStream_t st) {
   if (thin_supported(g, CGAN3D_BF16, 2)) return thin_wgrad_run(g, big, small, dw, beta, ws, ws_bytes, st);
   if (d1_supported(g, CGAN3D_BF16, 2)) return d1_wgrad_run(g, big, small, dw, beta, ws, ws_bytes, st);
+  if (tc_wgrad_s2_supported(g) && !getenv("CGAN3D_WGRAD_V1")) return tc_wgrad_s2_run(g, big, small, dw, beta, st);
   return tc_wgrad_run(g, big, small, dw, beta, st);
 }
 

@@ -434,6 +434,7 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 void *tc_encode_fn_ptr();  // conv_tc.cu
+CUtensorMapL2promotion tc_l2_promo();  // conv_tc.cu
 
 int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
                 cudaStream_t st) {
@@ -458,7 +459,7 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
   const cuuint32_t box[5] = {8, (cuuint32_t)(es * (p.Zh - 1) + 1), (cuuint32_t)(es * (p.Yh - 1) + 1), 1, 1};
   const cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (strided) failed with %d", (int)r);
   const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;

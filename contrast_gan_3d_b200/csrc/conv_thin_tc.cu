@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(192, 1)
 wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmS, float *__restrict__ dw,
                       const __grid_constant__ ThinCPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *ringB = smem;                                    // 8 S16 plane slots, each [2 chunks][rowsB][8 ch]
+  uint8_t *ringB = smem;                                    // 8 S16 plane slots, each [rowsB][16 ch] (SWIZZLE_32B)
   uint8_t *ringA = ringB + (size_t)kRingC * p.slotB_bytes;  // E slabs, [rowsA][8 j]
   uint64_t *bars = reinterpret_cast<uint64_t *>(ringA + (size_t)p.e_slots * p.slotA_bytes);
   uint64_t *b_full = bars, *b_empty = bars + kRingC, *a_full = b_empty + kRingC, *a_empty = a_full + p.e_slots;
@@ -508,10 +508,8 @@ wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
 #pragma unroll
         for (int i = 0; i < kRingC; ++i) if ((uint32_t)i == slot) { n = useB[i]; useB[i] = n + 1; }
         if (n > 0) tc::mbar_wait(&b_empty[slot], (n - 1) & 1);
-        tc::mbar_expect_tx(&b_full[slot], 2 * p.boxB_bytes);
-        uint8_t *dst = ringB + (size_t)slot * p.slotB_bytes;
-        tc::tma_load_5d(dst, &tmS, &b_full[slot], 0, z0, y0, xs, b);
-        tc::tma_load_5d(dst + (size_t)p.rowsB * 16, &tmS, &b_full[slot], 8, z0, y0, xs, b);
+        tc::mbar_expect_tx(&b_full[slot], p.boxB_bytes);
+        tc::tma_load_5d(ringB + (size_t)slot * p.slotB_bytes, &tmS, &b_full[slot], 0, z0, y0, xs, b);  // [row][16 ch], SWIZZLE_32B
       };
       uint32_t ea = 0;
       int col, x0, xlen;
@@ -531,7 +529,8 @@ wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
   } else if (warp == 5) {
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::make_idesc_bf16(64, 64, 1, 1);
-    const uint64_t a_hi = tc::make_desc(0, 128, (uint32_t)p.Zt * 16), b_hi = tc::make_desc(0, 128, (uint32_t)p.rowsB * 16);
+    // B: MN-major SWIZZLE_32B, one 16-channel block per ring slot (LBO = slot stride), 8-voxel K groups 256 B apart
+    const uint64_t a_hi = tc::make_desc(0, 128, (uint32_t)p.Zt * 16), b_hi = tc::make_desc_sw_mn(0, p.slotB_bytes, 256, 32);
     const uint32_t ringA_u32 = tc::smem_u32(ringA), ringB_u32 = tc::smem_u32(ringB);
     uint32_t useB[kRingC];
 #pragma unroll
@@ -565,8 +564,8 @@ wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
 #pragma unroll 4
             for (int kb = 0; kb < p.kblocks; ++kb) {
               tc::umma_bf16(d, a_desc, b_desc, idesc, 1u);
-              a_desc += 16;
-              b_desc += 16;
+              a_desc += 16;  // 16 rows of 16 B
+              b_desc += 32;  // 16 rows of 32 B
             }
           }
           __syncwarp();
@@ -640,6 +639,7 @@ typedef CUresult (*EncodeTiledFnT)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 void *tc_encode_fn_ptr();  // conv_tc.cu
+CUtensorMapL2promotion tc_l2_promo();  // conv_tc.cu
 
 static int encode_map(CUtensorMap *tm, const void *ptr, int rank, const cuuint64_t *gdim, const cuuint64_t *gstr,
                       const cuuint32_t *box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE) {
@@ -647,7 +647,7 @@ static int encode_map(CUtensorMap *tm, const void *ptr, int rank, const cuuint64
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, tc_l2_promo(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (thin conv) failed with %d", (int)r);
   return 0;
@@ -885,7 +885,7 @@ static bool plan_thin_c(const cgan3d_conv_geom &g, ThinCPlan &p) {
   p.kblocks = p.rowsB / 16;
   p.slotB_bytes = 2u * p.rowsB * 16;
   p.slotA_bytes = (uint32_t)(p.Yt + 7) * p.Zt * 16;
-  p.boxB_bytes = 16u * p.Zt * p.Yt;
+  p.boxB_bytes = 32u * p.Zt * p.Yt;
   p.boxA_bytes = p.slotA_bytes;
   const uint32_t fixed = kRingC * p.slotB_bytes + 512;
   if (fixed + 2 * p.slotA_bytes > kSmemLimitThin) return false;
@@ -925,8 +925,8 @@ int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small
   {
     const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zs, (cuuint64_t)p.Ys, (cuuint64_t)p.Xs, (cuuint64_t)p.B};
     const cuuint64_t gstr[4] = {32, (cuuint64_t)p.Zs * 32, (cuuint64_t)p.Ys * p.Zs * 32, (cuuint64_t)p.Xs * p.Ys * p.Zs * 32};
-    const cuuint32_t box[5] = {8, (cuuint32_t)p.Zt, (cuuint32_t)p.Yt, 1, 1};
-    int r = encode_map(&tmS, s16, 5, gdim, gstr, box);
+    const cuuint32_t box[5] = {16, (cuuint32_t)p.Zt, (cuuint32_t)p.Yt, 1, 1};
+    int r = encode_map(&tmS, s16, 5, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r) return r;
   }
   static bool attr_set = false;

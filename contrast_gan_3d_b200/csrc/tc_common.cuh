@@ -148,6 +148,13 @@ __device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t sbo_by
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
          (layout << 61);
 }
+// Swizzled MN-major operand: rows (K index) of `swz_bytes` hold swz_bytes/2 consecutive M/N elements; 8-row K groups are
+// sbo_bytes apart (8 * swz_bytes when dense), further blocks of swz_bytes/2 M/N elements are lbo_bytes apart.
+__device__ __forceinline__ uint64_t make_desc_sw_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swz_bytes) {
+  const uint64_t layout = swz_bytes == 128 ? 2ull : (swz_bytes == 64 ? 4ull : 6ull);
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.  a_mn / b_mn: 1 = MN-major operand.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
