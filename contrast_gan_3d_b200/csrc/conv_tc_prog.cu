@@ -15,6 +15,10 @@
 //   * Thin critic layers: Cin == 8 (gather) forms K = 16 from TWO z-adjacent taps of a parity class -- the second
 //     8-channel K chunk is the same slab one row later (A-descriptor LBO = 16 bytes) and the filter tile holds the two
 //     taps back to back; N (output channels) < 16 is padded to 16 with zero filter columns and only Nout channels are stored.
+//   * Scatter, stacked mode (8*N <= 256 and the tiles fit): the 8 output phases are stacked on the MMA N dimension.  Every
+//     (phase, tap) pair that reads the small-side slab at row shift (oy, oz) of plane i+xo goes into ONE MMA whose filter
+//     tile has a zero block for the phases without such a tap: 8 (k = 3) or 27 (k = 4) MMA groups per row tile instead
+//     of 27 / 64 -- an SS-mode MMA costs ~75-85 cycles for any N <= 128.
 //   * All filter tiles ([Cin/8][N][8] bf16 each) stay RESIDENT in shared memory for the whole kernel (<= 108 KB for
 //     the layers of this model), so the only streamed operand is the activation slab; each slab is released as soon
 //     as its taps are issued (ring of slots, no cross-plane reuse: these layers are L2/HBM-bound).
@@ -50,6 +54,8 @@ struct ProgPlan {
                          // wide critic layers do not fit in shared memory, so the channels are covered by 2 or 4 launches)
   int paired;            // 1: Cin == 8, K = 16 is two z-adjacent taps (tile t holds filter taps tile_tap[t][0..1])
   uint32_t a_lbo_bytes;
+  int a_swz;             // 0: activation slab in Cin/8 chunks [chunk][row][8 ch] (SWIZZLE_NONE); 32/64/128: whole voxels,
+                         // [row][Cin] with 2*Cin-byte rows in the matching TMA/UMMA swizzle mode (one TMA per slab)
   int in_scale;          // 2: gather from the big side (strided TMA), 1: scatter from the small side
   int out_scale;         // 1: gather, 2: scatter (output voxel = out_scale*grid + phase)
   int Zt, nzt, Zh, Yt, nslabs, Yh;
@@ -59,6 +65,10 @@ struct ProgPlan {
   ProgEntry entries[kMaxEntries];
   ProgTap taps[kMaxTaps];
   int8_t tile_tap[kMaxTaps][2];  // paired mode: filter taps of the two K chunks of tile t (-1 = zero)
+  int stack;                     // 1: scatter with the 8 phases stacked on N (tile t holds tap tile_phase_tap[t][phase])
+  int Nmma;                      // N of one MMA (N, or 8*N when stacked)
+  int acc_stride, mt_stride;     // TMEM columns between accumulators (phases) / between M-tiles
+  int8_t tile_phase_tap[kMaxTaps][8];
 };
 
 template <int KSTEPS, int MT>
@@ -67,7 +77,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
                     const __grid_constant__ ProgPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *bres = smem;                                         // resident filter tiles
-  uint8_t *ring = bres + (size_t)p.nbt * p.btile_bytes;         // activation slab slots
+  uint8_t *ring = bres + (((size_t)p.nbt * p.btile_bytes + 1023) & ~(size_t)1023);  // activation slab slots (1024-aligned)
   uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)p.nslots * p.slot_bytes);
   uint64_t *b_ready = bars, *s_full = bars + 1, *s_empty = s_full + p.nslots;
   uint64_t *tm_full = s_empty + p.nslots, *tm_empty = tm_full + 2;
@@ -92,7 +102,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   // contiguous, balanced range of steps (column-major over (b, z-tile, y-slab) x output plane)
   const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
   const int s_begin = (int)(total * blockIdx.x / gridDim.x), s_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
-  const int kch = p.paired ? 1 : (p.Cin >> 3);
+  const int kch = (p.paired || p.a_swz) ? 1 : (p.Cin >> 3);
   auto decode = [&](int st, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x) {
     x = st % p.Xg; st /= p.Xg;
     const int sl = st % p.nslabs; st /= p.nslabs;
@@ -121,19 +131,25 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           tc::mbar_expect_tx(&s_full[slot], p.box_bytes * kch);
           uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
           const int cz = p.in_scale * z0 + E.cz, cy = p.in_scale * y0 + E.cy, cx = p.in_scale * x + E.cx;
-          for (int cc = 0; cc < kch; ++cc)
-            tc::tma_load_5d(dst + (size_t)cc * p.rows_alloc * 16, &tmA, &s_full[slot], cc * 8, cz, cy, cx, b);
+          if (p.a_swz) {
+            tc::tma_load_5d(dst, &tmA, &s_full[slot], 0, cz, cy, cx, b);
+          } else {
+            for (int cc = 0; cc < kch; ++cc)
+              tc::tma_load_5d(dst + (size_t)cc * p.rows_alloc * 16, &tmA, &s_full[slot], cc * 8, cz, cy, cx, b);
+          }
         }
       }
     }
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(128, p.N, 0, 0);
+    const uint32_t idesc = tc::make_idesc_bf16(128, p.Nmma, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
-    const uint32_t a_lbo = p.a_lbo_bytes, b_lbo = (uint32_t)p.N * 16;
-    const uint64_t a_hi = tc::make_desc(0, a_lbo, 128), b_hi = tc::make_desc(0, b_lbo, 128);
-    const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
+    const uint32_t a_lbo = p.a_lbo_bytes, b_lbo = (uint32_t)p.Nmma * 16;
+    const uint32_t a_row = p.a_swz ? (uint32_t)p.a_swz >> 4 : 1u;  // 16-byte units per activation row
+    const uint64_t a_hi = p.a_swz ? tc::make_desc_sw(0, 8u * p.a_swz, (uint32_t)p.a_swz) : tc::make_desc(0, a_lbo, 128);
+    const uint64_t b_hi = tc::make_desc(0, b_lbo, 128);
+    const uint32_t a_kstep = p.a_swz ? 2u : (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;
     tc::mbar_wait(b_ready, 0);
     tc::tc_fence_after();
     uint32_t e = 0, acc = 0;
@@ -150,16 +166,16 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
         for (int t = 0; t < E.ntaps; ++t) {
           const ProgTap &T = p.taps[E.tap0 + t];
-          const uint64_t a0 = a_hi | (uint64_t)((a_slot + T.row_shift) & 0x3FFF);
+          const uint64_t a0 = a_hi | (uint64_t)((a_slot + T.row_shift * a_row) & 0x3FFF);
           const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)T.btile * p.btile_bytes) >> 4) & 0x3FFF);
-          const uint32_t d0 = d_base + (uint32_t)T.acc * (MT * p.N);
+          const uint32_t d0 = d_base + (uint32_t)T.acc * p.acc_stride;
           const uint32_t keep = T.first ? 0u : 1u;
           if (leader) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
               for (int kk = 0; kk < KSTEPS; ++kk)
-                tc::umma_bf16(d0 + mt * p.N, a0 + (uint64_t)(mt * 128 + kk * a_kstep), b0 + (uint64_t)(kk * b_kstep), idesc,
+                tc::umma_bf16(d0 + mt * p.mt_stride, a0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep), b0 + (uint64_t)(kk * b_kstep), idesc,
                               (kk != 0) ? 1u : keep);
             }
           }
@@ -190,7 +206,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           const int oy = p.out_scale * (y0 + gy) + py, oz = p.out_scale * (z0 + gz) + pz;
           const bool valid = gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo;
           bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.out_pitch + p.out_c0;
-          const uint32_t taddr = d_base + (uint32_t)(a * MT + mt) * p.N;
+          const uint32_t taddr = d_base + (uint32_t)(a * p.acc_stride + mt * p.mt_stride);
           for (int c0 = 0; c0 < p.Nout; c0 += 16) {
             uint32_t v[16];
             tc::tmem_ld16(taddr + c0, v);
@@ -224,7 +240,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
 // Columns n >= Nout are zero.
 __global__ void repack_prog_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int scatter,
                                    const __grid_constant__ ProgPlan p) {
-  const int K = p.paired ? 16 : p.Cin, N = p.N;
+  const int K = p.paired ? 16 : p.Cin, N = p.Nmma;
   const int64_t total = (int64_t)p.nbt * K * N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i & 7);
@@ -232,11 +248,12 @@ __global__ void repack_prog_kernel(const bf16 *__restrict__ wp, bf16 *__restrict
     const int n = (int)(t % N); t /= N;
     const int cc = (int)(t % (K >> 3));
     const int tile = (int)(t / (K >> 3));
-    const int tap = p.paired ? p.tile_tap[tile][cc] : tile;
+    const int nn = p.stack ? n % p.N : n;  // stacked: row n = phase * N + channel
+    const int tap = p.stack ? p.tile_phase_tap[tile][n / p.N] : (p.paired ? p.tile_tap[tile][cc] : tile);
     const int ci = p.paired ? c8 : cc * 8 + c8;
     bf16 v = __float2bfloat16_rn(0.f);
-    if (n < p.Nout && tap >= 0) {
-      const int no = n + p.out_c0;
+    if (nn < p.Nout && tap >= 0) {
+      const int no = nn + p.out_c0;
       const int cb = scatter ? no : ci, cs = scatter ? ci : no;
       v = wp[((int64_t)tap * Cb + cb) * Cs + cs];
     }
@@ -301,6 +318,42 @@ static bool build_program(const cgan3d_conv_geom &g, int scatter, ProgPlan &p) {
     for (int ph = 0; ph < 2; ++ph)
       for (int d = 0; d < k; ++d)
         if (((ph + 1 - d) & 1) == 0) { const int o = (ph + 1 - d) / 2; offmin = min(offmin, o); offmax = max(offmax, o); }
+    if (p.stack) {
+      // tap of phase ph that reads the slab at offset off along one axis: d = ph + 1 - 2*off (if 0 <= d < k)
+      auto tap1 = [&](int ph, int off) { const int d = ph + 1 - 2 * off; return (d >= 0 && d < k) ? d : -1; };
+      bool first = true;
+      for (int xo = offmin; xo <= offmax; ++xo) {
+        ProgEntry E{};
+        E.cx = (int8_t)xo; E.cy = (int8_t)offmin; E.cz = (int8_t)offmin;
+        E.tap0 = (uint8_t)nt; E.ntaps = 0;
+        for (int oy = offmin; oy <= offmax; ++oy)
+          for (int oz = offmin; oz <= offmax; ++oz) {
+            bool any = false;
+            int8_t taps8[8];
+            for (int ph = 0; ph < 8; ++ph) {
+              const int dx = tap1(ph >> 2, xo), dy = tap1((ph >> 1) & 1, oy), dz = tap1(ph & 1, oz);
+              taps8[ph] = (int8_t)((dx >= 0 && dy >= 0 && dz >= 0) ? (dx * k + dy) * k + dz : -1);
+              any = any || taps8[ph] >= 0;
+            }
+            if (!any) continue;
+            if (nt >= kMaxTaps) return false;
+            ProgTap T{};
+            T.row_shift = (uint16_t)((oy - offmin) * p.Zh + (oz - offmin));
+            T.btile = (uint8_t)nt;
+            T.acc = 0; T.first = first ? 1 : 0;
+            first = false;
+            for (int ph = 0; ph < 8; ++ph) p.tile_phase_tap[nt][ph] = taps8[ph];
+            p.taps[nt++] = T; E.ntaps++;
+          }
+        if (E.ntaps == 0) continue;
+        if (ne >= kMaxEntries) return false;
+        p.entries[ne++] = E;
+      }
+      p.nacc = 8;
+      p.nentries = ne;
+      p.ntaps = nt;
+      return true;
+    }
     bool seen[8] = {false, false, false, false, false, false, false, false};
     for (int xo = offmin; xo <= offmax; ++xo) {
       ProgEntry E{};
@@ -372,8 +425,17 @@ static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &be
   p.in_scale = scatter ? 1 : 2; p.out_scale = scatter ? 2 : 1;
   p.nbt = paired ? taps / 2 + (g.k == 3 ? 9 : 0) : taps;  // upper bound; build_program fixes the exact count
   p.btile_bytes = (uint32_t)(paired ? 16 : Cin) * N * 2;
-  const uint32_t b_total = p.nbt * p.btile_bytes;
+  p.Nmma = N; p.acc_stride = 0; p.mt_stride = N;  // acc_stride of the unstacked layout depends on mtiles (set below)
+  if (scatter && 8 * N <= 256) {
+    const int ncombo = g.k == 3 ? 8 : 27;
+    const uint32_t tile = (uint32_t)Cin * 8 * N * 2;
+    if ((ncombo * tile + 1023) / 1024 * 1024 + 40000 <= kSmemLimitProg) {
+      p.stack = 1; p.Nmma = 8 * N; p.nbt = ncombo; p.btile_bytes = tile;
+    }
+  }
+  const uint32_t b_total = (p.nbt * p.btile_bytes + 1023) / 1024 * 1024;
   if (b_total + 40000 > kSmemLimitProg) return false;
+  const int a_swz = (!paired && Cin <= 64) ? 2 * Cin : 0;
   double best_score = 0;
   bool found = false;
   for (int nzt = 1; nzt <= 4; ++nzt) {
@@ -386,7 +448,7 @@ static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &be
       if (mt > 4 || 2 * nacc * mt * N > 512) break;
       const int rows_alloc = ((mt * 128 + halo * Zh + halo) + 7) / 8 * 8;
       if (rows_alloc > 16383 || Yh * Zh > rows_alloc) continue;
-      const uint32_t slot = (uint32_t)(paired ? 1 : Cin / 8) * rows_alloc * 16;
+      const uint32_t slot = a_swz ? ((uint32_t)rows_alloc * a_swz + 1023) / 1024 * 1024 : (uint32_t)(paired ? 1 : Cin / 8) * rows_alloc * 16;
       const int nslots = (int)mn<uint32_t>(8, (kSmemLimitProg - b_total - 512) / slot);
       if (nslots < 3) break;
       const int nslabs = (p.Yg + Yt - 1) / Yt;
@@ -404,7 +466,10 @@ static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &be
   if (!found) return false;
   ProgPlan &q = best;
   const int es = q.in_scale;
-  q.box_bytes = 16u * q.Zh * q.Yh;
+  q.a_swz = a_swz;
+  if (q.stack) { q.acc_stride = q.N; q.mt_stride = 8 * q.N; }
+  else { q.acc_stride = q.mtiles * q.N; q.mt_stride = q.N; }
+  q.box_bytes = (a_swz ? (uint32_t)a_swz : 16u) * q.Zh * q.Yh;
   (void)es;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * nacc * q.mtiles * N)) cols <<= 1;
@@ -412,7 +477,7 @@ static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &be
   q.smem_bytes = b_total + q.nslots * q.slot_bytes + 512;
   q.a_lbo_bytes = paired ? 16u : (uint32_t)q.rows_alloc * 16;
   if (!build_program(g, scatter, q)) return false;
-  if (paired) {
+  if (paired || q.stack) {
     if ((uint32_t)q.ntaps * q.btile_bytes > b_total) return false;
     q.nbt = q.ntaps;
   }
@@ -427,7 +492,10 @@ bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op) {
 
 size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   if (dtype != CGAN3D_BF16 || (op != 0 && op != 1)) return 0;
-  return (size_t)g.k * g.k * g.k * mx(g.Cb, 16) * mx(g.Cs, 16) * 2 + 4 * 256 + 256;
+  ProgPlan p;
+  int nsplit = 1;
+  if (!plan_prog(g, op, p, &nsplit)) return 0;
+  return (((size_t)p.nbt * p.btile_bytes + 255) / 256 * 256) * nsplit + 256;
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -456,10 +524,12 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
   const cuuint64_t gdim[5] = {(cuuint64_t)Ci, (cuuint64_t)Zi, (cuuint64_t)Yi, (cuuint64_t)Xi, (cuuint64_t)g.B};
   const cuuint64_t gstr[4] = {(cuuint64_t)Ci * 2, (cuuint64_t)Zi * Ci * 2, (cuuint64_t)Yi * Zi * Ci * 2,
                               (cuuint64_t)Xi * Yi * Zi * Ci * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)(es * (p.Zh - 1) + 1), (cuuint32_t)(es * (p.Yh - 1) + 1), 1, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)(p.a_swz ? Ci : 8), (cuuint32_t)(es * (p.Zh - 1) + 1), (cuuint32_t)(es * (p.Yh - 1) + 1), 1, 1};
   const cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  const CUtensorMapSwizzle swz = p.a_swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (p.a_swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (p.a_swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(),
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, tc_l2_promo(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (strided) failed with %d", (int)r);
   const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
