@@ -34,6 +34,7 @@ struct TcPlan {
   int xseg, nxseg;
   int mtiles, rows_alloc, nitems, b_stages;
   uint32_t plane_bytes, btile_bytes, box_bytes, tmem_cols, smem_bytes;
+  int a_swz;  // 0: plane slab in Cin/8 chunks (SWIZZLE_NONE); 32/64/128: whole voxels, [row][Cin] in the matching swizzle mode
 };
 
 constexpr int kPlaneSlots = 3;
@@ -93,7 +94,7 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const int kchunks8 = p.Cin >> 3;
+  const int kchunks8 = p.a_swz ? 1 : (p.Cin >> 3);
   const int taps = 27;
 
   if (warp == 4) {
@@ -107,8 +108,12 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
           if (use > 0) tc::mbar_wait(&plane_empty[slot], (use - 1) & 1);
           tc::mbar_expect_tx(&plane_full[slot], p.box_bytes * kchunks8);
           uint8_t *dst = planes + (size_t)slot * p.plane_bytes;
-          for (int cc = 0; cc < kchunks8; ++cc)
-            tc::tma_load_5d(dst + (size_t)cc * p.rows_alloc * 16, &tmA, &plane_full[slot], cc * 8, z0 - 1, y0 - 1, px, b);
+          if (p.a_swz) {
+            tc::tma_load_5d(dst, &tmA, &plane_full[slot], 0, z0 - 1, y0 - 1, px, b);
+          } else {
+            for (int cc = 0; cc < kchunks8; ++cc)
+              tc::tma_load_5d(dst + (size_t)cc * p.rows_alloc * 16, &tmA, &plane_full[slot], cc * 8, z0 - 1, y0 - 1, px, b);
+          }
         }
       }
     }
@@ -138,8 +143,10 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
       const uint32_t idesc = tc::make_idesc_bf16(128, p.N, 0, 0);
       const uint32_t planes_u32 = tc::smem_u32(planes), bt_u32 = tc::smem_u32(bt);
       const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16, b_lbo = (uint32_t)p.N * 16;
-      const uint64_t a_desc_hi = tc::make_desc(0, a_lbo, 128), b_desc_hi = tc::make_desc(0, b_lbo, 128);
-      const uint32_t a_kstep = (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;  // descriptor address units (16 B)
+      const uint32_t a_row = p.a_swz ? (uint32_t)p.a_swz >> 4 : 1u;  // 16-byte units per activation row
+      const uint64_t a_desc_hi = p.a_swz ? tc::make_desc_sw(0, 8u * p.a_swz, (uint32_t)p.a_swz) : tc::make_desc(0, a_lbo, 128);
+      const uint64_t b_desc_hi = tc::make_desc(0, b_lbo, 128);
+      const uint32_t a_kstep = p.a_swz ? 2u : (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;  // descriptor address units (16 B)
       uint32_t e_base = 0, t = 0, acc = 0;
       int b, z0, zlen, y0, ylen, x0, xlen;
       for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen);) {
@@ -159,7 +166,7 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
                 tc::mbar_wait(&b_full[s], (t / p.b_stages) & 1);
                 tc::tc_fence_after();
                 const uint64_t b_desc0 = b_desc_hi | (uint64_t)(((bt_u32 + s * p.btile_bytes) >> 4) & 0x3FFF);
-                const uint32_t a_tap = a_plane + (uint32_t)(dy * p.Zh + dz);
+                const uint32_t a_tap = a_plane + (uint32_t)(dy * p.Zh + dz) * a_row;
                 const uint64_t a_desc0 = a_desc_hi | (uint64_t)(a_tap & 0x3FFF);
                 const uint32_t d_tmem0 = tmem_base + q * (MT * p.N);
                 if (leader) {
@@ -167,7 +174,7 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
                   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                     for (int kk = 0; kk < KSTEPS; ++kk)
-                      tc::umma_bf16(d_tmem0 + mt * p.N, a_desc0 + (uint64_t)(mt * 128 + kk * a_kstep),
+                      tc::umma_bf16(d_tmem0 + mt * p.N, a_desc0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep),
                                     b_desc0 + (uint64_t)(kk * b_kstep), idesc, (uint32_t)((tap | kk) != 0));
                   }
                   tc::umma_commit(&b_empty[s]);
@@ -299,7 +306,7 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
   for (int Yt = 1; Yt <= Y && Yt + 2 <= 256; ++Yt) {
     const int mt = (Yt * p.Zh + 127) / 128;
     if (2 * mt * N > 512 || mt > 4) break;
-    const int rows_alloc = ((mt * 128 + 2 * p.Zh + 2) + 7) / 8 * 8;
+    const int rows_alloc = ((mt * 128 + 2 * p.Zh + 2) + 31) / 32 * 32;  // 2*Cin*rows_alloc is a multiple of 1024 (swizzle atom)
     const uint32_t plane_bytes = (uint32_t)(Cin / 8) * rows_alloc * 16;
     const uint32_t smem = kPlaneSlots * plane_bytes + p.b_stages * p.btile_bytes + 512;
     if (rows_alloc * 16 > 16383 * 16) break;
@@ -316,7 +323,8 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
   }
   if (!found) return false;
   TcPlan &q = best;
-  q.box_bytes = 16u * q.Zh * q.Yh;
+  q.a_swz = Cin <= 64 ? 2 * Cin : 0;
+  q.box_bytes = (q.a_swz ? (uint32_t)q.a_swz : 16u) * q.Zh * q.Yh;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * q.mtiles * N)) cols <<= 1;
   q.tmem_cols = cols;
@@ -393,10 +401,12 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
   const cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)p.B};
   const cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)p.Z * Cin * 2, (cuuint64_t)p.Y * p.Z * Cin * 2,
                               (cuuint64_t)p.X * p.Y * p.Z * Cin * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)(p.a_swz ? Cin : 8), (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle swz = p.a_swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (p.a_swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (p.a_swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(),
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, tc_l2_promo(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled failed with %d", (int)r);
   const int grid = (int)mn<long long>((long long)p.nitems * p.X, (long long)num_sms());
