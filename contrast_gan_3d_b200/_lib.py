@@ -46,6 +46,8 @@ SIGNATURES = {
     "cgan3d_conv_scatter": (_i, [_G, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "cgan3d_conv_wgrad": (_i, [_G, _i, _vp, _vp, _vp, _f, _vp, _sz, _i, _vp]),
     "cgan3d_conv_select": (_i, [_G, _i, _i]),
+    "cgan3d_conv_fuses_bnstats": (_i, [_G, _i, _i]),
+    "cgan3d_conv_bnstats": (_i, [_G, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cgan3d_reflect_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cgan3d_reflect_pad_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cgan3d_bn_stats": (_i, [_vp, _i, _i64, _i, _vp, _vp]),

@@ -68,6 +68,24 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sum 64 per-thread values over the 32 lanes of a warp with a recursive-halving exchange (62 shuffles instead of 64 x 5):
+// afterwards v[0], v[1] of lane l hold the warp totals of channels warp_reduce64_channel(l) and +1.
+__device__ __forceinline__ void warp_reduce64(float (&v)[64], int lane) {
+#pragma unroll
+  for (int half = 32, off = 16; half >= 2; half >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = hi ? v[half + i] : v[i];
+      const float send = hi ? v[i] : v[half + i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+__device__ __forceinline__ int warp_reduce64_channel(int lane) {
+  return ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+}
+
 int num_sms();
 
 template <typename T>

@@ -66,6 +66,26 @@ int cgan3d_conv_gather(const cgan3d_conv_geom *g, int dtype, const void *big, co
   return generic_gather(*g, dtype, big, wpacked, bias, small, as_stream(stream));
 }
 
+int cgan3d_conv_fuses_bnstats(const cgan3d_conv_geom *g, int dtype, int op) {
+  if (!g || check_geom(g, dtype) != 0) return 0;
+  return tc_fuses_bnstats(*g, dtype, op) ? 1 : 0;
+}
+
+int cgan3d_conv_bnstats(const cgan3d_conv_geom *g, int dtype, int op, const void *in, const void *wpacked, void *out,
+                        double *sums, void *workspace, size_t workspace_bytes, void *stream) {
+  int r = check_geom(g, dtype);
+  if (r) return r;
+  CG_CHECK_ARG(in && wpacked && out && sums, "conv_bnstats: NULL pointer");
+  CG_CHECK_ARG(op == 0 || op == 1, "conv_bnstats: op must be 0 (gather) or 1 (scatter)");
+  if (!tc_fuses_bnstats(*g, dtype, op)) return fail(CGAN3D_E_UNSUPPORTED, "conv_bnstats: this layer / device cannot fuse the statistics");
+  const int C = op == 0 ? g->Cs : g->Cb;
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), as_stream(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "conv_bnstats memset");
+  if (g->B == 0) return 0;
+  if (op == 0) return tc_gather(*g, in, wpacked, nullptr, out, workspace, workspace_bytes, as_stream(stream), sums);
+  return tc_scatter(*g, in, wpacked, nullptr, out, workspace, workspace_bytes, as_stream(stream), sums);
+}
+
 int cgan3d_conv_scatter(const cgan3d_conv_geom *g, int dtype, const void *small, const void *wpacked,
                         const float *bias, void *big, void *workspace, size_t workspace_bytes, int impl,
                         void *stream) {

@@ -21,10 +21,13 @@ int reflect_pad_backward(const void *gp, void *gi, int dtype, int B, int X, int 
 // tcgen05 implicit-GEMM path (conv_tc.cu). op: 0 gather, 1 scatter, 2 wgrad.
 bool tc_supported(const cgan3d_conv_geom &g, int dtype, int op);
 size_t tc_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
+// bn_sums (optional, fp64 [2*Cout], zeroed by the caller): the epilogue adds the per-channel sum / sum of squares of the
+// fp32 accumulators (BatchNorm batch statistics fused into the convolution); see tc_fuses_bnstats.
 int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const float *bias, void *small,
-              void *ws, size_t ws_bytes, cudaStream_t st);
+              void *ws, size_t ws_bytes, cudaStream_t st, double *bn_sums = nullptr);
 int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, const float *bias, void *big,
-               void *ws, size_t ws_bytes, cudaStream_t st);
+               void *ws, size_t ws_bytes, cudaStream_t st, double *bn_sums = nullptr);
+bool tc_fuses_bnstats(const cgan3d_conv_geom &g, int dtype, int op);
 int tc_wgrad(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws,
              size_t ws_bytes, cudaStream_t st);
 

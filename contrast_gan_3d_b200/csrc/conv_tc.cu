@@ -66,9 +66,12 @@ struct ItemIter {
   }
 };
 
-template <int KSTEPS, int MT>
+// STATS: the epilogue also accumulates per-channel sum / sum of squares of the fp32 accumulators into bn_sums (fp64 [2*N],
+// N <= 64): the BatchNorm batch statistics of reference model/blocks.py:45 without a separate pass over the output.
+template <int KSTEPS, int MT, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out, const TcPlan p) {
+conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out, const TcPlan p,
+                  double *__restrict__ bn_sums) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *planes = smem;
   uint8_t *bt = planes + (size_t)kPlaneSlots * p.plane_bytes;
@@ -196,6 +199,11 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
   } else {
     // ------------------------------------------------ epilogue (warps 0..3 <-> TMEM lanes 32*warp..)
     uint32_t acc = 0;
+    float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+    }
     int b, z0, zlen, y0, ylen, x0, xlen;
     for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen);) {
       for (int i = 0; i < xlen; ++i, ++acc) {
@@ -208,20 +216,41 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
           const bool valid = oy < ylen && oz < zlen;
           bf16 *dst = out + ((((size_t)b * p.X + (x0 + i)) * p.Y + (y0 + oy)) * p.Z + (z0 + oz)) * p.N;
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (q * p.mtiles + mt) * p.N;
-          for (int c0 = 0; c0 < p.N; c0 += 16) {
-            uint32_t v[16];
-            tc::tmem_ld16(taddr + c0, v);
-            tc::tmem_ld_wait();
-            if (valid) {
-              uint32_t pk[8];
+          auto store_chunk = [&](const uint32_t (&v)[16], int c0) {
+            uint32_t pk[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                pk[j] = *reinterpret_cast<uint32_t *>(&h);
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
+            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          };
+          if constexpr (STATS) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {  // N <= 64: static register indices for the per-channel partial sums
+              if (cc * 16 < p.N) {
+                uint32_t v[16];
+                tc::tmem_ld16(taddr + cc * 16, v);
+                tc::tmem_ld_wait();
+                if (valid) {
+                  store_chunk(v, cc * 16);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float f = __uint_as_float(v[j]);
+                    ssum[cc * 16 + j] += f;
+                    ssq[cc * 16 + j] += f * f;
+                  }
+                }
               }
-              uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
-              d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          } else {
+            for (int c0 = 0; c0 < p.N; c0 += 16) {
+              uint32_t v[16];
+              tc::tmem_ld16(taddr + c0, v);
+              tc::tmem_ld_wait();
+              if (valid) store_chunk(v, c0);
             }
           }
         }
@@ -229,6 +258,17 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
       }
+    }
+    if constexpr (STATS) {  // a thread saw at most a few dozen rows: fp32 partials, fp64 across threads
+      warp_reduce64(ssum, lane);
+      warp_reduce64(ssq, lane);
+      const int ch = warp_reduce64_channel(lane);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (ch + i < p.N) {
+          atomicAdd(&bn_sums[0 + ch + i], (double)ssum[i]);
+          atomicAdd(&bn_sums[p.N + 0 + ch + i], (double)ssq[i]);
+        }
     }
   }
   tc::tc_fence_before();
@@ -289,7 +329,8 @@ CUtensorMapL2promotion tc_l2_promo() {
 bool tc_prog_supported(const cgan3d_conv_geom &g, int dtype, int op);
 size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
 int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
-                cudaStream_t st);
+                cudaStream_t st, double *bn_sums = nullptr);
+bool tc_prog_fuses_bnstats(const cgan3d_conv_geom &g, int scatter);
 
 static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
   if (N % 16 || N > 256 || N < 16) return false;
@@ -384,7 +425,7 @@ size_t tc_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
 }
 
 static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, double *bn_sums) {
   const int Cin = flip ? g.Cs : g.Cb, N = flip ? g.Cb : g.Cs;
   TcPlan p;
   if (!plan_s1(g.B, g.Xb, g.Yb, g.Zb, Cin, N, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: no tiling for this shape");
@@ -410,19 +451,24 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled failed with %d", (int)r);
   const int grid = (int)mn<long long>((long long)p.nitems * p.X, (long long)num_sms());
-  auto launch = [&](auto ks_tag, auto mt_tag) -> int {
+  if (bn_sums && N > 64) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: fused BatchNorm statistics need Cout <= 64");
+  auto launch_s = [&](auto ks_tag, auto mt_tag, auto st_tag) -> int {
     constexpr int KS = decltype(ks_tag)::value;
     constexpr int MT = decltype(mt_tag)::value;
+    constexpr bool ST = decltype(st_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_s1_tc_kernel<KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(conv_s1_tc_kernel<KS, MT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemLimit + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_s1_tc_kernel)");
       attr_set = true;
     }
-    conv_s1_tc_kernel<KS, MT><<<grid, kThreads, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
+    conv_s1_tc_kernel<KS, MT, ST><<<grid, kThreads, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p, bn_sums);
     CG_LAUNCH_CHECK("conv_s1_tc_kernel");
     return 0;
+  };
+  auto launch = [&](auto ks_tag, auto mt_tag) -> int {
+    return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}) : launch_s(ks_tag, mt_tag, std::false_type{});
   };
   auto by_mt = [&](auto ks_tag) -> int {
     switch (p.mtiles) {
@@ -442,22 +488,33 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
   }
 }
 
+bool tc_fuses_bnstats(const cgan3d_conv_geom &g, int dtype, int op) {
+  if (dtype != CGAN3D_BF16 || (op != 0 && op != 1) || !tc_supported(g, dtype, op)) return false;
+  if (thin_supported(g, dtype, op) || d1_supported(g, dtype, op)) return false;
+  const int N = op == 0 ? g.Cs : g.Cb;
+  if (N > 64) return false;
+  if (!s1_shape_ok(g, dtype, op)) return tc_prog_fuses_bnstats(g, op);
+  return true;
+}
+
 int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const float *bias, void *small, void *ws,
-              size_t ws_bytes, cudaStream_t st) {
+              size_t ws_bytes, cudaStream_t st, double *bn_sums) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  if (bn_sums && !tc_fuses_bnstats(g, CGAN3D_BF16, 0)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: this layer cannot fuse the BatchNorm statistics");
   if (thin_supported(g, CGAN3D_BF16, 0)) return thin_run(g, 0, big, wp, small, ws, ws_bytes, st);
   if (d1_supported(g, CGAN3D_BF16, 0)) return d1_run(g, 0, big, wp, small, ws, ws_bytes, st);
-  if (!s1_shape_ok(g, CGAN3D_BF16, 0)) return tc_prog_run(g, 0, big, wp, small, ws, ws_bytes, st);
-  return run_s1(g, 0, big, wp, small, ws, ws_bytes, st);
+  if (!s1_shape_ok(g, CGAN3D_BF16, 0)) return tc_prog_run(g, 0, big, wp, small, ws, ws_bytes, st, bn_sums);
+  return run_s1(g, 0, big, wp, small, ws, ws_bytes, st, bn_sums);
 }
 
 int tc_scatter(const cgan3d_conv_geom &g, const void *small, const void *wp, const float *bias, void *big, void *ws,
-               size_t ws_bytes, cudaStream_t st) {
+               size_t ws_bytes, cudaStream_t st, double *bn_sums) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
+  if (bn_sums && !tc_fuses_bnstats(g, CGAN3D_BF16, 1)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: this layer cannot fuse the BatchNorm statistics");
   if (thin_supported(g, CGAN3D_BF16, 1)) return thin_run(g, 1, small, wp, big, ws, ws_bytes, st);
   if (d1_supported(g, CGAN3D_BF16, 1)) return d1_run(g, 1, small, wp, big, ws, ws_bytes, st);
-  if (!s1_shape_ok(g, CGAN3D_BF16, 1)) return tc_prog_run(g, 1, small, wp, big, ws, ws_bytes, st);
-  return run_s1(g, 1, small, wp, big, ws, ws_bytes, st);
+  if (!s1_shape_ok(g, CGAN3D_BF16, 1)) return tc_prog_run(g, 1, small, wp, big, ws, ws_bytes, st, bn_sums);
+  return run_s1(g, 1, small, wp, big, ws, ws_bytes, st, bn_sums);
 }
 
 int tc_wgrad(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,

@@ -71,10 +71,12 @@ struct ProgPlan {
   int8_t tile_phase_tap[kMaxTaps][8];
 };
 
-template <int KSTEPS, int MT>
+// STATS: the epilogue also accumulates the per-channel sum / sum of squares of the fp32 accumulators (BatchNorm batch
+// statistics, reference model/blocks.py:45) into bn_sums (fp64 [2 * out_pitch], Nout <= 64).
+template <int KSTEPS, int MT, bool STATS>
 __global__ void __launch_bounds__(192, 1)
 conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out,
-                    const __grid_constant__ ProgPlan p) {
+                    const __grid_constant__ ProgPlan p, double *__restrict__ bn_sums) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *bres = smem;                                         // resident filter tiles
   uint8_t *ring = bres + (((size_t)p.nbt * p.btile_bytes + 1023) & ~(size_t)1023);  // activation slab slots (1024-aligned)
@@ -190,6 +192,11 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   } else {
     // ------------------------------------------------ epilogue (warps 0..3 <-> TMEM lanes 32*warp..)
     uint32_t acc = 0;
+    float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+    }
     for (int st = s_begin; st < s_end; ++st, ++acc) {
       int b, z0, zlen, y0, ylen, x;
       decode(st, b, z0, zlen, y0, ylen, x);
@@ -207,20 +214,41 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           const bool valid = gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo;
           bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.out_pitch + p.out_c0;
           const uint32_t taddr = d_base + (uint32_t)(a * p.acc_stride + mt * p.mt_stride);
-          for (int c0 = 0; c0 < p.Nout; c0 += 16) {
-            uint32_t v[16];
-            tc::tmem_ld16(taddr + c0, v);
-            tc::tmem_ld_wait();
-            if (valid) {
-              uint32_t pk[8];
+          auto store_chunk = [&](const uint32_t (&v)[16], int c0) {
+            uint32_t pk[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                pk[j] = *reinterpret_cast<uint32_t *>(&h);
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t *>(&h);
+            }
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
+            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (c0 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          };
+          if constexpr (STATS) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {  // Nout <= 64: static register indices for the per-channel partial sums
+              if (cc * 16 < p.Nout) {
+                uint32_t v[16];
+                tc::tmem_ld16(taddr + cc * 16, v);
+                tc::tmem_ld_wait();
+                if (valid) {
+                  store_chunk(v, cc * 16);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float f = __uint_as_float(v[j]);  // padded columns (>= Nout) hold exact zeros
+                    ssum[cc * 16 + j] += f;
+                    ssq[cc * 16 + j] += f * f;
+                  }
+                }
               }
-              uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
-              d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              if (c0 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          } else {
+            for (int c0 = 0; c0 < p.Nout; c0 += 16) {
+              uint32_t v[16];
+              tc::tmem_ld16(taddr + c0, v);
+              tc::tmem_ld_wait();
+              if (valid) store_chunk(v, c0);
             }
           }
         }
@@ -228,6 +256,17 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+    }
+    if constexpr (STATS) {  // a thread saw at most a few dozen rows: fp32 partials, fp64 across threads
+      warp_reduce64(ssum, lane);
+      warp_reduce64(ssq, lane);
+      const int ch = warp_reduce64_channel(lane);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (ch + i < p.Nout) {
+          atomicAdd(&bn_sums[p.out_c0 + ch + i], (double)ssum[i]);
+          atomicAdd(&bn_sums[p.out_pitch + p.out_c0 + ch + i], (double)ssq[i]);
+        }
     }
   }
   tc::tc_fence_before();
@@ -504,8 +543,13 @@ typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_
 void *tc_encode_fn_ptr();  // conv_tc.cu
 CUtensorMapL2promotion tc_l2_promo();  // conv_tc.cu
 
+bool tc_prog_fuses_bnstats(const cgan3d_conv_geom &g, int scatter) {
+  ProgPlan p;
+  return plan_prog(g, scatter, p) && p.Nout <= 64;
+}
+
 int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
-                cudaStream_t st) {
+                cudaStream_t st, double *bn_sums) {
   ProgPlan p;
   int nsplit = 1;
   if (!plan_prog(g, scatter, p, &nsplit)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: no tiling for this shape");
@@ -534,12 +578,14 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (strided) failed with %d", (int)r);
   const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
   const int grid = (int)mn<long long>(total, (long long)num_sms());
-  auto launch = [&](auto ks_tag, auto mt_tag) -> int {
+  if (bn_sums && p.Nout > 64) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: fused BatchNorm statistics need <= 64 channels per launch");
+  auto launch_s = [&](auto ks_tag, auto mt_tag, auto st_tag) -> int {
     constexpr int KS = decltype(ks_tag)::value;
     constexpr int MT = decltype(mt_tag)::value;
+    constexpr bool ST = decltype(st_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_prog_tc_kernel<KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(conv_prog_tc_kernel<KS, MT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemLimitProg + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_prog_tc_kernel)");
       attr_set = true;
@@ -549,10 +595,13 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
       bf16 *wb = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + part * part_bytes);
       repack_prog_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, scatter, p);
       CG_LAUNCH_CHECK("repack_prog");
-      conv_prog_tc_kernel<KS, MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p);
+      conv_prog_tc_kernel<KS, MT, ST><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p, bn_sums);
       CG_LAUNCH_CHECK("conv_prog_tc_kernel");
     }
     return 0;
+  };
+  auto launch = [&](auto ks_tag, auto mt_tag) -> int {
+    return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}) : launch_s(ks_tag, mt_tag, std::false_type{});
   };
   auto by_mt = [&](auto ks_tag) -> int {
     switch (p.mtiles) {

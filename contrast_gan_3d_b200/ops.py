@@ -141,6 +141,28 @@ def conv_scatter(g: ConvGeom, small, wp, impl=None):
     return big
 
 
+def conv_fuses_bnstats(g: ConvGeom, dtype: torch.dtype, transposed: bool) -> bool:
+    """True when the tcgen05 kernel of this layer can emit the BatchNorm batch statistics from its epilogue."""
+    if _CONV_IMPL == _lib.IMPL_GENERIC or dtype != torch.bfloat16:
+        return False
+    return bool(_lib.lib().cgan3d_conv_fuses_bnstats(C.byref(g), _dt(dtype), _lib.OP_SCATTER if transposed else _lib.OP_GATHER))
+
+
+def conv_bnstats(g: ConvGeom, x, wp, transposed: bool):
+    """conv (gather, or scatter for a transposed module) + per-channel [sum, sum of squares] (fp64 [2*Cout]) in one launch."""
+    dt = _dt(x.dtype)
+    op = _lib.OP_SCATTER if transposed else _lib.OP_GATHER
+    if transposed:
+        out = torch.empty((g.B, g.Xb, g.Yb, g.Zb, g.Cb), dtype=x.dtype, device=x.device)
+    else:
+        out = torch.empty((g.B, g.Xs, g.Ys, g.Zs, g.Cs), dtype=x.dtype, device=x.device)
+    sums = torch.empty(2 * out.shape[-1], dtype=torch.float64, device=x.device)
+    ws, n = _workspace(g, dt, op, x.device)
+    with _timed("scatter" if transposed else "gather", g, dt):
+        call("cgan3d_conv_bnstats", C.byref(g), dt, op, _p(x), _p(wp), _p(out), _p(sums), _p(ws), n, _st())
+    return out, sums
+
+
 def conv_wgrad(g: ConvGeom, big, small, impl=None):
     dt = _dt(big.dtype)
     dw = torch.empty((g.Cs, g.Cb, g.k, g.k, g.k), dtype=torch.float32, device=big.device)
@@ -225,15 +247,20 @@ class ConvBlockFn(torch.autograd.Function):
             xin = reflect_pad(xin, spec.pad)
         g, out_sp = spec.geometry(B, (X, Y, Z))
         wp = pack_weights(weight, cfg.dtype)
-        y = conv_scatter(g, xin, wp) if spec.transposed else conv_gather(g, xin, wp)
         n_rows, Co = B * out_sp[0] * out_sp[1] * out_sp[2], spec.cout
         dt = _dt(cfg.dtype)
+        sums = None
+        if gamma is not None and cfg.training and conv_fuses_bnstats(g, cfg.dtype, spec.transposed):
+            y, sums = conv_bnstats(g, xin, wp, spec.transposed)  # batch statistics from the conv epilogue
+        else:
+            y = conv_scatter(g, xin, wp) if spec.transposed else conv_gather(g, xin, wp)
         mi = None
         if gamma is not None:
             mi = torch.empty(2 * Co, dtype=torch.float32, device=x.device)
             if cfg.training:
-                sums = torch.empty(2 * Co, dtype=torch.float64, device=x.device)
-                call("cgan3d_bn_stats", _p(y), dt, n_rows, Co, _p(sums), _st())
+                if sums is None:
+                    sums = torch.empty(2 * Co, dtype=torch.float64, device=x.device)
+                    call("cgan3d_bn_stats", _p(y), dt, n_rows, Co, _p(sums), _st())
                 call("cgan3d_bn_finalize", _p(sums), n_rows, Co, cfg.eps, cfg.momentum, _p(mi), _p(running_mean),
                      _p(running_var), _p(nbt), _st())
             else:

@@ -90,6 +90,15 @@ int cgan3d_conv_scatter(const cgan3d_conv_geom *g, int dtype, const void *small,
                         void *stream);
 int cgan3d_conv_wgrad(const cgan3d_conv_geom *g, int dtype, const void *big, const void *small, float *dw,
                       float beta, void *workspace, size_t workspace_bytes, int impl, void *stream);
+/* Convolution + BatchNorm batch statistics in one launch (tcgen05 path only): same result in `out` as conv_gather
+ * (op 0, in = big side) / conv_scatter (op 1, in = small side) without bias, and sums[0..C) = sum, sums[C..2C) = sum of
+ * squares over all output voxels of each output channel (fp64, taken from the fp32 accumulators before the storage
+ * rounding).  Replaces aten::convolution + the statistics half of aten::native_batch_norm (reference
+ * model/blocks.py:52-53).  cgan3d_conv_fuses_bnstats returns 1 when the layer supports it on this device; otherwise
+ * call conv_gather / conv_scatter followed by cgan3d_bn_stats.                                                        */
+int cgan3d_conv_fuses_bnstats(const cgan3d_conv_geom *g, int dtype, int op);
+int cgan3d_conv_bnstats(const cgan3d_conv_geom *g, int dtype, int op, const void *in, const void *wpacked, void *out,
+                        double *sums, void *workspace, size_t workspace_bytes, void *stream);
 /* which implementation `impl=0` would choose: 1 generic, 2 tcgen05 */
 int cgan3d_conv_select(const cgan3d_conv_geom *g, int dtype, int op);
 

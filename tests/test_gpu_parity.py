@@ -617,3 +617,31 @@ def test_full_size_layers_tcgen05_vs_generic():
         assert bool((d <= 2 ** -7 * y_gen.abs() + 1e-3).all()), f"{cin}->{cout} k{k} s{s}: {d.max().item()}"
         y2 = f(x * 2, _lib.IMPL_TC).float()
         assert torch.equal(y2, 2 * y_tc), f"{cin}->{cout} k{k} s{s}: linearity"
+
+
+@pytest.mark.parametrize("case", [("s1_64", False, 64, 64, 3, 1, 0, 2, (9, 10, 12)), ("s1_32_16", False, 32, 16, 3, 1, 0, 1, (6, 13, 11)),
+                                  ("down", False, 16, 32, 3, 2, 0, 2, (12, 10, 16)), ("critic_mid", False, 8, 16, 4, 2, 0, 2, (12, 16, 8)),
+                                  ("up", True, 32, 16, 3, 2, 1, 2, (6, 5, 8)), ("critic_mid2", False, 32, 64, 4, 2, 0, 1, (16, 16, 16))],
+                         ids=lambda c: c[0])
+def test_conv_with_fused_batchnorm_statistics(case):
+    """cgan3d_conv_bnstats: identical output to the plain tcgen05 conv, and per-channel sum / sum of squares equal to those of
+    the fp32 ATen result (they are taken from the fp32 accumulators, before the bf16 storage rounding)."""
+    _lib, ops = _ops()
+    name, tr, cin, cout, k, s, op, B, sp = case
+    gen = torch.Generator().manual_seed(len(name))
+    x = torch.randn((B, cin, *sp), generator=gen).bfloat16().float()
+    wshape = (cin, cout, k, k, k) if tr else (cout, cin, k, k, k)
+    w = (torch.randn(wshape, generator=gen) / (cin * k ** 3) ** 0.5).bfloat16().float()
+    y = F.conv_transpose3d(x, w, stride=s, padding=1, output_padding=op) if tr else F.conv3d(x, w, stride=s, padding=1)
+    spec = ops.ConvSpec(transposed=tr, cin=cin, cout=cout, k=k, stride=s, pad=1, out_pad=op)
+    g, _ = spec.geometry(B, sp)
+    assert ops.conv_fuses_bnstats(g, torch.bfloat16, tr), "this layer should fuse its BatchNorm statistics"
+    xd = cl(x).to(DEV, torch.bfloat16)
+    wp = ops.pack_weights(w.to(DEV), torch.bfloat16)
+    plain = ops.conv_scatter(g, xd, wp, impl=_lib.IMPL_TC) if tr else ops.conv_gather(g, xd, wp, impl=_lib.IMPL_TC)
+    fused, sums = ops.conv_bnstats(g, xd, wp, tr)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, plain)
+    yc = y.double().permute(1, 0, 2, 3, 4).reshape(cout, -1)
+    ref = torch.cat([yc.sum(1), (yc * yc).sum(1)])
+    assert_close32(sums, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()), msg="fused statistics")
