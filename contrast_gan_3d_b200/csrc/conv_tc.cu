@@ -380,7 +380,8 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
 bool thin_supported(const cgan3d_conv_geom &g, int dtype, int op);
 size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op);
 int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
-             cudaStream_t st);
+             cudaStream_t st, double *bn_sums = nullptr);
+bool thin_fuses_bnstats(const cgan3d_conv_geom &g, int op);
 int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
                    cudaStream_t st);
 
@@ -490,7 +491,8 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
 
 bool tc_fuses_bnstats(const cgan3d_conv_geom &g, int dtype, int op) {
   if (dtype != CGAN3D_BF16 || (op != 0 && op != 1) || !tc_supported(g, dtype, op)) return false;
-  if (thin_supported(g, dtype, op) || d1_supported(g, dtype, op)) return false;
+  if (thin_supported(g, dtype, op)) return thin_fuses_bnstats(g, op);
+  if (d1_supported(g, dtype, op)) return false;
   const int N = op == 0 ? g.Cs : g.Cb;
   if (N > 64) return false;
   if (!s1_shape_ok(g, dtype, op)) return tc_prog_fuses_bnstats(g, op);
@@ -501,7 +503,7 @@ int tc_gather(const cgan3d_conv_geom &g, const void *big, const void *wp, const 
               size_t ws_bytes, cudaStream_t st, double *bn_sums) {
   if (bias) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: bias is applied by the bias_act pass");
   if (bn_sums && !tc_fuses_bnstats(g, CGAN3D_BF16, 0)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: this layer cannot fuse the BatchNorm statistics");
-  if (thin_supported(g, CGAN3D_BF16, 0)) return thin_run(g, 0, big, wp, small, ws, ws_bytes, st);
+  if (thin_supported(g, CGAN3D_BF16, 0)) return thin_run(g, 0, big, wp, small, ws, ws_bytes, st, bn_sums);
   if (d1_supported(g, CGAN3D_BF16, 0)) return d1_run(g, 0, big, wp, small, ws, ws_bytes, st);
   if (!s1_shape_ok(g, CGAN3D_BF16, 0)) return tc_prog_run(g, 0, big, wp, small, ws, ws_bytes, st, bn_sums);
   return run_s1(g, 0, big, wp, small, ws, ws_bytes, st, bn_sums);

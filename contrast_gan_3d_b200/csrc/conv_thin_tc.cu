@@ -39,10 +39,10 @@ struct ThinAPlan {
   int debug;
 };
 
-template <int MT>
+template <int MT, bool STATS>
 __global__ void __launch_bounds__(192, 1)
 conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wT, bf16 *__restrict__ out,
-                   const __grid_constant__ ThinAPlan p) {
+                   const __grid_constant__ ThinAPlan p, double *__restrict__ bn_sums) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *bres = smem;                                    // 49 resident Toeplitz tiles
   uint8_t *ring = bres + kTapTilesA * kTileBytesA;         // slab slots
@@ -137,6 +137,11 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
     }
   } else {
     uint32_t e = 0;
+    float ssum[STATS ? 16 : 1], ssq[STATS ? 16 : 1];  // per-channel BatchNorm partial sums of this thread's rows
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+    }
     for (int it = i_begin; it < i_end; ++it, ++e) {
       int b, x0, xlen, y0, ylen, z0;
       decode(it, b, x0, xlen, y0, ylen, z0);
@@ -165,12 +170,27 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
             uint4 *d4 = reinterpret_cast<uint4 *>(dst + zo * 16);
             d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if constexpr (STATS) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float f = __uint_as_float(v[j]);
+                ssum[j] += f;
+                ssq[j] += f * f;
+              }
+            }
           }
         }
       }
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+    }
+    if constexpr (STATS) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = warp_sum(ssum[j]), b2 = warp_sum(ssq[j]);
+        if (lane == 0) { atomicAdd(&bn_sums[j], (double)a); atomicAdd(&bn_sums[16 + j], (double)b2); }
+      }
     }
   }
   tc::tc_fence_before();
@@ -774,7 +794,7 @@ size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
 }
 
 static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      cudaStream_t st, double *bn_sums) {
   ThinAPlan p;
   if (!plan_thin_a(g, op, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: shape not supported");
   if (const char *dbg = getenv("CGAN3D_THIN_DEBUG")) p.debug = atoi(dbg);
@@ -799,17 +819,21 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   if (r) return r;
   const long long total = (long long)p.B * p.nxt * p.nyt * p.nzb;
   const int grid = (int)mn<long long>(total, (long long)num_sms());
-  auto launch = [&](auto mt_tag) -> int {
+  auto launch_s = [&](auto mt_tag, auto st_tag) -> int {
     constexpr int MT = decltype(mt_tag)::value;
+    constexpr bool ST = decltype(st_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv7_c1_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
+      cudaError_t e = cudaFuncSetAttribute(conv7_c1_tc_kernel<MT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv7_c1_tc_kernel)");
       attr_set = true;
     }
-    conv7_c1_tc_kernel<MT><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p);
+    conv7_c1_tc_kernel<MT, ST><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p, bn_sums);
     CG_LAUNCH_CHECK("conv7_c1_tc_kernel");
     return 0;
+  };
+  auto launch = [&](auto mt_tag) -> int {
+    return bn_sums ? launch_s(mt_tag, std::true_type{}) : launch_s(mt_tag, std::false_type{});
   };
   switch (p.mtiles) {
     case 1: return launch(std::integral_constant<int, 1>{});
@@ -942,10 +966,13 @@ int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small
   return 0;
 }
 
+bool thin_fuses_bnstats(const cgan3d_conv_geom &g, int op) { return op == 0 && thin_a_shape(g, 0); }
+
 int thin_run(const cgan3d_conv_geom &g, int op, const void *in, const void *wp, void *outp, void *ws, size_t ws_bytes,
-             cudaStream_t st) {
+             cudaStream_t st, double *bn_sums) {
+  if (bn_sums && !thin_fuses_bnstats(g, op)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: this op cannot fuse the BatchNorm statistics");
   if ((op == 0 || op == 1) && thin_b_shape(g, op)) return run_thin_b(g, op, in, wp, outp, ws, ws_bytes, st);
-  if (op == 0 || op == 1) return run_thin_a(g, op, in, wp, outp, ws, ws_bytes, st);
+  if (op == 0 || op == 1) return run_thin_a(g, op, in, wp, outp, ws, ws_bytes, st, bn_sums);
   return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv: op %d not built", op);
 }
 

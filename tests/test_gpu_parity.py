@@ -619,7 +619,7 @@ def test_full_size_layers_tcgen05_vs_generic():
         assert torch.equal(y2, 2 * y_tc), f"{cin}->{cout} k{k} s{s}: linearity"
 
 
-@pytest.mark.parametrize("case", [("s1_64", False, 64, 64, 3, 1, 0, 2, (9, 10, 12)), ("s1_32_16", False, 32, 16, 3, 1, 0, 1, (6, 13, 11)),
+@pytest.mark.parametrize("case", [("first7", False, 1, 16, 7, 1, 0, 2, (12, 20, 15)), ("s1_64", False, 64, 64, 3, 1, 0, 2, (9, 10, 12)), ("s1_32_16", False, 32, 16, 3, 1, 0, 1, (6, 13, 11)),
                                   ("down", False, 16, 32, 3, 2, 0, 2, (12, 10, 16)), ("critic_mid", False, 8, 16, 4, 2, 0, 2, (12, 16, 8)),
                                   ("up", True, 32, 16, 3, 2, 1, 2, (6, 5, 8)), ("critic_mid2", False, 32, 64, 4, 2, 0, 1, (16, 16, 16))],
                          ids=lambda c: c[0])
@@ -632,8 +632,9 @@ def test_conv_with_fused_batchnorm_statistics(case):
     x = torch.randn((B, cin, *sp), generator=gen).bfloat16().float()
     wshape = (cin, cout, k, k, k) if tr else (cout, cin, k, k, k)
     w = (torch.randn(wshape, generator=gen) / (cin * k ** 3) ** 0.5).bfloat16().float()
-    y = F.conv_transpose3d(x, w, stride=s, padding=1, output_padding=op) if tr else F.conv3d(x, w, stride=s, padding=1)
-    spec = ops.ConvSpec(transposed=tr, cin=cin, cout=cout, k=k, stride=s, pad=1, out_pad=op)
+    pad = 0 if k == 7 else 1
+    y = F.conv_transpose3d(x, w, stride=s, padding=pad, output_padding=op) if tr else F.conv3d(x, w, stride=s, padding=pad)
+    spec = ops.ConvSpec(transposed=tr, cin=cin, cout=cout, k=k, stride=s, pad=pad, out_pad=op)
     g, _ = spec.geometry(B, sp)
     assert ops.conv_fuses_bnstats(g, torch.bfloat16, tr), "this layer should fuse its BatchNorm statistics"
     xd = cl(x).to(DEV, torch.bfloat16)
