@@ -211,12 +211,21 @@ __global__ void d1_toeplitz_kernel(const bf16 *__restrict__ wp, bf16 *__restrict
 }
 
 // copy[row][c] = in[row][c - 1] (0 outside), c in [0, Zc): makes every z window start (2*z0 - 1) a multiple of 8 columns
-__global__ void d1_shift_copy_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc) {
-  const long long total = rows * Zc;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / Zc;
-    const int z = (int)(i - r * Zc) - 1;
-    out[i] = (z >= 0 && z < Z) ? in[r * Z + z] : __float2bfloat16_rn(0.f);
+__global__ void __launch_bounds__(128)
+d1_shift_copy_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc) {
+  extern __shared__ uint16_t line[];  // line[c] = in[c - 1]
+  const long long r = blockIdx.x;
+  const uint16_t *src = reinterpret_cast<const uint16_t *>(in) + r * Z;
+  for (int i = threadIdx.x; i < Zc; i += blockDim.x) {
+    const int z = i - 1;
+    line[i] = (z >= 0 && z < Z) ? src[z] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < (Zc >> 3); j += blockDim.x) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (uint32_t)line[j * 8 + 2 * k] | ((uint32_t)line[j * 8 + 2 * k + 1] << 16);
+    reinterpret_cast<uint4 *>(out + r * Zc)[j] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -275,7 +284,7 @@ static int run_d1_gather(const cgan3d_conv_geom &g, const void *in, const void *
   CG_LAUNCH_CHECK("d1_toeplitz");
   bf16 *cp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kD1Tiles * kD1TileBytes + 256);
   const long long rows = (long long)p.B * p.Xi * p.Yi;
-  d1_shift_copy_kernel<<<num_sms() * 8, 256, 0, st>>>(reinterpret_cast<const bf16 *>(in), cp, rows, p.Zi, p.Zc);
+  d1_shift_copy_kernel<<<(unsigned)rows, 128, (size_t)p.Zc * 2, st>>>(reinterpret_cast<const bf16 *>(in), cp, rows, p.Zi, p.Zc);
   CG_LAUNCH_CHECK("d1_shift_copy");
   CUtensorMap tm;
   const cuuint64_t zc = (cuuint64_t)p.Zc;

@@ -795,22 +795,19 @@ __global__ void reflect_pad_bwd_kernel(const T *__restrict__ gp, T *__restrict__
   }
 }
 
-// 16-byte-chunk versions (C * sizeof(T) % 16 == 0): one thread moves VEC = 16 / sizeof(T) channels of one voxel
-template <typename T>
-__global__ void reflect_pad_vec_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int B, int X, int Y, int Z, int cpv,
-                                       int p) {
-  const int Xp = X + 2 * p, Yp = Y + 2 * p, Zp = Z + 2 * p;
-  const int64_t total = (int64_t)B * Xp * Yp * Zp * cpv;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t line = i / (Zp * cpv);  // (b, x, y)
-    const int rem = (int)(i - line * (Zp * cpv));
-    const int z = rem / cpv, c = rem - z * cpv;
-    const int y = (int)(line % Yp);
-    const int64_t t = line / Yp;
-    const int x = (int)(t % Xp);
-    const int b = (int)(t / Xp);
-    const int sx = reflect_idx(x - p, X), sy = reflect_idx(y - p, Y), sz = reflect_idx(z - p, Z);
-    out[i] = in[((((int64_t)b * X + sx) * Y + sy) * Z + sz) * cpv + c];
+// One block per padded (b, x, y) line: the mirrored x / y sources are block-uniform, a thread only mirrors z.
+// U = unit moved per thread: uint4 (16-byte chunks, C * sizeof(T) % 16 == 0) or the scalar element type.
+template <typename U>
+__global__ void __launch_bounds__(256)
+reflect_pad_line_kernel(const U *__restrict__ in, U *__restrict__ out, int X, int Y, int Z, int upv, int p) {
+  const int Yp = Y + 2 * p, Zp = Z + 2 * p, Xp = X + 2 * p;
+  const int y = blockIdx.x, x = blockIdx.y, b = blockIdx.z;
+  const int sx = reflect_idx(x - p, X), sy = reflect_idx(y - p, Y);
+  const U *src = in + (((int64_t)b * X + sx) * Y + sy) * (int64_t)Z * upv;
+  U *dst = out + (((int64_t)b * Xp + x) * Yp + y) * (int64_t)Zp * upv;
+  for (int i = threadIdx.x; i < Zp * upv; i += blockDim.x) {
+    const int z = i / upv, c = i - z * upv;
+    dst[i] = src[reflect_idx(z - p, Z) * upv + c];
   }
 }
 
@@ -853,15 +850,16 @@ reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *__restrict__ gi,
 
 int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z, int C, int pad, cudaStream_t st) {
   const int esz = dtype == CGAN3D_F32 ? 4 : 2;
-  if ((C * esz) % 16 == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15)) {
-    const int cpv = C * esz / 16;
-    const int64_t tv = (int64_t)B * (X + 2 * pad) * (Y + 2 * pad) * (Z + 2 * pad) * cpv;
-    const int bl = (int)mn<int64_t>((tv + 255) / 256, (int64_t)num_sms() * 16);
-    if (dtype == CGAN3D_F32)
-      reflect_pad_vec_kernel<float><<<bl, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, B, X, Y, Z, cpv, pad);
+  const int Xp = X + 2 * pad, Yp = Y + 2 * pad;
+  if (Xp <= 65535 && B <= 65535) {
+    const dim3 grid((unsigned)Yp, (unsigned)Xp, (unsigned)B);
+    if ((C * esz) % 16 == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15))
+      reflect_pad_line_kernel<uint4><<<grid, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, X, Y, Z, C * esz / 16, pad);
+    else if (dtype == CGAN3D_F32)
+      reflect_pad_line_kernel<float><<<grid, 256, 0, st>>>((const float *)in, (float *)out, X, Y, Z, C, pad);
     else
-      reflect_pad_vec_kernel<__nv_bfloat16><<<bl, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, B, X, Y, Z, cpv, pad);
-    CG_LAUNCH_CHECK("reflect_pad_vec");
+      reflect_pad_line_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, X, Y, Z, C, pad);
+    CG_LAUNCH_CHECK("reflect_pad(line)");
     return 0;
   }
   const int64_t total = (int64_t)B * (X + 2 * pad) * (Y + 2 * pad) * (Z + 2 * pad) * C;

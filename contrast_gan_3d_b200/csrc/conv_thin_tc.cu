@@ -221,18 +221,28 @@ __global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict_
 // TMA needs 16-byte aligned row pitches AND a 16-byte aligned start coordinate along the contiguous axis, but the z
 // windows start every 4 voxels.  Two z-shifted, zero-margined copies of the 1-channel input make every window start
 // aligned in one of them:  copy[s][row][c] = in[row][c - 8 + shift_s]  (0 outside), c in [0, Zc), Zc % 8 == 0.
-__global__ void shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc, int s0,
-                                      int s1) {
-  const long long per = rows * Zc, total = 2 * per;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cp = i >= per;
-    const long long j = i - cp * per;
-    const long long r = j / Zc;
-    const int z = (int)(j - r * Zc) - 8 + (cp ? s1 : s0);
-    out[i] = (z >= 0 && z < Z) ? in[r * Z + z] : __float2bfloat16_rn(0.f);
+// One block per input line: the line is staged in shared memory (with zero margins) and written out as 16-byte chunks.
+__global__ void __launch_bounds__(128)
+shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc, int s0, int s1) {
+  extern __shared__ uint16_t line[];  // line[8 + z] = in[z], zeros in [0, 8) and beyond Z
+  const long long r = blockIdx.x;
+  const uint16_t *src = reinterpret_cast<const uint16_t *>(in) + r * Z;
+  const int n = Zc + 24;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int z = i - 8;
+    line[i] = (z >= 0 && z < Z) ? src[z] : (uint16_t)0;
+  }
+  __syncthreads();
+  const int chunks = Zc >> 3;
+  for (int i = threadIdx.x; i < 2 * chunks; i += blockDim.x) {
+    const int cp = i >= chunks, j = i - cp * chunks;
+    const int base = j * 8 + (cp ? s1 : s0);  // out[c] = in[c - 8 + s] = line[c + s]
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (uint32_t)line[base + 2 * k] | ((uint32_t)line[base + 2 * k + 1] << 16);
+    reinterpret_cast<uint4 *>(out + ((long long)cp * rows + r) * Zc)[j] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 //  (B) 16 -> 1 channels (fprop of `last_conv`, dgrad of `first`): filter x- AND z-offsets STACKED ON N.
@@ -630,27 +640,24 @@ wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
 }
 
 // E[b][xe][ye][z][j] = Q1[b][xe - P][ye - P][z + j - P]  (0 outside Q1), j = 0..7: one 16-byte row per (xe, ye, z)
-__global__ void expand_z_kernel(const bf16 *__restrict__ q, bf16 *__restrict__ e, int B, int Xq, int Yq, int Zq, int Xe, int Ye, int Ze,
-                                int P) {
-  const long long total = (long long)B * Xe * Ye * Ze;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int z = (int)(t % Ze); t /= Ze;
-    const int ye = (int)(t % Ye); t /= Ye;
-    const int xe = (int)(t % Xe);
-    const int b = (int)(t / Xe);
-    const int xq = xe - P, yq = ye - P;
-    uint32_t pk[4] = {0, 0, 0, 0};
-    if (xq >= 0 && xq < Xq && yq >= 0 && yq < Yq) {
-      const bf16 *line = q + (((size_t)b * Xq + xq) * Yq + yq) * Zq;
+__global__ void __launch_bounds__(128)
+expand_z_kernel(const bf16 *__restrict__ q, bf16 *__restrict__ e, int B, int Xq, int Yq, int Zq, int Xe, int Ye, int Ze, int P) {
+  extern __shared__ uint16_t line[];  // line[i] = Q1 line value at z = i - P (0 outside), i in [0, Ze + 8)
+  const int ye = blockIdx.x, xe = blockIdx.y, b = blockIdx.z;
+  const int xq = xe - P, yq = ye - P;
+  const bool inside = xq >= 0 && xq < Xq && yq >= 0 && yq < Yq;
+  const uint16_t *src = reinterpret_cast<const uint16_t *>(q) + (((size_t)b * Xq + (inside ? xq : 0)) * Yq + (inside ? yq : 0)) * Zq;
+  for (int i = threadIdx.x; i < Ze + 8; i += blockDim.x) {
+    const int z = i - P;
+    line[i] = (inside && z >= 0 && z < Zq) ? src[z] : (uint16_t)0;
+  }
+  __syncthreads();
+  uint4 *dst = reinterpret_cast<uint4 *>(e) + (((size_t)b * Xe + xe) * Ye + ye) * (size_t)Ze;
+  for (int z = threadIdx.x; z < Ze; z += blockDim.x) {
+    uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int zq = z + j - P;
-        const uint16_t h = (zq >= 0 && zq < Zq) ? __bfloat16_as_ushort(line[zq]) : (uint16_t)0;
-        pk[j >> 1] |= (uint32_t)h << ((j & 1) * 16);
-      }
-    }
-    reinterpret_cast<uint4 *>(e)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    for (int k = 0; k < 4; ++k) w[k] = (uint32_t)line[z + 2 * k] | ((uint32_t)line[z + 2 * k + 1] << 16);
+    dst[z] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -807,8 +814,8 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   CG_LAUNCH_CHECK("toeplitz_a");
   bf16 *rp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kTapTilesA * kTileBytesA + 256);
   const long long rows = (long long)p.B * p.Xi * p.Yi;
-  shifted_copies_kernel<<<num_sms() * 8, 256, 0, st>>>(reinterpret_cast<const bf16 *>(in), rp, rows, p.Zi, p.Zc, p.zshift[0],
-                                                      p.zshift[1]);
+  shifted_copies_kernel<<<(unsigned)rows, 128, (size_t)(p.Zc + 24) * 2, st>>>(reinterpret_cast<const bf16 *>(in), rp, rows, p.Zi, p.Zc,
+                                                                             p.zshift[0], p.zshift[1]);
   CG_LAUNCH_CHECK("shifted_copies");
   CUtensorMap tm;
   const cuuint64_t zc = (cuuint64_t)p.Zc;
@@ -936,7 +943,9 @@ int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small
     if (e != cudaSuccess) return cuda_fail(e, "tcgen05 thin wgrad memset");
   }
   bf16 *E = reinterpret_cast<bf16 *>(ws);
-  expand_z_kernel<<<num_sms() * 16, 256, 0, st>>>(reinterpret_cast<const bf16 *>(q1), E, p.B, Xq, Yq, Zq, p.Xe, p.Ye, p.Zs, p.P);
+  if (p.Xe > 65535 || p.B > 65535) return fail(CGAN3D_E_SHAPE, "tcgen05 thin wgrad: extent too large");
+  expand_z_kernel<<<dim3((unsigned)p.Ye, (unsigned)p.Xe, (unsigned)p.B), 128, (size_t)(p.Zs + 8) * 2, st>>>(
+      reinterpret_cast<const bf16 *>(q1), E, p.B, Xq, Yq, Zq, p.Xe, p.Ye, p.Zs, p.P);
   CG_LAUNCH_CHECK("expand_z");
   CUtensorMap tmE, tmS;
   {
