@@ -13,10 +13,14 @@
 //     taps per MMA.
 //   * The 4 parity-class sub-slabs of X are adjacent N blocks: ONE MMA with N = 4*Cb covers every class at a row shift.
 //     2 (Cs = 32) or 4 (Cs = 64) MMAs per K block and dx instead of 6-9.
+//   * Stride 1 (the generator's ResNet layers, Cs = 64): the N blocks are the SAME X halo slab one / two voxels later
+//     (LBO = one row), so one MMA with N = 3*Cb yields the three dz taps of a (dx, dy) pair: 3 MMAs per K block and dx
+//     instead of 9.
 //   * A CTA owns one dx (filter x-offset) and a contiguous range of (b, y-slab, x) steps; split-K over CTAs, fp32 atomics.
 #include "common.cuh"
 #include "conv_internal.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace cg {
 
@@ -30,10 +34,14 @@ struct WsPlan {
   int Zh, Yt, Yh, nslabs;
   int kpad, rowsA, rowsB;
   int nblkA;       // M blocks: 1 (Cs == 64) or 2 (Cs == 32: block 1 = the slab one row later)
+  int stride;      // 2: N blocks = the 4 parity-class sub-slabs; 1: N blocks = 3 row-shifted views of one halo slab
+  int nsrc, nblkB; // TMA sub-slabs of X per step / N blocks per MMA
+  uint32_t lboB;   // bytes between N blocks
   int nmma, stages, steps_per_dx;
   uint16_t row_shift[kMaxWsMma];
-  int8_t acc_tap[kMaxWsMma][2][4];  // (dy*k+dz) of [MMA][M block][parity source]; -1 = discard
+  int8_t acc_tap[kMaxWsMma][2][4];  // (dy*k+dz) of [MMA][M block][N block]; -1 = discard
   uint32_t rowbytesA, rowbytesB, a_bytes, srcB_bytes, stage_bytes, boxA_bytes, boxB_bytes, smem_bytes, tmem_cols;
+  int debug;
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -70,7 +78,7 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
   const int dx = blockIdx.x % p.k;
   const int grp = blockIdx.x / p.k, ngrp = (gridDim.x - dx + p.k - 1) / p.k;
   const int s_begin = (int)((long long)p.steps_per_dx * grp / ngrp), s_end = (int)((long long)p.steps_per_dx * (grp + 1) / ngrp);
-  const int ncol = 4 * p.Cb;
+  const int ncol = p.nblkB * p.Cb;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -84,19 +92,23 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
         const int y0 = sl * p.Yt;
         const uint32_t s = n % p.stages, use = n / p.stages;
         if (use > 0) tc::mbar_wait(&empty[s], (use - 1) & 1);
-        tc::mbar_expect_tx(&full[s], p.boxA_bytes + 4 * p.boxB_bytes);
+        tc::mbar_expect_tx(&full[s], p.boxA_bytes + p.nsrc * p.boxB_bytes);
         uint8_t *a = stage_mem + (size_t)s * p.stage_bytes, *bb = a + p.a_bytes;
         // dY slab; with two M blocks it starts one voxel early so that block 0 = dY[z-1] and block 1 (next row) = dY[z]
         tc::tma_load_5d(a, &tmY, &full[s], 0, p.nblkA == 2 ? -1 : 0, y0, x, b);
-        for (int src = 0; src < 4; ++src)  // parity class (q, r) = (src >> 1, src & 1): sub-slab starts at 2*o - class
-          tc::tma_load_5d(bb + (size_t)src * p.srcB_bytes, &tmX, &full[s], 0, -(src & 1), 2 * y0 - (src >> 1), 2 * x + dx - 1, b);
+        if (p.stride == 2) {
+          for (int src = 0; src < 4; ++src)  // parity class (q, r) = (src >> 1, src & 1): sub-slab starts at 2*o - class
+            tc::tma_load_5d(bb + (size_t)src * p.srcB_bytes, &tmX, &full[s], 0, -(src & 1), 2 * y0 - (src >> 1), 2 * x + dx - 1, b);
+        } else {
+          tc::tma_load_5d(bb, &tmX, &full[s], 0, -1, y0 - 1, x + dx - 1, b);  // halo slab of plane x + dx - 1
+        }
       }
     }
   } else if (warp == 5) {
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::make_idesc_bf16(64, ncol, 1, 1);
     const uint64_t a_hi = tc::make_desc_sw_mn(0, p.rowbytesA, 8 * p.rowbytesA, p.rowbytesA);
-    const uint64_t b_hi = tc::make_desc_sw_mn(0, p.srcB_bytes, 8 * p.rowbytesB, p.rowbytesB);
+    const uint64_t b_hi = tc::make_desc_sw_mn(0, p.lboB, 8 * p.rowbytesB, p.rowbytesB);
     const uint32_t stage0 = tc::smem_u32(stage_mem);
     const int kblocks = p.kpad >> 4;
     const uint32_t a_step = (16 * p.rowbytesA) >> 4, b_step = (16 * p.rowbytesB) >> 4;
@@ -143,7 +155,7 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
             const int nn = c0 + c;
             const int src = nn / p.Cb, cb = nn - src * p.Cb;
             const int t2 = p.acc_tap[j][blk][src];
-            if (t2 >= 0) atomicAdd(&dw[((size_t)cs * p.Cb + cb) * p.taps + dx * p.k * p.k + t2], __uint_as_float(v[c]));
+            if (t2 >= 0 && !p.debug) atomicAdd(&dw[((size_t)cs * p.Cb + cb) * p.taps + dx * p.k * p.k + t2], __uint_as_float(v[c]));
           }
         }
       }
@@ -155,54 +167,82 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
 }
 
 static bool plan_ws(const cgan3d_conv_geom &g, WsPlan &p) {
-  const int k = g.k;
-  if (g.stride != 2 || g.pad != 1 || (k != 3 && k != 4)) return false;
-  if (g.Cs != 32 && g.Cs != 64) return false;
-  if (g.Cb != 16 && g.Cb != 32) return false;
+  const int k = g.k, s = g.stride;
+  if (g.pad != 1) return false;
+  if (s == 2) {
+    if (k != 3 && k != 4) return false;
+    if (g.Cs != 32 && g.Cs != 64) return false;
+    if (g.Cb != 16 && g.Cb != 32) return false;
+  } else if (s == 1) {
+    if (k != 3 || g.Cs != 64) return false;
+    if (g.Cb != 16 && g.Cb != 32 && g.Cb != 64) return false;
+    if (g.Xb != g.Xs || g.Yb != g.Ys || g.Zb != g.Zs) return false;
+  } else {
+    return false;
+  }
   p = WsPlan{};
   p.B = g.B; p.X = g.Xs; p.Y = g.Ys; p.Z = g.Zs; p.Cb = g.Cb; p.Cs = g.Cs; p.k = k; p.taps = k * k * k;
-  p.Zh = p.Z + 1;
-  if (2 * (p.Zh - 1) + 1 > 256) return false;
+  p.stride = s;
+  const int halo = s == 1 ? 2 : 1;
+  p.Zh = p.Z + halo;
+  if (s * (p.Zh - 1) + 1 > 256) return false;
   p.nblkA = 64 / g.Cs;
   p.rowbytesA = 2u * g.Cs;
   p.rowbytesB = 2u * g.Cb;
   p.stages = 2;
-  // MMA program: sub-grid shift (sy, sz) in {0,1}^2; tap d has parity class (d-1)&1 and shift (d - 1 + class) / 2
-  auto cls = [](int d) { return (d - 1) & 1; };
-  auto shf = [&](int d) { return (d - 1 + cls(d)) / 2; };
-  auto find = [&](int c, int sh) { for (int d = 0; d < k; ++d) if (cls(d) == c && shf(d) == sh) return d; return -1; };
   int nm = 0;
-  for (int by = 0; by < 2; ++by)
-    for (int bz = 0; bz < 2; bz += p.nblkA) {
-      bool any = false;
-      for (int blk = 0; blk < 2; ++blk)
-        for (int src = 0; src < 4; ++src) {
-          int tap = -1;
-          if (blk < p.nblkA) {
-            // two M blocks: block 0 holds dY[z-1] (z shift bz + 1), block 1 holds dY[z] (z shift bz)
-            const int sz = p.nblkA == 2 ? bz + 1 - blk : bz;
-            const int dy = find(src >> 1, by), dz = find(src & 1, sz);
-            if (dy >= 0 && dz >= 0) tap = dy * k + dz;
+  if (s == 2) {
+    p.nsrc = 4; p.nblkB = 4;
+    // MMA program: sub-grid shift (sy, sz) in {0,1}^2; tap d has parity class (d-1)&1 and shift (d - 1 + class) / 2
+    auto cls = [](int d) { return (d - 1) & 1; };
+    auto shf = [&](int d) { return (d - 1 + cls(d)) / 2; };
+    auto find = [&](int c, int sh) { for (int d = 0; d < k; ++d) if (cls(d) == c && shf(d) == sh) return d; return -1; };
+    for (int by = 0; by < 2; ++by)
+      for (int bz = 0; bz < 2; bz += p.nblkA) {
+        bool any = false;
+        for (int blk = 0; blk < 2; ++blk)
+          for (int src = 0; src < 4; ++src) {
+            int tap = -1;
+            if (blk < p.nblkA) {
+              // two M blocks: block 0 holds dY[z-1] (z shift bz + 1), block 1 holds dY[z] (z shift bz)
+              const int sz = p.nblkA == 2 ? bz + 1 - blk : bz;
+              const int dy = find(src >> 1, by), dz = find(src & 1, sz);
+              if (dy >= 0 && dz >= 0) tap = dy * k + dz;
+            }
+            p.acc_tap[nm][blk][src] = (int8_t)tap;
+            any = any || tap >= 0;
           }
-          p.acc_tap[nm][blk][src] = (int8_t)tap;
-          any = any || tap >= 0;
-        }
-      if (!any) continue;
-      p.row_shift[nm] = (uint16_t)(by * p.Zh + bz);
+        if (!any) continue;
+        p.row_shift[nm] = (uint16_t)(by * p.Zh + bz);
+        ++nm;
+      }
+  } else {
+    p.nsrc = 1; p.nblkB = 3;
+    for (int dy = 0; dy < 3; ++dy) {  // N block dz = the halo slab dz voxels later
+      for (int blk = 0; blk < 2; ++blk)
+        for (int nb = 0; nb < 4; ++nb) p.acc_tap[nm][blk][nb] = (int8_t)((blk == 0 && nb < 3) ? dy * 3 + nb : -1);
+      p.row_shift[nm] = (uint16_t)(dy * p.Zh);
       ++nm;
     }
+  }
   p.nmma = nm;
   const int ngroups = (nm + 1) / 2;
-  if (ngroups * 4 * g.Cb > 512) return false;
+  const int ncol = p.nblkB * g.Cb;
+  if (ngroups * ncol > 512 || ncol > 256) return false;
+  auto sizes = [&](int Yt, int &kpad, int &rowsA, int &rowsB) {
+    kpad = (Yt * p.Zh + 15) / 16 * 16;
+    rowsA = kpad + 8;
+    rowsB = (kpad + halo * p.Zh + halo + 2 + 7) / 8 * 8;
+  };
   bool ok = false;
   for (int Yt = mn(p.Y, 64); Yt >= 1; --Yt) {
-    if (2 * Yt + 1 > 256) continue;
-    const int kpad = (Yt * p.Zh + 15) / 16 * 16;
-    const int rowsA = kpad + 8, rowsB = (kpad + p.Zh + 2 + 7) / 8 * 8;
-    if ((Yt + 1) * p.Zh > rowsB) continue;
+    if (s * (Yt + halo - 1) + 1 > 256) continue;
+    int kpad, rowsA, rowsB;
+    sizes(Yt, kpad, rowsA, rowsB);
+    if ((Yt + halo) * p.Zh > rowsB) continue;
     const uint32_t a_bytes = ((uint32_t)rowsA * p.rowbytesA + 1023) / 1024 * 1024;
     const uint32_t srcB = ((uint32_t)rowsB * p.rowbytesB + 1023) / 1024 * 1024;
-    if ((size_t)p.stages * (a_bytes + 4 * srcB) + 512 > kSmemLimitWs) continue;
+    if ((size_t)p.stages * (a_bytes + p.nsrc * srcB) + 512 > kSmemLimitWs) continue;
     p.Yt = Yt;
     ok = true;
     break;
@@ -210,19 +250,18 @@ static bool plan_ws(const cgan3d_conv_geom &g, WsPlan &p) {
   if (!ok) return false;
   p.nslabs = (p.Y + p.Yt - 1) / p.Yt;
   p.Yt = (p.Y + p.nslabs - 1) / p.nslabs;
-  p.Yh = p.Yt + 1;
-  p.kpad = (p.Yt * p.Zh + 15) / 16 * 16;
-  p.rowsA = p.kpad + 8;
-  p.rowsB = (p.kpad + p.Zh + 2 + 7) / 8 * 8;
+  p.Yh = p.Yt + halo;
+  sizes(p.Yt, p.kpad, p.rowsA, p.rowsB);
   p.a_bytes = ((uint32_t)p.rowsA * p.rowbytesA + 1023) / 1024 * 1024;
   p.srcB_bytes = ((uint32_t)p.rowsB * p.rowbytesB + 1023) / 1024 * 1024;
-  p.stage_bytes = p.a_bytes + 4 * p.srcB_bytes;
+  p.lboB = s == 2 ? p.srcB_bytes : p.rowbytesB;
+  p.stage_bytes = p.a_bytes + p.nsrc * p.srcB_bytes;
   p.boxA_bytes = p.rowbytesA * p.Zh * p.Yt;
   p.boxB_bytes = p.rowbytesB * p.Zh * p.Yh;
   p.smem_bytes = p.stages * p.stage_bytes + 512 + 1024;
   p.steps_per_dx = p.B * p.nslabs * p.X;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(ngroups * 4 * g.Cb)) cols <<= 1;
+  while (cols < (uint32_t)(ngroups * ncol)) cols <<= 1;
   p.tmem_cols = cols;
   return true;
 }
@@ -255,6 +294,7 @@ bool tc_wgrad_s2_supported(const cgan3d_conv_geom &g) {
 int tc_wgrad_s2_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st) {
   WsPlan p;
   if (!plan_ws(g, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided wgrad: shape not supported");
+  if (const char *e = getenv("CGAN3D_WS_DEBUG")) p.debug = atoi(e);
   if ((reinterpret_cast<uintptr_t>(big) & 15) || (reinterpret_cast<uintptr_t>(small) & 15))
     return fail(CGAN3D_E_ARG, "tcgen05 strided wgrad: pointers must be 16-byte aligned");
   if (beta == 0.f) {
@@ -264,7 +304,7 @@ int tc_wgrad_s2_run(const cgan3d_conv_geom &g, const void *big, const void *smal
   CUtensorMap tmY, tmX;
   int r = encode_voxel_map(&tmY, small, g.Cs, g.Zs, g.Ys, g.Xs, g.B, p.Zh, p.Yt, 1);
   if (r) return r;
-  r = encode_voxel_map(&tmX, big, g.Cb, g.Zb, g.Yb, g.Xb, g.B, p.Zh, p.Yh, 2);
+  r = encode_voxel_map(&tmX, big, g.Cb, g.Zb, g.Yb, g.Xb, g.B, p.Zh, p.Yh, g.stride);
   if (r) return r;
   static bool attr_set = false;
   if (!attr_set) {
