@@ -204,53 +204,87 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
       tc::mbar_wait(&tm_full[q], (acc >> 1) & 1);
       tc::tc_fence_after();
       const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(p.nacc * MT * p.N);
-      for (int a = 0; a < p.nacc; ++a) {
+      // one 16-channel chunk of output phase `a`, M-tile `mt`: bf16 store (+ BatchNorm partial sums; cc is static)
+      auto emit = [&](const uint32_t (&v)[16], int a, int mt, auto cc_tag) {
+        constexpr int cc = decltype(cc_tag)::value;
         const int px = (a >> 2) & 1, py = (a >> 1) & 1, pz = a & 1;
         const int ox = p.out_scale * x + px;
-        for (int mt = 0; mt < MT; ++mt) {
-          const int r = mt * 128 + warp * 32 + lane;
-          const int gy = r / p.Zh, gz = r - gy * p.Zh;
-          const int oy = p.out_scale * (y0 + gy) + py, oz = p.out_scale * (z0 + gz) + pz;
-          const bool valid = gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo;
-          bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.out_pitch + p.out_c0;
-          const uint32_t taddr = d_base + (uint32_t)(a * p.acc_stride + mt * p.mt_stride);
-          auto store_chunk = [&](const uint32_t (&v)[16], int c0) {
-            uint32_t pk[8];
+        const int r = mt * 128 + warp * 32 + lane;
+        const int gy = r / p.Zh, gz = r - gy * p.Zh;
+        const int oy = p.out_scale * (y0 + gy) + py, oz = p.out_scale * (z0 + gz) + pz;
+        if (!(gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo)) return;
+        bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.out_pitch + p.out_c0 + cc * 16;
+        uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-              pk[j] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
-            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            if (c0 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          };
-          if constexpr (STATS) {
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          pk[j] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (cc * 16 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if constexpr (STATS) {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {  // Nout <= 64: static register indices for the per-channel partial sums
-              if (cc * 16 < p.Nout) {
-                uint32_t v[16];
-                tc::tmem_ld16(taddr + cc * 16, v);
-                tc::tmem_ld_wait();
-                if (valid) {
-                  store_chunk(v, cc * 16);
+          for (int j = 0; j < 16; ++j) {
+            const float f = __uint_as_float(v[j]);  // padded columns (>= Nout) hold exact zeros
+            ssum[cc * 16 + j] += f;
+            ssq[cc * 16 + j] += f * f;
+          }
+        }
+      };
+      // TMEM loads are issued four at a time before a single wait: a load -> wait -> store chain per chunk left the
+      // epilogue latency-bound (ncu: tensor pipe 32 % active with neither L2 nor DRAM saturated)
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t t_mt = d_base + (uint32_t)(mt * p.mt_stride);
+        if (p.nacc == 1) {  // gather: the (up to) four 16-channel chunks of the single accumulator
+          uint32_t v[4][16];
+          if (0 < p.Nout) tc::tmem_ld16(t_mt + 0, v[0]);
+          if (16 < p.Nout) tc::tmem_ld16(t_mt + 16, v[1]);
+          if (32 < p.Nout) tc::tmem_ld16(t_mt + 32, v[2]);
+          if (48 < p.Nout) tc::tmem_ld16(t_mt + 48, v[3]);
+          tc::tmem_ld_wait();
+          if (0 < p.Nout) emit(v[0], 0, mt, std::integral_constant<int, 0>{});
+          if (16 < p.Nout) emit(v[1], 0, mt, std::integral_constant<int, 1>{});
+          if (32 < p.Nout) emit(v[2], 0, mt, std::integral_constant<int, 2>{});
+          if (48 < p.Nout) emit(v[3], 0, mt, std::integral_constant<int, 3>{});
+          if constexpr (!STATS) {
+            for (int c0 = 64; c0 < p.Nout; c0 += 16) {  // wide layers (no fused statistics): one chunk at a time
+              tc::tmem_ld16(t_mt + c0, v[0]);
+              tc::tmem_ld_wait();
+              const int r = mt * 128 + warp * 32 + lane;
+              const int gy = r / p.Zh, gz = r - gy * p.Zh;
+              if (gy < ylen && gz < zlen && x < p.Xo && y0 + gy < p.Yo && z0 + gz < p.Zo) {
+                bf16 *dst = out + ((((size_t)b * p.Xo + x) * p.Yo + (y0 + gy)) * p.Zo + (z0 + gz)) * p.out_pitch + p.out_c0 + c0;
+                uint32_t pk[8];
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const float f = __uint_as_float(v[j]);  // padded columns (>= Nout) hold exact zeros
-                    ssum[cc * 16 + j] += f;
-                    ssq[cc * 16 + j] += f * f;
-                  }
+                for (int j = 0; j < 8; ++j) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[0][2 * j]), __uint_as_float(v[0][2 * j + 1]));
+                  pk[j] = *reinterpret_cast<uint32_t *>(&h);
                 }
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+                d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
               }
             }
-          } else {
-            for (int c0 = 0; c0 < p.Nout; c0 += 16) {
-              uint32_t v[16];
-              tc::tmem_ld16(taddr + c0, v);
-              tc::tmem_ld_wait();
-              if (valid) store_chunk(v, c0);
-            }
           }
+        } else {  // scatter: 8 output phases, four at a time per 16-channel chunk
+          auto phases4 = [&](auto cc_tag) {
+            constexpr int cc = decltype(cc_tag)::value;
+            if (cc * 16 >= p.Nout) return;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint32_t v[4][16];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tc::tmem_ld16(t_mt + (uint32_t)((4 * g + j) * p.acc_stride + cc * 16), v[j]);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) emit(v[j], 4 * g + j, mt, cc_tag);
+            }
+          };
+          phases4(std::integral_constant<int, 0>{});
+          phases4(std::integral_constant<int, 1>{});
+          phases4(std::integral_constant<int, 2>{});
+          phases4(std::integral_constant<int, 3>{});
         }
       }
       tc::tc_fence_before();

@@ -94,19 +94,18 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
         if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
         uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
         if (p.debug & 1) { tc::mbar_arrive(&s_full[slot]); continue; }
-        tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
+        tc::mbar_expect_tx(&s_full[slot], p.box_bytes);
         // TMA needs a 16-byte aligned start along z: block parity selects the copy whose z shift makes it so
         const int cp = (z0 >> 2) & 1;
         const int c0 = z0 - p.P - p.zshift[cp] + 8;
-        tc::tma_load_5d(dst, &tmA, &s_full[slot], c0, y0 - p.P, x0 - p.P, b, cp);
-        tc::tma_load_5d(dst + (size_t)p.rows_alloc * 16, &tmA, &s_full[slot], c0 + 8, y0 - p.P, x0 - p.P, b, cp);
+        tc::tma_load_5d(dst, &tmA, &s_full[slot], c0, y0 - p.P, x0 - p.P, b, cp);  // rows of 16 z = 32 bytes, SWIZZLE_32B
       }
     }
   } else if (warp == 5) {
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
-    const uint64_t a_hi = tc::make_desc(0, (uint32_t)p.rows_alloc * 16, 128), b_hi = tc::make_desc(0, 64 * 16, 128);
+    const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc(0, 64 * 16, 128);
     tc::mbar_wait(b_ready, 0);
     tc::tc_fence_after();
     uint32_t e = 0;
@@ -120,11 +119,11 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
       for (int dx = 0; dx < 7; ++dx) {
         for (int dy = 0; dy < 7; ++dy) {
           const int tap = dx * 7 + dy;
-          const uint64_t a0 = a_hi | (uint64_t)((a_slot + (uint32_t)(dx * p.Yh + dy)) & 0x3FFF);
+          const uint64_t a0 = a_hi | (uint64_t)((a_slot + 2u * (uint32_t)(dx * p.Yh + dy)) & 0x3FFF);  // 32-byte rows
           const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)tap * kTileBytesA) >> 4) & 0x3FFF);
           if (leader && !(p.debug & 2)) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 64, a0 + (uint64_t)(mt * 128), b0, idesc, (uint32_t)(tap != 0));
+            for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 64, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(tap != 0));
           }
           __syncwarp();
         }
@@ -711,7 +710,7 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
       if (Yt > mt * 128) continue;
       const int Xt = mn(p.Xo, (mt * 128 - Yt) / Yh + 1), Xh = Xt + 6;
       if (Xh > 256) continue;
-      const int rows_alloc = round_up(mx(Xh * Yh, mt * 128 + 6 * Yh + 6), 8);
+      const int rows_alloc = round_up(mx(Xh * Yh, mt * 128 + 6 * Yh + 6), 32);  // 32-byte rows: slots are multiples of 1 KB
       const uint32_t slot = 2u * rows_alloc * 16;
       const int nslots = (int)mn<uint32_t>(6, (kSmemLimitThin - fixed) / slot);
       if (nslots < 2) continue;
@@ -729,7 +728,7 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
     if (nyt > 8 && found) break;
   }
   if (!found) return false;
-  best.box_bytes = 16u * best.Yh * best.Xh;
+  best.box_bytes = 32u * best.Yh * best.Xh;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * best.mtiles * 64)) cols <<= 1;
   best.tmem_cols = cols;
@@ -821,8 +820,8 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   const cuuint64_t zc = (cuuint64_t)p.Zc;
   const cuuint64_t gdim[5] = {zc, (cuuint64_t)p.Yi, (cuuint64_t)p.Xi, (cuuint64_t)p.B, 2};
   const cuuint64_t gstr[4] = {zc * 2, (cuuint64_t)p.Yi * zc * 2, (cuuint64_t)p.Xi * p.Yi * zc * 2, (cuuint64_t)rows * zc * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)p.Yh, (cuuint32_t)p.Xh, 1, 1};
-  int r = encode_map(&tm, rp, 5, gdim, gstr, box);
+  const cuuint32_t box[5] = {16, (cuuint32_t)p.Yh, (cuuint32_t)p.Xh, 1, 1};
+  int r = encode_map(&tm, rp, 5, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_32B);
   if (r) return r;
   const long long total = (long long)p.B * p.nxt * p.nyt * p.nzb;
   const int grid = (int)mn<long long>(total, (long long)num_sms());

@@ -4,6 +4,8 @@
 // (reference model/blocks.py:45,50,52-53,87-88; generator.py:85; trainer/Trainer.py:171).
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cg {
@@ -165,8 +167,12 @@ struct V8<__nv_bfloat16> {
 // first + i * lanes_in_grid), so every iteration of the whole grid reads one contiguous span.  load(row, raw[]) fetches
 // the row's 16-byte chunks WITHOUT consuming them, so U of them are in flight per thread before eval(raw, v) runs;
 // fp32 runs of 32 rows feed fp64 totals.
-template <int NS, int U, int NRAW, typename FL, typename FE>
-__device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, double *sums, FL load, FE eval) {
+struct NoPost {
+  __device__ __forceinline__ void operator()(double (&)[1][8]) const {}
+  __device__ __forceinline__ void operator()(double (&)[2][8]) const {}
+};
+template <int NS, int U, int NRAW, typename FL, typename FE, typename FP = NoPost>
+__device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, double *sums, FL load, FE eval, FP post = FP()) {
   extern __shared__ double sh[];  // [lanes][NS][C]
   const int C8 = C >> 3;
   const int lanes = blockDim.x / C8;
@@ -211,6 +217,7 @@ __device__ __forceinline__ void col_reduce8_body(int64_t n_rows, int C, double *
 #pragma unroll
         for (int k = 0; k < 8; ++k) tot[s][k] += (double)part[s][k];
     }
+    post(tot);  // linear map of this thread's totals (commutes with the remaining summation)
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -253,7 +260,8 @@ static ColGrid col_grid8(int64_t n_rows, int C, int ns) {
   const int lanes = 256 / (C >> 3);
   ColGrid g;
   g.rows_per_block = 0;  // rows are walked grid-strided
-  g.blocks = (int)mx<int64_t>(1, mn<int64_t>((n_rows + lanes - 1) / lanes, (int64_t)num_sms() * 4));
+  static int per_sm = getenv("CGAN3D_RED_BLOCKS") ? atoi(getenv("CGAN3D_RED_BLOCKS")) : 4;
+  g.blocks = (int)mx<int64_t>(1, mn<int64_t>((n_rows + lanes - 1) / lanes, (int64_t)num_sms() * per_sm));
   g.smem = (size_t)ns * lanes * C * sizeof(double);
   return g;
 }
@@ -314,11 +322,15 @@ bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t
         unpack8<T>(raw + NV, dd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float xh = fmaf(yy[k], k8.invstd[k], k8.nm[k]);
+          // streams sum g and sum g*y; sum g*xhat = invstd * sum g*y - mean*invstd * sum g is applied to the totals
           const float g = dd[k] * act_bwd_t<ACT>(fmaf(k8.a[k], yy[k], k8.b[k]), act, slope);
           v[0][k] = g;
-          v[1][k] = g * xh;
+          v[1][k] = g * yy[k];
         }
+      },
+      [&](double (&tot)[2][8]) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot[1][k] = (double)k8.invstd[k] * tot[1][k] + (double)k8.nm[k] * tot[0][k];
       });
 }
 

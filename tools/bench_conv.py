@@ -29,6 +29,7 @@ CASES = {
     "down1": (False, 32, 64, 3, 2, 1, 0, 8, (64, 64, 64)),
     "up0": (True, 64, 32, 3, 2, 1, 1, 8, (32, 32, 32)),
     "up1": (True, 32, 16, 3, 2, 1, 1, 4, (64, 64, 64)),
+    "up1_c3": (True, 32, 16, 3, 2, 1, 1, 16, (64, 64, 64)),
     "first_c3": (False, 1, 16, 7, 1, 0, 0, 16, (134, 134, 134)),
     "last_c3": (False, 16, 1, 7, 1, 0, 0, 16, (134, 134, 134)),
     "first": (False, 1, 16, 7, 1, 0, 0, 2, (134, 134, 134)),
