@@ -227,18 +227,20 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
             d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           };
-          if constexpr (STATS) {
+          if (p.N <= 64) {  // up to four 16-channel chunks: all TMEM loads in flight before one wait
+            uint32_t v[4][16];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {  // N <= 64: static register indices for the per-channel partial sums
-              if (cc * 16 < p.N) {
-                uint32_t v[16];
-                tc::tmem_ld16(taddr + cc * 16, v);
-                tc::tmem_ld_wait();
-                if (valid) {
-                  store_chunk(v, cc * 16);
+            for (int cc = 0; cc < 4; ++cc)
+              if (cc * 16 < p.N) tc::tmem_ld16(taddr + cc * 16, v[cc]);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              if (cc * 16 < p.N && valid) {
+                store_chunk(v[cc], cc * 16);
+                if constexpr (STATS) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
-                    const float f = __uint_as_float(v[j]);
+                    const float f = __uint_as_float(v[cc][j]);
                     ssum[cc * 16 + j] += f;
                     ssq[cc * 16 + j] += f * f;
                   }

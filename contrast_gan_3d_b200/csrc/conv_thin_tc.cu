@@ -154,16 +154,17 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
         const int xx = r / p.Yh, yy = r - xx * p.Yh;
         const bool valid = xx < xlen && yy < ylen;
         bf16 *dst = out + ((((size_t)b * p.Xo + (x0 + xx)) * p.Yo + (y0 + yy)) * p.Zo + z0) * 16;
+        uint32_t v[4][16];  // the four output z of this row: all TMEM loads in flight before one wait
+#pragma unroll
+        for (int zo = 0; zo < 4; ++zo) tc::tmem_ld16(d_base + (uint32_t)(mt * 64 + zo * 16), v[zo]);
+        tc::tmem_ld_wait();
 #pragma unroll
         for (int zo = 0; zo < 4; ++zo) {
-          uint32_t v[16];
-          tc::tmem_ld16(d_base + (uint32_t)(mt * 64 + zo * 16), v);
-          tc::tmem_ld_wait();
           if (valid && z0 + zo < p.Zo) {
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[zo][2 * j]), __uint_as_float(v[zo][2 * j + 1]));
               pk[j] = *reinterpret_cast<uint32_t *>(&h);
             }
             uint4 *d4 = reinterpret_cast<uint4 *>(dst + zo * 16);
@@ -172,7 +173,7 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
             if constexpr (STATS) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float f = __uint_as_float(v[j]);
+                const float f = __uint_as_float(v[zo][j]);
                 ssum[j] += f;
                 ssq[j] += f * f;
               }
