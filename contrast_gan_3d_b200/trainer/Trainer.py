@@ -138,11 +138,16 @@ class Trainer:
     # ---------------------------------------------------------------- critic / generator updates
     def train_critic(self, real: Tensor, reconstructions: Tensor, retain_graph: bool) -> Dict[str, Tensor]:
         self.optimizer_D.zero_grad(set_to_none=True)
+        overlap = self.grad_reducer is not None and hasattr(self.grad_reducer, "prepare")
+        if overlap:
+            self.grad_reducer.prepare(self.critic.parameters())  # grads become views into the all-reduce buckets
         real_logits = self.critic(real)
         fake_logits = self.critic(reconstructions.detach())
         loss_critic = self.gan_loss_w * self.loss_GAN(fake_logits, real_logits)
         loss_critic.backward()
-        if self.grad_reducer is not None:
+        if overlap:
+            self.grad_reducer.finish(self.critic.parameters())
+        elif self.grad_reducer is not None:
             self.grad_reducer.reduce(self.critic.parameters())
         if isinstance(self.optimizer_D, FusedAdam):
             self.optimizer_D.step(clip=self.weight_clip)  # Adam + clamp(+-clip) in one kernel
@@ -156,6 +161,9 @@ class Trainer:
 
     def train_generator(self, inputs: Tensor, reconstructions: Tensor, centerlines_masks: Tensor) -> Dict[str, Tensor]:
         self.optimizer_G.zero_grad(set_to_none=True)
+        overlap = self.grad_reducer is not None and hasattr(self.grad_reducer, "prepare")
+        if overlap:
+            self.grad_reducer.prepare(self.generator.parameters())
         # The critic's parameter gradients of this pass are dead (the reference lets autograd compute them and zeroes them
         # before their next use, Trainer.py:111): freeze the critic so that only its dgrad chain runs.
         critic_params = [p for p in self.critic.parameters() if p.requires_grad]
@@ -174,7 +182,9 @@ class Trainer:
             loss_hu = self.hu_loss_w * self.loss_HU(reconstructions, centerlines_masks)
         full_loss_G = loss_G + loss_sim + loss_hu
         full_loss_G.backward()
-        if self.grad_reducer is not None:
+        if overlap:
+            self.grad_reducer.finish(self.generator.parameters())
+        elif self.grad_reducer is not None:
             self.grad_reducer.reduce(self.generator.parameters())
         self.optimizer_G.step()
         if self.lr_scheduler_G is not None:

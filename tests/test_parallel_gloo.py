@@ -28,8 +28,18 @@ def _worker(rank, world, port, q):
         p.grad = torch.randn_like(p)
     local = [p.grad.clone() for p in D.parameters()]
     GradBucketReducer(bucket_bytes=4096).reduce(D.parameters())  # small buckets: several all-reduces
-    q.put((rank, [p.detach().numpy().copy() for p in D.parameters()], [t.numpy().copy() for t in local],
-           [p.grad.numpy().copy() for p in D.parameters()]))
+    reduced = [p.grad.numpy().copy() for p in D.parameters()]
+    # overlapped path: gradients are views into the buckets, all-reduce launched from autograd hooks during backward
+    red = GradBucketReducer(bucket_bytes=4096)
+    for p in D.parameters():
+        p.grad = None
+    red.prepare(D.parameters())
+    loss = sum((p * l).sum() for p, l in zip(D.parameters(), local))  # d loss / d p == the same local gradients
+    loss.backward()
+    red.finish(D.parameters())
+    for p, r in zip(D.parameters(), reduced):
+        assert torch.allclose(p.grad, torch.from_numpy(r), rtol=1e-6, atol=1e-7), "overlapped reducer != pack/unpack reducer"
+    q.put((rank, [p.detach().numpy().copy() for p in D.parameters()], [t.numpy().copy() for t in local], reduced))
     dist.barrier()
     dist.destroy_process_group()
 
