@@ -352,6 +352,23 @@ def train_step(st: StepState, opt: Tensor, low: Tensor, high: Tensor, mask_low: 
     return out
 
 
+def validate(st: StepState, batches: Sequence[Tuple[Tensor, Tensor, Tensor]]) -> Dict[str, float]:
+    """Trainer.validate (Trainer.py:247-308): eval-mode networks (BatchNorm uses its running statistics), no_grad;
+    `batches` = one (opt, low, high) triple per validation iteration, visited in ScanType order OPT, LOW, HIGH."""
+    loss_sim = loss_g = loss_real_c = loss_fake_c = 0.0
+    with torch.no_grad():
+        for opt, low, high in batches:
+            loss_real_c -= float(wasserstein_loss(critic_forward(st.dp, st.db, opt, st.d_layers, train=False)))  # :263-267
+            for sample in (low, high):
+                sample_hat = sample - generator_forward(st.gp, st.gb, sample, st.g_layers, train=False)  # :269-270
+                loss_fake = float(wasserstein_loss(critic_forward(st.dp, st.db, sample_hat, st.d_layers, train=False)))  # :271-272
+                loss_fake_c += loss_fake
+                loss_g -= loss_fake
+                loss_sim += float(zncc_loss(sample_hat, sample))  # :276
+    n = len(batches)
+    return {"D": (loss_real_c + loss_fake_c) / n, "G": loss_g / (n * 2), "sim": loss_sim / (n * 2)}  # :300-304
+
+
 # --------------------------------------------------------------------------------------
 # data: scaler, synthetic HU patches, crop/pad index law, conv shape arithmetic, tiler
 # --------------------------------------------------------------------------------------

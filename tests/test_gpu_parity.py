@@ -646,3 +646,25 @@ def test_conv_with_fused_batchnorm_statistics(case):
     yc = y.double().permute(1, 0, 2, 3, 4).reshape(cout, -1)
     ref = torch.cat([yc.sum(1), (yc * yc).sum(1)])
     assert_close32(sums, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()), msg="fused statistics")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_validate_against_oracle(dtype):
+    """Trainer.validate (eval-mode BatchNorm from the running statistics, non-cubic validation patches as in the reference's
+    (256, 256, 128) setting, scaled down) after one training step, against the oracle's restatement."""
+    st = O.StepState(seed=0)
+    tr = _make_trainer(dtype)
+    tr.val_iterations = 2
+    gen = torch.Generator().manual_seed(21)
+    opt, low, high, ml, mh = _batches(gen, (32, 32, 32))
+    O.train_step(st, opt, low, high, ml, mh, 0)
+    tr.train_step([dict(data=opt, seg=None, name=[]), dict(data=low, seg=ml, name=[]), dict(data=high, seg=mh, name=[])], 0)
+    vpatch = (64, 64, 32)
+    vb = [tuple(O.synthetic_patches(gen, (2, 1, *vpatch)) for _ in range(3)) for _ in range(2)]
+    ref = O.validate(st, vb)
+    loaders = {0: iter([dict(data=b[0]) for b in vb]), -1: iter([dict(data=b[1]) for b in vb]), 1: iter([dict(data=b[2]) for b in vb])}
+    got = tr.validate(loaders, 400)
+    assert tr.generator.training and tr.critic.training  # validate() restores train mode (Trainer.py:297-298)
+    rt, at = (2e-3, 1e-4) if dtype == torch.float32 else (2e-2, 2e-3)  # weights went through one Adam step (see above)
+    for k in ("D", "G", "sim"):
+        assert abs(float(got[k]) - ref[k]) <= rt * abs(ref[k]) + at, (k, float(got[k]), ref[k])
