@@ -169,3 +169,22 @@ def test_grid_tiles_divisible_and_squeeze():
     assert len(t) == 32 and t[0] == (0, 0, 0) and t[1] == (0, 0, 128) and t[2] == (0, 128, 0)
     t = O.grid_tiles((20, 16, 16), (16, 16, 16))
     assert t == [(0, 0, 0), (4, 0, 0)]
+
+
+def test_oracle_validate_against_reference_golden(golden_dir):
+    """Trainer.validate of the unmodified reference (tests/golden/make_golden_validate.py) vs the oracle's restatement."""
+    g = np.load(golden_dir / "validate_32.npz")
+    st = O.StepState(seed=0)
+    gen = torch.Generator().manual_seed(21)
+    patch = (32, 32, 32)
+    opt = O.synthetic_patches(gen, (2, 1, *patch))
+    low = O.synthetic_patches(gen, (1, 1, *patch))
+    high = O.synthetic_patches(gen, (1, 1, *patch))
+    ml = O.synthetic_masks(gen, (1, 1, *patch))
+    mh = O.synthetic_masks(gen, (1, 1, *patch))
+    O.train_step(st, opt, low, high, ml, mh, 0)
+    vb = [tuple(O.synthetic_patches(gen, (2, 1, 64, 64, 32)) for _ in range(3)) for _ in range(2)]
+    got = O.validate(st, vb)
+    ref = dict(zip(("D", "G", "sim"), g["val"]))
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 1e-4 * abs(ref[k]) + 1e-6, (k, got[k], ref[k])
