@@ -305,13 +305,20 @@ struct BnC8 {
 };
 
 template <typename T, int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t n_rows, int C, int rpb,
                       const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
                       float slope, double *sums) {
   const int c0 = (threadIdx.x % (C >> 3)) * 8;
-  BnC8 k8;
-  k8.load(mi, gamma, beta, C, c0);
+  struct { float a[8], b[8], invstd[8], nm[8]; } k8;  // only what the streaming loop needs (register budget: 2 blocks/SM)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float mean = mi[c0 + k], is = mi[C + c0 + k];
+    k8.invstd[k] = is;
+    k8.nm[k] = -mean * is;
+    k8.a[k] = gamma[c0 + k] * is;
+    k8.b[k] = beta[c0 + k] - mean * k8.a[k];
+  }
   constexpr int NV = (int)sizeof(T) / 2;
   col_reduce8_body<2, 4, 2 * NV>(
       n_rows, C, sums,
@@ -365,7 +372,7 @@ bn_apply8_kernel(const T *__restrict__ y, T *__restrict__ z, int64_t total8, int
 }
 
 template <typename T, int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t total8, int C, double inv_n,
                      const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
                      float slope, const double *__restrict__ sums) {
