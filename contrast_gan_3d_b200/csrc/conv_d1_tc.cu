@@ -211,17 +211,20 @@ __global__ void d1_toeplitz_kernel(const bf16 *__restrict__ wp, bf16 *__restrict
 }
 
 // copy[row][c] = in[row][c - 1] (0 outside), c in [0, Zc): makes every z window start (2*z0 - 1) a multiple of 8 columns
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 d1_shift_copy_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc) {
-  extern __shared__ uint16_t line[];  // line[c] = in[c - 1]
-  const long long r = blockIdx.x;
+  extern __shared__ uint16_t lines[];  // one warp per line (8 lines per block): line[c] = in[c - 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint16_t *line = lines + (size_t)warp * Zc;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
   const uint16_t *src = reinterpret_cast<const uint16_t *>(in) + r * Z;
-  for (int i = threadIdx.x; i < Zc; i += blockDim.x) {
+  for (int i = lane; i < Zc; i += 32) {
     const int z = i - 1;
     line[i] = (z >= 0 && z < Z) ? src[z] : (uint16_t)0;
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < (Zc >> 3); j += blockDim.x) {
+  __syncwarp();
+  for (int j = lane; j < (Zc >> 3); j += 32) {
     uint32_t w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) w[k] = (uint32_t)line[j * 8 + 2 * k] | ((uint32_t)line[j * 8 + 2 * k + 1] << 16);
@@ -284,7 +287,8 @@ static int run_d1_gather(const cgan3d_conv_geom &g, const void *in, const void *
   CG_LAUNCH_CHECK("d1_toeplitz");
   bf16 *cp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kD1Tiles * kD1TileBytes + 256);
   const long long rows = (long long)p.B * p.Xi * p.Yi;
-  d1_shift_copy_kernel<<<(unsigned)rows, 128, (size_t)p.Zc * 2, st>>>(reinterpret_cast<const bf16 *>(in), cp, rows, p.Zi, p.Zc);
+  d1_shift_copy_kernel<<<(unsigned)((rows + 7) / 8), 256, (size_t)8 * p.Zc * 2, st>>>(reinterpret_cast<const bf16 *>(in), cp, rows, p.Zi,
+                                                                                     p.Zc);
   CG_LAUNCH_CHECK("d1_shift_copy");
   CUtensorMap tm;
   const cuuint64_t zc = (cuuint64_t)p.Zc;
@@ -416,29 +420,33 @@ d1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_constan
 }
 
 // E[b][x][yy][oz][dyp*4 + dz] = in[b][x][2*yy - 1 + dyp][2*oz - 1 + dz]  (0 outside), yy in [0, Ys], oz in [0, Zs)
-__global__ void d1_expand_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ e, int B, int Xi, int Yi, int Zi, int Ye, int Zs) {
-  const long long total = (long long)B * Xi * Ye * Zs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int oz = (int)(t % Zs); t /= Zs;
-    const int yy = (int)(t % Ye); t /= Ye;
-    const int x = (int)(t % Xi);
-    const int b = (int)(t / Xi);
-    uint32_t pk[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int dyp = 0; dyp < 2; ++dyp) {
-      const int y = 2 * yy - 1 + dyp;
-      if (y < 0 || y >= Yi) continue;
-      const bf16 *line = in + (((size_t)b * Xi + x) * Yi + y) * Zi;
-#pragma unroll
-      for (int dz = 0; dz < 4; ++dz) {
-        const int z = 2 * oz - 1 + dz;
-        const uint16_t h = (z >= 0 && z < Zi) ? __bfloat16_as_ushort(line[z]) : (uint16_t)0;
-        const int j = dyp * 4 + dz;
-        pk[j >> 1] |= (uint32_t)h << ((j & 1) * 16);
-      }
-    }
-    reinterpret_cast<uint4 *>(e)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+// One warp per (b, x, yy) output line (8 lines per block): the two source lines are staged in shared memory.
+__global__ void __launch_bounds__(256)
+d1_expand_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ e, long long lines_total, int Xi, int Yi, int Zi, int Ye, int Zs) {
+  extern __shared__ uint16_t lines[];  // per warp: two lines, line[dyp][1 + z] = in[.., 2*yy - 1 + dyp, z]; zeros outside
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = (2 * Zs + 2 + 7) & ~7;
+  uint16_t *l0 = lines + (size_t)warp * 2 * n, *l1 = l0 + n;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= lines_total) return;
+  const int yy = (int)(r % Ye);
+  const long long bx = r / Ye;  // b * Xi + x
+  const int y0 = 2 * yy - 1, y1 = 2 * yy;
+  const uint16_t *base = reinterpret_cast<const uint16_t *>(in) + (size_t)bx * Yi * Zi;
+  const bool in0 = y0 >= 0 && y0 < Yi, in1 = y1 < Yi;
+  for (int i = lane; i < n; i += 32) {
+    const int z = i - 1;
+    const bool zin = z >= 0 && z < Zi;
+    l0[i] = (in0 && zin) ? base[(size_t)y0 * Zi + z] : (uint16_t)0;
+    l1[i] = (in1 && zin) ? base[(size_t)y1 * Zi + z] : (uint16_t)0;
+  }
+  __syncwarp();
+  uint4 *dst = reinterpret_cast<uint4 *>(e) + (size_t)r * Zs;
+  for (int oz = lane; oz < Zs; oz += 32) {
+    // j = dyp*4 + dz reads line[dyp][2*oz + dz]
+    const uint32_t a0 = (uint32_t)l0[2 * oz] | ((uint32_t)l0[2 * oz + 1] << 16), a1 = (uint32_t)l0[2 * oz + 2] | ((uint32_t)l0[2 * oz + 3] << 16);
+    const uint32_t b0 = (uint32_t)l1[2 * oz] | ((uint32_t)l1[2 * oz + 1] << 16), b1 = (uint32_t)l1[2 * oz + 2] | ((uint32_t)l1[2 * oz + 3] << 16);
+    dst[oz] = make_uint4(a0, a1, b0, b1);
   }
 }
 
@@ -476,7 +484,9 @@ int d1_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, 
     if (e != cudaSuccess) return cuda_fail(e, "tcgen05 critic-first wgrad memset");
   }
   bf16 *E = reinterpret_cast<bf16 *>(ws);
-  d1_expand_kernel<<<num_sms() * 16, 256, 0, st>>>(reinterpret_cast<const bf16 *>(big), E, p.B, p.Xi, p.Yi, p.Zi, p.Ye, p.Zs);
+  const long long elines = (long long)p.B * p.Xi * p.Ye;
+  d1_expand_kernel<<<(unsigned)((elines + 7) / 8), 256, (size_t)8 * 2 * ((2 * p.Zs + 2 + 7) & ~7) * 2, st>>>(
+      reinterpret_cast<const bf16 *>(big), E, elines, p.Xi, p.Yi, p.Zi, p.Ye, p.Zs);
   CG_LAUNCH_CHECK("d1_expand");
   CUtensorMap tmE, tmS;
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};

@@ -221,20 +221,24 @@ __global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict_
 // TMA needs 16-byte aligned row pitches AND a 16-byte aligned start coordinate along the contiguous axis, but the z
 // windows start every 4 voxels.  Two z-shifted, zero-margined copies of the 1-channel input make every window start
 // aligned in one of them:  copy[s][row][c] = in[row][c - 8 + shift_s]  (0 outside), c in [0, Zc), Zc % 8 == 0.
-// One block per input line: the line is staged in shared memory (with zero margins) and written out as 16-byte chunks.
-__global__ void __launch_bounds__(128)
+// One WARP per input line (8 lines per block): the line is staged in shared memory (with zero margins) and written out as
+// 16-byte chunks.
+__global__ void __launch_bounds__(256)
 shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc, int s0, int s1) {
-  extern __shared__ uint16_t line[];  // line[8 + z] = in[z], zeros in [0, 8) and beyond Z
-  const long long r = blockIdx.x;
+  extern __shared__ uint16_t lines[];  // per warp: line[8 + z] = in[z], zeros in [0, 8) and beyond Z
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = (Zc + 24 + 7) & ~7;
+  uint16_t *line = lines + (size_t)warp * n;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
   const uint16_t *src = reinterpret_cast<const uint16_t *>(in) + r * Z;
-  const int n = Zc + 24;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = lane; i < n; i += 32) {
     const int z = i - 8;
     line[i] = (z >= 0 && z < Z) ? src[z] : (uint16_t)0;
   }
-  __syncthreads();
+  __syncwarp();
   const int chunks = Zc >> 3;
-  for (int i = threadIdx.x; i < 2 * chunks; i += blockDim.x) {
+  for (int i = lane; i < 2 * chunks; i += 32) {
     const int cp = i >= chunks, j = i - cp * chunks;
     const int base = j * 8 + (cp ? s1 : s0);  // out[c] = in[c - 8 + s] = line[c + s]
     uint32_t w[4];
@@ -640,20 +644,28 @@ wgrad7_thin_tc_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_cons
 }
 
 // E[b][xe][ye][z][j] = Q1[b][xe - P][ye - P][z + j - P]  (0 outside Q1), j = 0..7: one 16-byte row per (xe, ye, z)
-__global__ void __launch_bounds__(128)
-expand_z_kernel(const bf16 *__restrict__ q, bf16 *__restrict__ e, int B, int Xq, int Yq, int Zq, int Xe, int Ye, int Ze, int P) {
-  extern __shared__ uint16_t line[];  // line[i] = Q1 line value at z = i - P (0 outside), i in [0, Ze + 8)
-  const int ye = blockIdx.x, xe = blockIdx.y, b = blockIdx.z;
+// One warp per (b, xe, ye) line, 8 lines per block.
+__global__ void __launch_bounds__(256)
+expand_z_kernel(const bf16 *__restrict__ q, bf16 *__restrict__ e, long long lines_total, int Xq, int Yq, int Zq, int Xe, int Ye, int Ze, int P) {
+  extern __shared__ uint16_t lines[];  // per warp: line[i] = Q1 line value at z = i - P (0 outside), i in [0, Ze + 8)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = (Ze + 8 + 7) & ~7;
+  uint16_t *line = lines + (size_t)warp * n;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= lines_total) return;
+  const int ye = (int)(r % Ye);
+  const int xe = (int)((r / Ye) % Xe);
+  const int b = (int)(r / ((long long)Ye * Xe));
   const int xq = xe - P, yq = ye - P;
   const bool inside = xq >= 0 && xq < Xq && yq >= 0 && yq < Yq;
   const uint16_t *src = reinterpret_cast<const uint16_t *>(q) + (((size_t)b * Xq + (inside ? xq : 0)) * Yq + (inside ? yq : 0)) * Zq;
-  for (int i = threadIdx.x; i < Ze + 8; i += blockDim.x) {
+  for (int i = lane; i < Ze + 8; i += 32) {
     const int z = i - P;
     line[i] = (inside && z >= 0 && z < Zq) ? src[z] : (uint16_t)0;
   }
-  __syncthreads();
-  uint4 *dst = reinterpret_cast<uint4 *>(e) + (((size_t)b * Xe + xe) * Ye + ye) * (size_t)Ze;
-  for (int z = threadIdx.x; z < Ze; z += blockDim.x) {
+  __syncwarp();
+  uint4 *dst = reinterpret_cast<uint4 *>(e) + (size_t)r * Ze;
+  for (int z = lane; z < Ze; z += 32) {
     uint32_t w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) w[k] = (uint32_t)line[z + 2 * k] | ((uint32_t)line[z + 2 * k + 1] << 16);
@@ -814,8 +826,8 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   CG_LAUNCH_CHECK("toeplitz_a");
   bf16 *rp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kTapTilesA * kTileBytesA + 256);
   const long long rows = (long long)p.B * p.Xi * p.Yi;
-  shifted_copies_kernel<<<(unsigned)rows, 128, (size_t)(p.Zc + 24) * 2, st>>>(reinterpret_cast<const bf16 *>(in), rp, rows, p.Zi, p.Zc,
-                                                                             p.zshift[0], p.zshift[1]);
+  shifted_copies_kernel<<<(unsigned)((rows + 7) / 8), 256, (size_t)8 * ((p.Zc + 24 + 7) & ~7) * 2, st>>>(
+      reinterpret_cast<const bf16 *>(in), rp, rows, p.Zi, p.Zc, p.zshift[0], p.zshift[1]);
   CG_LAUNCH_CHECK("shifted_copies");
   CUtensorMap tm;
   const cuuint64_t zc = (cuuint64_t)p.Zc;
@@ -943,9 +955,9 @@ int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small
     if (e != cudaSuccess) return cuda_fail(e, "tcgen05 thin wgrad memset");
   }
   bf16 *E = reinterpret_cast<bf16 *>(ws);
-  if (p.Xe > 65535 || p.B > 65535) return fail(CGAN3D_E_SHAPE, "tcgen05 thin wgrad: extent too large");
-  expand_z_kernel<<<dim3((unsigned)p.Ye, (unsigned)p.Xe, (unsigned)p.B), 128, (size_t)(p.Zs + 8) * 2, st>>>(
-      reinterpret_cast<const bf16 *>(q1), E, p.B, Xq, Yq, Zq, p.Xe, p.Ye, p.Zs, p.P);
+  const long long elines = (long long)p.B * p.Xe * p.Ye;
+  expand_z_kernel<<<(unsigned)((elines + 7) / 8), 256, (size_t)8 * ((p.Zs + 8 + 7) & ~7) * 2, st>>>(
+      reinterpret_cast<const bf16 *>(q1), E, elines, Xq, Yq, Zq, p.Xe, p.Ye, p.Zs, p.P);
   CG_LAUNCH_CHECK("expand_z");
   CUtensorMap tmE, tmS;
   {
