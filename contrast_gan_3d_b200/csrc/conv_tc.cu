@@ -35,6 +35,7 @@ struct TcPlan {
   int mtiles, rows_alloc, nitems, b_stages;
   uint32_t plane_bytes, btile_bytes, box_bytes, tmem_cols, smem_bytes;
   int a_swz;  // 0: plane slab in Cin/8 chunks (SWIZZLE_NONE); 32/64/128: whole voxels, [row][Cin] in the matching swizzle mode
+  int pair;   // 1: CTA pairs (cta_group::2): two columns per pair, each CTA holds half of the weight rows
 };
 
 constexpr int kPlaneSlots = 3;
@@ -45,18 +46,28 @@ constexpr uint32_t kSmemLimit = 232448 - 1024;
 // range [c*total/grid, (c+1)*total/grid): at most one plane of imbalance; a range that crosses a column boundary is
 // processed as two items (each item re-loads its two halo planes).
 struct ItemIter {
-  int idx, end;
+  int idx, end, rank;
   __device__ __forceinline__ ItemIter(const TcPlan &p) {
-    const long long total = (long long)p.nitems * p.X;  // nitems == number of columns
-    idx = (int)(total * blockIdx.x / gridDim.x);
-    end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    // CTA pairs: the two CTAs of a cluster walk the same range of (column pair, plane) items in lockstep
+    const int nblk = p.pair ? (int)gridDim.x >> 1 : (int)gridDim.x, blk = p.pair ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+    const int ncols = p.pair ? (p.nitems + 1) >> 1 : p.nitems;
+    rank = p.pair ? (int)blockIdx.x & 1 : 0;
+    const long long total = (long long)ncols * p.X;
+    idx = (int)(total * blk / nblk);
+    end = (int)(total * (blk + 1) / nblk);
   }
-  __device__ __forceinline__ bool next(const TcPlan &p, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x0, int &xlen) {
+  // live == false: the odd CTA of the last pair when the column count is odd (it computes a copy of the last column and stores nothing)
+  __device__ __forceinline__ bool next(const TcPlan &p, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x0, int &xlen, bool &live) {
     if (idx >= end) return false;
     int col = idx / p.X;
     x0 = idx - col * p.X;
     xlen = min(p.X - x0, end - idx);
     idx += xlen;
+    live = true;
+    if (p.pair) {
+      col = 2 * col + rank;
+      if (col >= p.nitems) { col = p.nitems - 1; live = false; }
+    }
     const int sl = col % p.nslabs; col /= p.nslabs;
     const int zt = col % p.nzt;
     b = col / p.nzt;
@@ -68,10 +79,15 @@ struct ItemIter {
 
 // STATS: the epilogue also accumulates per-channel sum / sum of squares of the fp32 accumulators into bn_sums (fp64 [2*N],
 // N <= 64): the BatchNorm batch statistics of reference model/blocks.py:45 without a separate pass over the output.
-template <int KSTEPS, int MT, bool STATS>
+//
+// PAIR: two CTAs of a cluster (one TPC) run as one cta_group::2 unit.  Each owns a column of the output and supplies its
+// own activation planes (the A rows) plus HALF of every weight tile (the B rows), so the weight traffic per SM halves
+// and one tcgen05.mma of the rank-0 CTA drives both tensor cores (50.8 instead of 77 cycles per M = 128, N = 64 slice).
+// TMA loads of both CTAs count their bytes on the rank-0 barriers; its MMA commits are multicast to both CTAs.
+template <int KSTEPS, int MT, bool STATS, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out, const TcPlan p,
-                  double *__restrict__ bn_sums) {
+conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const bf16 *__restrict__ wB,
+                  bf16 *__restrict__ out, const TcPlan p, double *__restrict__ bn_sums) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *planes = smem;
   uint8_t *bt = planes + (size_t)kPlaneSlots * p.plane_bytes;
@@ -85,16 +101,23 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPlaneSlots; ++i) { tc::mbar_init(&plane_full[i], 1); tc::mbar_init(&plane_empty[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], PAIR ? 8 : 4); }
     tc::fence_barrier_init();
   }
+  const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
+  if constexpr (PAIR) {  // the peer's barriers must exist before anything signals them
+    __syncthreads();
+    tc::cluster_sync();
+  }
   if (warp == 5) {
-    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
-    tc::tmem_relinquish();
+    if constexpr (PAIR) { tc::tmem_alloc2(tmem_ptr, p.tmem_cols); tc::tmem_relinquish2(); }
+    else { tc::tmem_alloc(tmem_ptr, p.tmem_cols); tc::tmem_relinquish(); }
   }
   if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmA);
+  if (PAIR && warp == 6 && lane == 0) tc::tma_prefetch_desc(&tmW);
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) tc::cluster_sync();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int kchunks8 = p.a_swz ? 1 : (p.Cin >> 3);
@@ -105,12 +128,18 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
     if (lane == 0) {
       uint32_t e = 0;
       int b, z0, zlen, y0, ylen, x0, xlen;
-      for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen);) {
+      bool live;
+      for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen, live);) {
         for (int px = x0 - 1; px <= x0 + xlen; ++px, ++e) {
           const uint32_t slot = e % kPlaneSlots, use = e / kPlaneSlots;
           if (use > 0) tc::mbar_wait(&plane_empty[slot], (use - 1) & 1);
-          tc::mbar_expect_tx(&plane_full[slot], p.box_bytes * kchunks8);
           uint8_t *dst = planes + (size_t)slot * p.plane_bytes;
+          if constexpr (PAIR) {  // whole-voxel swizzled planes only
+            if (cta_rank == 0) tc::mbar_expect_tx(&plane_full[slot], 2 * p.box_bytes);
+            tc::tma_load_5d_2cta(dst, &tmA, &plane_full[slot], 0, z0 - 1, y0 - 1, px, b);
+            continue;
+          }
+          tc::mbar_expect_tx(&plane_full[slot], p.box_bytes * kchunks8);
           if (p.a_swz) {
             tc::tma_load_5d(dst, &tmA, &plane_full[slot], 0, z0 - 1, y0 - 1, px, b);
           } else {
@@ -125,17 +154,26 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
     if (lane == 0) {
       uint32_t t = 0;
       int b, z0, zlen, y0, ylen, x0, xlen;
-      for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen);) {
+      bool live;
+      const int wrows = (int)(p.btile_bytes >> 8);  // 256-byte rows of the weight map per (tap, half) tile
+      for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen, live);) {
         for (int i = 0; i < xlen; ++i)
           for (int tap = 0; tap < taps; ++tap, ++t) {
             const uint32_t s = t % p.b_stages, use = t / p.b_stages;
             if (use > 0) tc::mbar_wait(&b_empty[s], (use - 1) & 1);
+            if constexpr (PAIR) {
+              if (cta_rank == 0) tc::mbar_expect_tx(&b_full[s], 2 * p.btile_bytes);
+              tc::tma_load_2d_2cta(bt + (size_t)s * p.btile_bytes, &tmW, &b_full[s], 0, (tap * 2 + (int)cta_rank) * wrows);
+              continue;
+            }
             tc::mbar_expect_tx(&b_full[s], p.btile_bytes);
             tc::bulk_g2s(bt + (size_t)s * p.btile_bytes, reinterpret_cast<const uint8_t *>(wB) + (size_t)tap * p.btile_bytes,
                          p.btile_bytes, &b_full[s]);
           }
       }
     }
+  } else if (warp == 5 && cta_rank != 0) {
+    // the odd CTA of a pair issues nothing: the rank-0 CTA's MMAs read this CTA's planes and weights and write its TMEM
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer
     // The whole warp runs the (warp-uniform) control flow so that ptxas keeps descriptors, TMEM addresses and loop
@@ -143,16 +181,25 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
     // (A lane-0-only loop forces per-MMA R2UR transfers and made the issue thread, not the tensor pipe, the limit.)
     {
       const bool leader = tc::elect_one();
-      const uint32_t idesc = tc::make_idesc_bf16(128, p.N, 0, 0);
+      const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 256 : 128, p.N, 0, 0);
       const uint32_t planes_u32 = tc::smem_u32(planes), bt_u32 = tc::smem_u32(bt);
-      const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16, b_lbo = (uint32_t)p.N * 16;
+      const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16, b_lbo = (uint32_t)(PAIR ? p.N >> 1 : p.N) * 16;
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accum) {
+        if constexpr (PAIR) tc::umma_bf16_2cta(d, ad, bd, idesc, accum);
+        else tc::umma_bf16(d, ad, bd, idesc, accum);
+      };
+      auto commit = [&](uint64_t *bar) {
+        if constexpr (PAIR) tc::umma_commit_2cta(bar, 3);
+        else tc::umma_commit(bar);
+      };
       const uint32_t a_row = p.a_swz ? (uint32_t)p.a_swz >> 4 : 1u;  // 16-byte units per activation row
       const uint64_t a_desc_hi = p.a_swz ? tc::make_desc_sw(0, 8u * p.a_swz, (uint32_t)p.a_swz) : tc::make_desc(0, a_lbo, 128);
       const uint64_t b_desc_hi = tc::make_desc(0, b_lbo, 128);
       const uint32_t a_kstep = p.a_swz ? 2u : (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;  // descriptor address units (16 B)
       uint32_t e_base = 0, t = 0, acc = 0;
       int b, z0, zlen, y0, ylen, x0, xlen;
-      for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen);) {
+      bool live;
+      for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen, live);) {
         for (int i = 0; i < xlen; ++i, ++acc) {
           const uint32_t q = acc & 1, uq = acc >> 1;
           if (uq > 0) tc::mbar_wait(&tm_empty[q], (uq - 1) & 1);
@@ -177,20 +224,20 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
                   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                     for (int kk = 0; kk < KSTEPS; ++kk)
-                      tc::umma_bf16(d_tmem0 + mt * p.N, a_desc0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep),
-                                    b_desc0 + (uint64_t)(kk * b_kstep), idesc, (uint32_t)((tap | kk) != 0));
+                      mma(d_tmem0 + mt * p.N, a_desc0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep), b_desc0 + (uint64_t)(kk * b_kstep),
+                          (uint32_t)((tap | kk) != 0));
                   }
-                  tc::umma_commit(&b_empty[s]);
+                  commit(&b_empty[s]);
                 }
                 __syncwarp();
               }
-            if (dx == 0 && leader) tc::umma_commit(&plane_empty[slot]);  // last use of input plane x-1
+            if (dx == 0 && leader) commit(&plane_empty[slot]);  // last use of input plane x-1
           }
-          if (leader) tc::umma_commit(&tm_full[q]);
+          if (leader) commit(&tm_full[q]);
         }
         if (leader) {
-          tc::umma_commit(&plane_empty[(e_base + xlen) % kPlaneSlots]);
-          tc::umma_commit(&plane_empty[(e_base + xlen + 1) % kPlaneSlots]);
+          commit(&plane_empty[(e_base + xlen) % kPlaneSlots]);
+          commit(&plane_empty[(e_base + xlen + 1) % kPlaneSlots]);
         }
         e_base += xlen + 2;
         __syncwarp();
@@ -205,7 +252,8 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
       for (int j = 0; j < 64; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
     }
     int b, z0, zlen, y0, ylen, x0, xlen;
-    for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen);) {
+    bool live;
+    for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen, live);) {
       for (int i = 0; i < xlen; ++i, ++acc) {
         const uint32_t q = acc & 1;
         tc::mbar_wait(&tm_full[q], (acc >> 1) & 1);
@@ -213,7 +261,7 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
         for (int mt = 0; mt < p.mtiles; ++mt) {
           const int r = mt * 128 + warp * 32 + lane;
           const int oy = r / p.Zh, oz = r - oy * p.Zh;
-          const bool valid = oy < ylen && oz < zlen;
+          const bool valid = live && oy < ylen && oz < zlen;
           bf16 *dst = out + ((((size_t)b * p.X + (x0 + i)) * p.Y + (y0 + oy)) * p.Z + (z0 + oz)) * p.N;
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (q * p.mtiles + mt) * p.N;
           auto store_chunk = [&](const uint32_t (&v)[16], int c0) {
@@ -258,7 +306,10 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
         }
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+        if (lane == 0) {
+          if constexpr (PAIR) tc::mbar_arrive_cluster(&tm_empty[q], 0);  // both CTAs' epilogues release the rank-0 issuer
+          else tc::mbar_arrive(&tm_empty[q]);
+        }
       }
     }
     if constexpr (STATS) {  // a thread saw at most a few dozen rows: fp32 partials, fp64 across threads
@@ -275,19 +326,27 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restric
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (PAIR) {
+    tc::cluster_sync();  // neither CTA may retire while the other can still signal its barriers or read its shared memory
+    if (warp == 5) tc::tmem_dealloc2(tmem_base, p.tmem_cols);
+  } else {
+    if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
-// [tap][Cb][Cs] (generic packed) -> [tap'][Cin/8][N][8]; flip = dgrad (reverse taps, swap channel roles)
-__global__ void repack_b_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int taps, int flip) {
-  const int Cin = flip ? Cs : Cb, N = flip ? Cb : Cs;
+// [tap][Cb][Cs] (generic packed) -> [tap'][half][Cin/8][N/nh][8]; flip = dgrad (reverse taps, swap channel roles);
+// nh = 2 splits the output channels into the two halves held by the CTAs of a pair
+__global__ void repack_b_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int taps, int flip, int nh) {
+  const int Cin = flip ? Cs : Cb, N = flip ? Cb : Cs, Nl = N / nh;
   const int64_t total = (int64_t)taps * Cin * N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i & 7);
     int64_t t = i >> 3;
-    const int n = (int)(t % N); t /= N;
-    const int cc = (int)(t % (Cin >> 3));
-    const int tap = (int)(t / (Cin >> 3));
+    const int nl = (int)(t % Nl); t /= Nl;
+    const int cc = (int)(t % (Cin >> 3)); t /= (Cin >> 3);
+    const int h = (int)(t % nh);
+    const int tap = (int)(t / nh);
+    const int n = h * Nl + nl;
     const int ci = cc * 8 + c8;
     const int src_tap = flip ? (taps - 1 - tap) : tap;
     const int cb = flip ? n : ci, cs = flip ? ci : n;
@@ -334,15 +393,23 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
                 cudaStream_t st, double *bn_sums = nullptr);
 bool tc_prog_fuses_bnstats(const cgan3d_conv_geom &g, int scatter);
 
+// CTA pairs need whole-voxel swizzled planes (one TMA box per plane), N/2 a multiple of 16 and 256-byte weight-map rows.
+static bool pair_ok(int Cin, int N) {
+  static int off = -1;
+  if (off < 0) off = getenv("CGAN3D_NO_PAIR") ? 1 : 0;
+  return !off && Cin <= 64 && N % 32 == 0 && (Cin * N) % 256 == 0;
+}
+
 static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
   if (N % 16 || N > 256 || N < 16) return false;
   if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
   TcPlan p{};
   p.B = B; p.X = X; p.Y = Y; p.Z = Z; p.Cin = Cin; p.N = N;
+  p.pair = pair_ok(Cin, N) ? 1 : 0;
   p.nzt = (Z + 61) / 62;
   p.Zt = (Z + p.nzt - 1) / p.nzt;
   p.Zh = p.Zt + 2;
-  p.btile_bytes = (uint32_t)Cin * N * 2;
+  p.btile_bytes = (uint32_t)Cin * N * 2 / (p.pair ? 2 : 1);
   p.b_stages = p.btile_bytes <= 8192 ? 4 : (p.btile_bytes <= 16384 ? 3 : 2);
   double best_eff = 0;
   bool found = false;
@@ -439,7 +506,7 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   bf16 *wb = reinterpret_cast<bf16 *>(ws);
-  repack_b_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, 27, flip);
+  repack_b_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, 27, flip, p.pair ? 2 : 1);
   CG_LAUNCH_CHECK("repack_b");
   CUtensorMap tm;
   const cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)p.Z, (cuuint64_t)p.Y, (cuuint64_t)p.X, (cuuint64_t)p.B};
@@ -453,25 +520,56 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, tc_l2_promo(),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  const int grid = (int)mn<long long>((long long)p.nitems * p.X, (long long)num_sms());
+  CUtensorMap tmw{};
+  if (p.pair) {  // the repacked weights as rows of 256 bytes: one (tap, half) tile is btile_bytes / 256 rows
+    const cuuint64_t wdim[2] = {64, (cuuint64_t)(27 * 2) * (p.btile_bytes >> 8)};
+    const cuuint64_t wstr[1] = {256};
+    const cuuint32_t wbox[2] = {64, (cuuint32_t)(p.btile_bytes >> 8)};
+    r = enc(&tmw, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, wb, wdim, wstr, wbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (weights) failed with %d", (int)r);
+  }
+  const long long work = (long long)(p.pair ? (p.nitems + 1) / 2 : p.nitems) * p.X;
+  const int grid = p.pair ? 2 * (int)mn<long long>(work, (long long)(num_sms() / 2)) : (int)mn<long long>(work, (long long)num_sms());
   if (bn_sums && N > 64) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: fused BatchNorm statistics need Cout <= 64");
-  auto launch_s = [&](auto ks_tag, auto mt_tag, auto st_tag) -> int {
+  auto launch_s = [&](auto ks_tag, auto mt_tag, auto st_tag, auto pair_tag) -> int {
     constexpr int KS = decltype(ks_tag)::value;
     constexpr int MT = decltype(mt_tag)::value;
     constexpr bool ST = decltype(st_tag)::value;
+    constexpr bool PR = decltype(pair_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_s1_tc_kernel<KS, MT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(conv_s1_tc_kernel<KS, MT, ST, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemLimit + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_s1_tc_kernel)");
       attr_set = true;
     }
-    conv_s1_tc_kernel<KS, MT, ST><<<grid, kThreads, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p, bn_sums);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = p.smem_bytes + 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_s1_tc_kernel<KS, MT, ST, PR>, tm, tmw, (const bf16 *)wb, reinterpret_cast<bf16 *>(outp), p,
+                                       bn_sums);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_s1_tc_kernel launch");
     CG_LAUNCH_CHECK("conv_s1_tc_kernel");
     return 0;
   };
   auto launch = [&](auto ks_tag, auto mt_tag) -> int {
-    return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}) : launch_s(ks_tag, mt_tag, std::false_type{});
+    if (p.pair) {
+      if constexpr (decltype(ks_tag)::value <= 4)
+        return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}, std::true_type{}) : launch_s(ks_tag, mt_tag, std::false_type{}, std::true_type{});
+      else
+        return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: CTA pairs need Cin <= 64");
+    }
+    return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}, std::false_type{}) : launch_s(ks_tag, mt_tag, std::false_type{}, std::false_type{});
   };
   auto by_mt = [&](auto ks_tag) -> int {
     switch (p.mtiles) {

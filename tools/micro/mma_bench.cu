@@ -58,7 +58,7 @@ int main() {
   printf("M N nacc sw a_stride cycles_per_mma\n");
   for (int M : {128, 64})
     for (int sw : {0, 32, 128})
-      for (int N : {16, 32, 64, 128, 256})
+      for (int N : {16, 32, 64, 96, 128, 192, 256})
         for (int nacc : {1, 2, 8})
           for (int astr : {0, 128}) {
             if (nacc * N > 512) continue;
