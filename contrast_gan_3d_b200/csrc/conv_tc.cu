@@ -433,6 +433,12 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
   }
   if (!found) return false;
   TcPlan &q = best;
+  {  // a deeper weight ring when shared memory is left over: one tap is consumed in mtiles * Cin/16 MMAs (~600 cycles for a
+     // CTA pair at Cin = 64), well below the L2 latency of the next tile
+    static int max_stages = -1;
+    if (max_stages < 0) { const char *e = getenv("CGAN3D_B_STAGES"); max_stages = e ? atoi(e) : 12; }
+    while (q.b_stages < max_stages && q.smem_bytes + q.btile_bytes <= kSmemLimit) { q.b_stages += 1; q.smem_bytes += q.btile_bytes; }
+  }
   q.a_swz = Cin <= 64 ? 2 * Cin : 0;
   q.box_bytes = (q.a_swz ? (uint32_t)q.a_swz : 16u) * q.Zh * q.Yh;
   uint32_t cols = 32;

@@ -37,39 +37,61 @@ struct ThinAPlan {
   int Zc;         // z extent of the two shifted copies: copy[s][row][c] = in[row][c - 8 + zshift[s]]
   int zshift[2];
   int debug;
+  int pair;       // CTA pairs (cta_group::2): consecutive work items go to the two CTAs, each holds half of the N rows
 };
 
-template <int MT, bool STATS>
+// PAIR: see conv_tc.cu — the two CTAs of a cluster process consecutive work items in lockstep; each holds the Toeplitz
+// rows of two of the four output z (32 of the 64 N rows), and the rank-0 CTA issues every MMA for both.
+template <int MT, bool STATS, bool PAIR>
 __global__ void __launch_bounds__(192, 1)
-conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wT, bf16 *__restrict__ out,
-                   const __grid_constant__ ThinAPlan p, double *__restrict__ bn_sums) {
+conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const bf16 *__restrict__ wT,
+                   bf16 *__restrict__ out, const __grid_constant__ ThinAPlan p, double *__restrict__ bn_sums) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t kTileB = PAIR ? kTileBytesA / 2 : kTileBytesA;
+  // accumulator ring: with one M tile per item an item is only ~2 us of MMAs, so the MMA -> epilogue -> MMA hand-off
+  // latency must be hidden behind several buffers (all 512 TMEM columns are used)
+  constexpr uint32_t NACC = 512 / (MT * 64);
   uint8_t *bres = smem;                                    // 49 resident Toeplitz tiles
-  uint8_t *ring = bres + kTapTilesA * kTileBytesA;         // slab slots
-  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)p.nslots * p.slot_bytes);
+  uint8_t *ring = bres + kTapTilesA * kTileB;              // slab slots
+  uint8_t *stage = ring + (size_t)p.nslots * p.slot_bytes; // epilogue store staging: 4 warps x 32 rows x 128 B
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 16384);
   uint64_t *b_ready = bars, *s_full = bars + 1, *s_empty = s_full + p.nslots;
-  uint64_t *tm_full = s_empty + p.nslots, *tm_empty = tm_full + 2;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tm_empty + 2);
+  uint64_t *tm_full = s_empty + p.nslots, *tm_empty = tm_full + NACC;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tm_empty + NACC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     tc::mbar_init(b_ready, 1);
     for (int i = 0; i < p.nslots; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    for (int i = 0; i < (int)NACC; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], PAIR ? 8 : 4); }
     tc::fence_barrier_init();
   }
+  const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
+  if constexpr (PAIR) {
+    __syncthreads();
+    tc::cluster_sync();
+  }
   if (warp == 5) {
-    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
-    tc::tmem_relinquish();
+    if constexpr (PAIR) { tc::tmem_alloc2(tmem_ptr, p.tmem_cols); tc::tmem_relinquish2(); }
+    else { tc::tmem_alloc(tmem_ptr, p.tmem_cols); tc::tmem_relinquish(); }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) tc::cluster_sync();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const long long total = (long long)p.B * p.nxt * p.nyt * p.nzb;
-  const int i_begin = (int)(total * blockIdx.x / gridDim.x), i_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
-  auto decode = [&](int it, int &b, int &x0, int &xlen, int &y0, int &ylen, int &z0) {
+  // work items: PAIR -> the pair walks item pairs (2j, 2j+1); an odd total leaves the last odd CTA a dead copy of item 2j
+  const long long total_items = (long long)p.B * p.nxt * p.nyt * p.nzb;
+  const long long total = PAIR ? (total_items + 1) / 2 : total_items;
+  const int nblk = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x, blk = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+  const int i_begin = (int)(total * blk / nblk), i_end = (int)(total * (blk + 1) / nblk);
+  auto decode = [&](int it, int &b, int &x0, int &xlen, int &y0, int &ylen, int &z0) -> bool {
+    bool live = true;
+    if constexpr (PAIR) {
+      it = 2 * it + (int)cta_rank;
+      if (it >= total_items) { it = (int)total_items - 1; live = false; }
+    }
     const int zb = it % p.nzb; it /= p.nzb;
     const int yt = it % p.nyt; it /= p.nyt;
     const int xt = it % p.nxt;
@@ -77,15 +99,21 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
     x0 = xt * p.Xt; xlen = min(p.Xt, p.Xo - x0);
     y0 = yt * p.Yt; ylen = min(p.Yt, p.Yo - y0);
     z0 = zb * 4;
+    return live;
   };
 
   if (warp == 4) {
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmA);
-      tc::mbar_expect_tx(b_ready, kTapTilesA * kTileBytesA);
-      for (int t = 0; t < kTapTilesA; ++t)
-        tc::bulk_g2s(bres + (size_t)t * kTileBytesA, reinterpret_cast<const uint8_t *>(wT) + (size_t)t * kTileBytesA, kTileBytesA,
-                     b_ready);
+      if constexpr (PAIR) {  // one box per CTA: its 49 half tiles (49 KB as 196 rows of 256 bytes), counted on the rank-0 barrier
+        if (cta_rank == 0) tc::mbar_expect_tx(b_ready, 2 * kTapTilesA * kTileB);
+        tc::tma_load_2d_2cta(bres, &tmW, b_ready, 0, (int)cta_rank * (int)(kTapTilesA * kTileB / 256));
+      } else {
+        tc::mbar_expect_tx(b_ready, kTapTilesA * kTileBytesA);
+        for (int t = 0; t < kTapTilesA; ++t)
+          tc::bulk_g2s(bres + (size_t)t * kTileBytesA, reinterpret_cast<const uint8_t *>(wT) + (size_t)t * kTileBytesA, kTileBytesA,
+                       b_ready);
+      }
       uint32_t e = 0;
       for (int it = i_begin; it < i_end; ++it, ++e) {
         int b, x0, xlen, y0, ylen, z0;
@@ -93,49 +121,66 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
         const uint32_t slot = e % p.nslots, use = e / p.nslots;
         if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
         uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
-        if (p.debug & 1) { tc::mbar_arrive(&s_full[slot]); continue; }
-        tc::mbar_expect_tx(&s_full[slot], p.box_bytes);
         // TMA needs a 16-byte aligned start along z: block parity selects the copy whose z shift makes it so
         const int cp = (z0 >> 2) & 1;
         const int c0 = z0 - p.P - p.zshift[cp] + 8;
+        if constexpr (PAIR) {
+          if (cta_rank == 0) tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
+          tc::tma_load_5d_2cta(dst, &tmA, &s_full[slot], c0, y0 - p.P, x0 - p.P, b, cp);
+          continue;
+        }
+        if (p.debug & 1) { tc::mbar_arrive(&s_full[slot]); continue; }
+        tc::mbar_expect_tx(&s_full[slot], p.box_bytes);
         tc::tma_load_5d(dst, &tmA, &s_full[slot], c0, y0 - p.P, x0 - p.P, b, cp);  // rows of 16 z = 32 bytes, SWIZZLE_32B
       }
     }
+  } else if (warp == 5 && cta_rank != 0) {
+    // odd CTA of a pair: the rank-0 CTA issues the MMAs for both
   } else if (warp == 5) {
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 256 : 128, 64, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
-    const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc(0, 64 * 16, 128);
+    const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc(0, (PAIR ? 32 : 64) * 16, 128);
     tc::mbar_wait(b_ready, 0);
     tc::tc_fence_after();
     uint32_t e = 0;
     for (int it = i_begin; it < i_end; ++it, ++e) {
-      const uint32_t q = e & 1, uq = e >> 1, slot = e % p.nslots;
+      const uint32_t q = e % NACC, uq = e / NACC, slot = e % p.nslots;
       if (uq > 0) tc::mbar_wait(&tm_empty[q], (uq - 1) & 1);
       tc::mbar_wait(&s_full[slot], (e / p.nslots) & 1);
       tc::tc_fence_after();
       const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
       const uint32_t d_base = tmem_base + q * (uint32_t)(MT * 64);
+      // lean issue loop: the seven dy taps of one dx go out back to back with descriptor adds only (a loop iteration
+      // per MMA costs ~120 cycles of dependent scalar work on the single issuing warp, more than the MMA itself)
+      const uint64_t a_it = a_hi | (uint64_t)(a_slot & 0x3FFF), b_it = b_hi | (uint64_t)((b_u32 >> 4) & 0x3FFF);
       for (int dx = 0; dx < 7; ++dx) {
-        for (int dy = 0; dy < 7; ++dy) {
-          const int tap = dx * 7 + dy;
-          const uint64_t a0 = a_hi | (uint64_t)((a_slot + 2u * (uint32_t)(dx * p.Yh + dy)) & 0x3FFF);  // 32-byte rows
-          const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)tap * kTileBytesA) >> 4) & 0x3FFF);
-          if (leader && !(p.debug & 2)) {
+        const uint64_t a_dx = a_it + (uint64_t)(2u * (uint32_t)(dx * p.Yh));             // 32-byte rows
+        const uint64_t b_dx = b_it + (uint64_t)((uint32_t)(dx * 7) * (kTileB >> 4));
+        if (leader && !(p.debug & 2)) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 64, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(tap != 0));
+          for (int dy = 0; dy < 7; ++dy) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t accum = dy != 0 ? 1u : (uint32_t)(dx != 0);
+              if constexpr (PAIR)
+                tc::umma_bf16_2cta(d_base + mt * 64, a_dx + (uint64_t)(2 * dy + mt * 256), b_dx + (uint64_t)(dy * (kTileB >> 4)), idesc, accum);
+              else
+                tc::umma_bf16(d_base + mt * 64, a_dx + (uint64_t)(2 * dy + mt * 256), b_dx + (uint64_t)(dy * (kTileB >> 4)), idesc, accum);
+            }
           }
-          __syncwarp();
         }
+        __syncwarp();
       }
       if (leader) {
-        tc::umma_commit(&s_empty[slot]);
-        tc::umma_commit(&tm_full[q]);
+        if constexpr (PAIR) { tc::umma_commit_2cta(&s_empty[slot], 3); tc::umma_commit_2cta(&tm_full[q], 3); }
+        else { tc::umma_commit(&s_empty[slot]); tc::umma_commit(&tm_full[q]); }
       }
       __syncwarp();
     }
   } else {
     uint32_t e = 0;
+    uint4 *stage_w = reinterpret_cast<uint4 *>(stage) + warp * 256;  // this warp's 32 rows x 128 B
     float ssum[STATS ? 16 : 1], ssq[STATS ? 16 : 1];  // per-channel BatchNorm partial sums of this thread's rows
     if (STATS) {
 #pragma unroll
@@ -143,34 +188,37 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
     }
     for (int it = i_begin; it < i_end; ++it, ++e) {
       int b, x0, xlen, y0, ylen, z0;
-      decode(it, b, x0, xlen, y0, ylen, z0);
-      const uint32_t q = e & 1;
-      tc::mbar_wait(&tm_full[q], (e >> 1) & 1);
+      const bool live = decode(it, b, x0, xlen, y0, ylen, z0);
+      const uint32_t q = e % NACC;
+      tc::mbar_wait(&tm_full[q], (e / NACC) & 1);
       tc::tc_fence_after();
       const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(MT * 64);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         const int r = mt * 128 + warp * 32 + lane;
         const int xx = r / p.Yh, yy = r - xx * p.Yh;
-        const bool valid = xx < xlen && yy < ylen;
+        const bool valid = live && xx < xlen && yy < ylen && !(p.debug & 4);
         bf16 *dst = out + ((((size_t)b * p.Xo + (x0 + xx)) * p.Yo + (y0 + yy)) * p.Zo + z0) * 16;
         uint32_t v[4][16];  // the four output z of this row: all TMEM loads in flight before one wait
 #pragma unroll
         for (int zo = 0; zo < 4; ++zo) tc::tmem_ld16(d_base + (uint32_t)(mt * 64 + zo * 16), v[zo]);
         tc::tmem_ld_wait();
+        // A lane owns one (x,y) row = 128 contiguous output bytes, but neighbouring lanes are a whole z line (4 KB) apart:
+        // direct stores would be 32 quarter-line writes per instruction.  Stage the warp's 32 x 128 B in shared memory
+        // (16-byte chunks XOR-swizzled by row, conflict-free both ways) and store full 128-byte lines, 4 rows per instruction.
+        __syncwarp();
 #pragma unroll
         for (int zo = 0; zo < 4; ++zo) {
-          if (valid && z0 + zo < p.Zo) {
-            uint32_t pk[8];
+          uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[zo][2 * j]), __uint_as_float(v[zo][2 * j + 1]));
-              pk[j] = *reinterpret_cast<uint32_t *>(&h);
-            }
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst + zo * 16);
-            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            if constexpr (STATS) {
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[zo][2 * j]), __uint_as_float(v[zo][2 * j + 1]));
+            pk[j] = *reinterpret_cast<uint32_t *>(&h);
+          }
+          stage_w[lane * 8 + ((2 * zo) ^ (lane & 7))] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          stage_w[lane * 8 + ((2 * zo + 1) ^ (lane & 7))] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if constexpr (STATS) {
+            if (valid && z0 + zo < p.Zo) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float f = __uint_as_float(v[zo][j]);
@@ -180,10 +228,23 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
             }
           }
         }
+        __syncwarp();
+        const unsigned long long dst_u = reinterpret_cast<unsigned long long>(dst);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3), ch = lane & 7;
+          const unsigned long long d_row = __shfl_sync(0xffffffffu, dst_u, row);
+          const bool v_row = __shfl_sync(0xffffffffu, (int)valid, row) != 0;
+          const uint4 val = stage_w[row * 8 + (ch ^ (row & 7))];
+          if (v_row && z0 + (ch >> 1) < p.Zo) reinterpret_cast<uint4 *>(d_row)[ch] = val;
+        }
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+      if (lane == 0) {
+        if constexpr (PAIR) tc::mbar_arrive_cluster(&tm_empty[q], 0);
+        else tc::mbar_arrive(&tm_empty[q]);
+      }
     }
     if constexpr (STATS) {
 #pragma unroll
@@ -195,19 +256,33 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restri
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (PAIR) {
+    tc::cluster_sync();
+    if (warp == 5) tc::tmem_dealloc2(tmem_base, p.tmem_cols);
+  } else {
+    if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 // Toeplitz tiles: T[(dx,dy)][zi/8][n = zo*16 + co][zi%8] = w(dx,dy,zi-zo,co) for 0 <= zi-zo < 7, else 0.
 // wp is the packed filter [tap][Cb][Cs] with Cb*Cs == 16; flip = 1 reverses the taps (transposed convolution).
-__global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip) {
+// split = 1 (CTA pairs): [half][(dx,dy)][zi/8][32 n][8], half = n / 32.
+__global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip, int split) {
   const int total = kTapTilesA * 2 * 64 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int z8 = i & 7;
     int t = i >> 3;
-    const int n = t & 63; t >>= 6;
-    const int chunk = t & 1;
-    const int tile = t >> 1;
+    int n, chunk, tile;
+    if (split) {
+      const int nl = t & 31; t >>= 5;
+      chunk = t & 1; t >>= 1;
+      tile = t % kTapTilesA;
+      n = (t / kTapTilesA) * 32 + nl;
+    } else {
+      n = t & 63; t >>= 6;
+      chunk = t & 1;
+      tile = t >> 1;
+    }
     const int zi = chunk * 8 + z8, zo = n >> 4, co = n & 15, dz = zi - zo;
     bf16 v = __float2bfloat16_rn(0.f);
     if (dz >= 0 && dz < 7) {
@@ -692,6 +767,18 @@ static int encode_map(CUtensorMap *tm, const void *ptr, int rank, const cuuint64
   return 0;
 }
 
+// un-swizzled map of an arbitrary element type (weight tiles viewed as rows of 256 bytes)
+static int encode_map_raw(CUtensorMap *tm, const void *ptr, CUtensorMapDataType dt, int rank, const cuuint64_t *gdim, const cuuint64_t *gstr,
+                          const cuuint32_t *box) {
+  EncodeTiledFnT enc = reinterpret_cast<EncodeTiledFnT>(tc_encode_fn_ptr());
+  if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, dt, (cuuint32_t)rank, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (weight tiles) failed with %d", (int)r);
+  return 0;
+}
+
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // op 0: gather with Cb == 1, Cs == 16 (valid conv, P = pad);  op 1: scatter with Cb == 16, Cs == 1 (P = 6 - pad)
@@ -712,7 +799,12 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
   p.zshift[0] = ((0 - p.P) % 8 + 8) % 8;
   p.zshift[1] = ((4 - p.P) % 8 + 8) % 8;
   p.Zc = round_up(p.Zi + 16, 8);
-  const uint32_t fixed = kTapTilesA * kTileBytesA + 512;
+  {
+    static int off = -1;
+    if (off < 0) off = getenv("CGAN3D_NO_PAIR") ? 1 : 0;
+    p.pair = off ? 0 : 1;
+  }
+  const uint32_t fixed = kTapTilesA * kTileBytesA / (p.pair ? 2 : 1) + 16384 + 512;  // Toeplitz tiles, store staging, barriers
   double best_score = 0;
   bool found = false;
   for (int nyt = 1; nyt <= p.Yo; ++nyt) {
@@ -730,7 +822,9 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
       const int nxt = (p.Xo + Xt - 1) / Xt;
       const double eff = (double)p.Xo * p.Yo / ((double)nxt * nyt * mt * 128);
       const double halo = (double)(Xh * Yh) / (Xt * Yt);
-      const double score = eff / (1.0 + 0.02 * halo) * (nslots >= 3 ? 1.0 : 0.8);
+      static double halo_w = -1;
+      if (halo_w < 0) { const char *e = getenv("CGAN3D_THIN_HALO_W"); halo_w = e ? atof(e) : 0.05; }
+      const double score = eff / (1.0 + halo_w * halo) * (nslots >= 3 ? 1.0 : 0.8);
       if (score > best_score + 1e-9) {
         best_score = score; found = true;
         best = p;
@@ -742,9 +836,7 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
   }
   if (!found) return false;
   best.box_bytes = 32u * best.Yh * best.Xh;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * best.mtiles * 64)) cols <<= 1;
-  best.tmem_cols = cols;
+  best.tmem_cols = 512;  // a ring of 512 / (mtiles * 64) accumulator buffers
   best.smem_bytes = fixed + best.nslots * best.slot_bytes;
   return true;
 }
@@ -822,7 +914,7 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255))
     return fail(CGAN3D_E_ARG, "tcgen05 thin conv: pointers must be 16-byte aligned (workspace 256)");
   bf16 *wt = reinterpret_cast<bf16 *>(ws);
-  toeplitz_a_kernel<<<49, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op);
+  toeplitz_a_kernel<<<49, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op, p.pair);
   CG_LAUNCH_CHECK("toeplitz_a");
   bf16 *rp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kTapTilesA * kTileBytesA + 256);
   const long long rows = (long long)p.B * p.Xi * p.Yi;
@@ -836,23 +928,46 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   const cuuint32_t box[5] = {16, (cuuint32_t)p.Yh, (cuuint32_t)p.Xh, 1, 1};
   int r = encode_map(&tm, rp, 5, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_32B);
   if (r) return r;
+  CUtensorMap tmw{};
+  if (p.pair) {  // the Toeplitz tiles as rows of 256 bytes: 196 rows per CTA half
+    const cuuint64_t wdim[2] = {64, (cuuint64_t)(kTapTilesA * kTileBytesA / 256)};
+    const cuuint64_t wstr[1] = {256};
+    const cuuint32_t wbox[2] = {64, (cuuint32_t)(kTapTilesA * kTileBytesA / 512)};
+    r = encode_map_raw(&tmw, wt, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, wdim, wstr, wbox);
+    if (r) return r;
+  }
   const long long total = (long long)p.B * p.nxt * p.nyt * p.nzb;
-  const int grid = (int)mn<long long>(total, (long long)num_sms());
-  auto launch_s = [&](auto mt_tag, auto st_tag) -> int {
+  const int grid = p.pair ? 2 * (int)mn<long long>((total + 1) / 2, (long long)(num_sms() / 2)) : (int)mn<long long>(total, (long long)num_sms());
+  auto launch_s = [&](auto mt_tag, auto st_tag, auto pair_tag) -> int {
     constexpr int MT = decltype(mt_tag)::value;
     constexpr bool ST = decltype(st_tag)::value;
+    constexpr bool PR = decltype(pair_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv7_c1_tc_kernel<MT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
+      cudaError_t e = cudaFuncSetAttribute(conv7_c1_tc_kernel<MT, ST, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv7_c1_tc_kernel)");
       attr_set = true;
     }
-    conv7_c1_tc_kernel<MT, ST><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p, bn_sums);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = p.smem_bytes + 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv7_c1_tc_kernel<MT, ST, PR>, tm, tmw, (const bf16 *)wt, reinterpret_cast<bf16 *>(outp), p, bn_sums);
+    if (e != cudaSuccess) return cuda_fail(e, "conv7_c1_tc_kernel launch");
     CG_LAUNCH_CHECK("conv7_c1_tc_kernel");
     return 0;
   };
   auto launch = [&](auto mt_tag) -> int {
-    return bn_sums ? launch_s(mt_tag, std::true_type{}) : launch_s(mt_tag, std::false_type{});
+    if (p.pair) return bn_sums ? launch_s(mt_tag, std::true_type{}, std::true_type{}) : launch_s(mt_tag, std::false_type{}, std::true_type{});
+    return bn_sums ? launch_s(mt_tag, std::true_type{}, std::false_type{}) : launch_s(mt_tag, std::false_type{}, std::false_type{});
   };
   switch (p.mtiles) {
     case 1: return launch(std::integral_constant<int, 1>{});
