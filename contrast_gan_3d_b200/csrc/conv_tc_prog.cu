@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "conv_internal.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace cg {
 
@@ -69,14 +70,17 @@ struct ProgPlan {
   int Nmma;                      // N of one MMA (N, or 8*N when stacked)
   int acc_stride, mt_stride;     // TMEM columns between accumulators (phases) / between M-tiles
   int8_t tile_phase_tap[kMaxTaps][8];
+  int pair;                      // 1: CTA pairs (cta_group::2); btile_bytes is then the HALF tile (Nmma/2 rows) held by one CTA
 };
 
 // STATS: the epilogue also accumulates the per-channel sum / sum of squares of the fp32 accumulators (BatchNorm batch
 // statistics, reference model/blocks.py:45) into bn_sums (fp64 [2 * out_pitch], Nout <= 64).
-template <int KSTEPS, int MT, bool STATS>
+// PAIR: CTA pairs as in conv_tc.cu -- the two CTAs of a cluster process consecutive steps in lockstep, each holds half of
+// the rows of every resident filter tile, the rank-0 CTA issues the MMAs of both.
+template <int KSTEPS, int MT, bool STATS, bool PAIR>
 __global__ void __launch_bounds__(192, 1)
-conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wB, bf16 *__restrict__ out,
-                    const __grid_constant__ ProgPlan p, double *__restrict__ bn_sums) {
+conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const bf16 *__restrict__ wB,
+                    bf16 *__restrict__ out, const __grid_constant__ ProgPlan p, double *__restrict__ bn_sums) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *bres = smem;                                         // resident filter tiles
   uint8_t *ring = bres + (((size_t)p.nbt * p.btile_bytes + 1023) & ~(size_t)1023);  // activation slab slots (1024-aligned)
@@ -89,39 +93,62 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   if (threadIdx.x == 0) {
     tc::mbar_init(b_ready, 1);
     for (int i = 0; i < p.nslots; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], PAIR ? 8 : 4); }
     tc::fence_barrier_init();
   }
+  const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
+  if constexpr (PAIR) {
+    __syncthreads();
+    tc::cluster_sync();
+  }
   if (warp == 5) {
-    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
-    tc::tmem_relinquish();
+    if constexpr (PAIR) { tc::tmem_alloc2(tmem_ptr, p.tmem_cols); tc::tmem_relinquish2(); }
+    else { tc::tmem_alloc(tmem_ptr, p.tmem_cols); tc::tmem_relinquish(); }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) tc::cluster_sync();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // contiguous, balanced range of steps (column-major over (b, z-tile, y-slab) x output plane)
-  const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
-  const int s_begin = (int)(total * blockIdx.x / gridDim.x), s_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  // contiguous, balanced range of steps (column-major over (b, z-tile, y-slab) x output plane); a CTA pair walks step
+  // pairs (2j, 2j+1), an odd step count leaves the last odd CTA a dead copy of step 2j
+  const long long total_steps = (long long)p.B * p.nzt * p.nslabs * p.Xg;
+  const long long total = PAIR ? (total_steps + 1) / 2 : total_steps;
+  const int nblk = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x, blk = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+  const int s_begin = (int)(total * blk / nblk), s_end = (int)(total * (blk + 1) / nblk);
   const int kch = (p.paired || p.a_swz) ? 1 : (p.Cin >> 3);
-  auto decode = [&](int st, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x) {
+  auto decode = [&](int st, int &b, int &z0, int &zlen, int &y0, int &ylen, int &x) -> bool {
+    bool live = true;
+    if constexpr (PAIR) {
+      st = 2 * st + (int)cta_rank;
+      if (st >= total_steps) { st = (int)total_steps - 1; live = false; }
+    }
     x = st % p.Xg; st /= p.Xg;
     const int sl = st % p.nslabs; st /= p.nslabs;
     const int zt = st % p.nzt;
     b = st / p.nzt;
     y0 = sl * p.Yt; ylen = min(p.Yt, p.Yg - y0);
     z0 = zt * p.Zt; zlen = min(p.Zt, p.Zg - z0);
+    return live;
   };
 
   if (warp == 4) {
     // ------------------------------------------------ producer: resident filters once, then the slab stream
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmA);
-      tc::mbar_expect_tx(b_ready, (uint32_t)p.nbt * p.btile_bytes);
-      for (int t = 0; t < p.nbt; ++t)
-        tc::bulk_g2s(bres + (size_t)t * p.btile_bytes, reinterpret_cast<const uint8_t *>(wB) + (size_t)t * p.btile_bytes,
-                     p.btile_bytes, b_ready);
+      if constexpr (PAIR) {  // this CTA's half tiles, byte counts on the rank-0 barrier
+        tc::tma_prefetch_desc(&tmW);
+        if (cta_rank == 0) tc::mbar_expect_tx(b_ready, 2u * (uint32_t)p.nbt * p.btile_bytes);
+        const int trows = (int)(p.btile_bytes >> 8);
+        for (int t = 0; t < p.nbt; ++t)
+          tc::tma_load_2d_2cta(bres + (size_t)t * p.btile_bytes, &tmW, b_ready, 0, ((int)cta_rank * p.nbt + t) * trows);
+      } else {
+        tc::mbar_expect_tx(b_ready, (uint32_t)p.nbt * p.btile_bytes);
+        for (int t = 0; t < p.nbt; ++t)
+          tc::bulk_g2s(bres + (size_t)t * p.btile_bytes, reinterpret_cast<const uint8_t *>(wB) + (size_t)t * p.btile_bytes,
+                       p.btile_bytes, b_ready);
+      }
       uint32_t e = 0;
       for (int st = s_begin; st < s_end; ++st) {
         int b, z0, zlen, y0, ylen, x;
@@ -130,9 +157,14 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           const ProgEntry &E = p.entries[en];
           const uint32_t slot = e % p.nslots, use = e / p.nslots;
           if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
-          tc::mbar_expect_tx(&s_full[slot], p.box_bytes * kch);
           uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
           const int cz = p.in_scale * z0 + E.cz, cy = p.in_scale * y0 + E.cy, cx = p.in_scale * x + E.cx;
+          if constexpr (PAIR) {  // one box per slab (swizzled whole voxels, or the 8-channel critic slabs)
+            if (cta_rank == 0) tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
+            tc::tma_load_5d_2cta(dst, &tmA, &s_full[slot], 0, cz, cy, cx, b);
+            continue;
+          }
+          tc::mbar_expect_tx(&s_full[slot], p.box_bytes * kch);
           if (p.a_swz) {
             tc::tma_load_5d(dst, &tmA, &s_full[slot], 0, cz, cy, cx, b);
           } else {
@@ -142,12 +174,18 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         }
       }
     }
+  } else if (warp == 5 && cta_rank != 0) {
+    // odd CTA of a pair: the rank-0 CTA issues the MMAs of both
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(128, p.Nmma, 0, 0);
+    const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 256 : 128, p.Nmma, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
-    const uint32_t a_lbo = p.a_lbo_bytes, b_lbo = (uint32_t)p.Nmma * 16;
+    const uint32_t a_lbo = p.a_lbo_bytes, b_lbo = (uint32_t)(PAIR ? p.Nmma >> 1 : p.Nmma) * 16;
+    auto commit = [&](uint64_t *bar) {
+      if constexpr (PAIR) tc::umma_commit_2cta(bar, 3);
+      else tc::umma_commit(bar);
+    };
     const uint32_t a_row = p.a_swz ? (uint32_t)p.a_swz >> 4 : 1u;  // 16-byte units per activation row
     const uint64_t a_hi = p.a_swz ? tc::make_desc_sw(0, 8u * p.a_swz, (uint32_t)p.a_swz) : tc::make_desc(0, a_lbo, 128);
     const uint64_t b_hi = tc::make_desc(0, b_lbo, 128);
@@ -176,17 +214,22 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-              for (int kk = 0; kk < KSTEPS; ++kk)
-                tc::umma_bf16(d0 + mt * p.mt_stride, a0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep), b0 + (uint64_t)(kk * b_kstep), idesc,
-                              (kk != 0) ? 1u : keep);
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                if constexpr (PAIR)
+                  tc::umma_bf16_2cta(d0 + mt * p.mt_stride, a0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep), b0 + (uint64_t)(kk * b_kstep),
+                                     idesc, (kk != 0) ? 1u : keep);
+                else
+                  tc::umma_bf16(d0 + mt * p.mt_stride, a0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep), b0 + (uint64_t)(kk * b_kstep), idesc,
+                                (kk != 0) ? 1u : keep);
+              }
             }
           }
           __syncwarp();
         }
-        if (leader) tc::umma_commit(&s_empty[slot]);
+        if (leader) commit(&s_empty[slot]);
         __syncwarp();
       }
-      if (leader) tc::umma_commit(&tm_full[q]);
+      if (leader) commit(&tm_full[q]);
       __syncwarp();
     }
   } else {
@@ -199,7 +242,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
     }
     for (int st = s_begin; st < s_end; ++st, ++acc) {
       int b, z0, zlen, y0, ylen, x;
-      decode(st, b, z0, zlen, y0, ylen, x);
+      const bool live = decode(st, b, z0, zlen, y0, ylen, x);
       const uint32_t q = acc & 1;
       tc::mbar_wait(&tm_full[q], (acc >> 1) & 1);
       tc::tc_fence_after();
@@ -212,7 +255,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         const int r = mt * 128 + warp * 32 + lane;
         const int gy = r / p.Zh, gz = r - gy * p.Zh;
         const int oy = p.out_scale * (y0 + gy) + py, oz = p.out_scale * (z0 + gz) + pz;
-        if (!(gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo)) return;
+        if (!(live && gy < ylen && gz < zlen && ox < p.Xo && oy < p.Yo && oz < p.Zo)) return;
         bf16 *dst = out + ((((size_t)b * p.Xo + ox) * p.Yo + oy) * p.Zo + oz) * p.out_pitch + p.out_c0 + cc * 16;
         uint32_t pk[8];
 #pragma unroll
@@ -253,7 +296,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
               tc::tmem_ld_wait();
               const int r = mt * 128 + warp * 32 + lane;
               const int gy = r / p.Zh, gz = r - gy * p.Zh;
-              if (gy < ylen && gz < zlen && x < p.Xo && y0 + gy < p.Yo && z0 + gz < p.Zo) {
+              if (live && gy < ylen && gz < zlen && x < p.Xo && y0 + gy < p.Yo && z0 + gz < p.Zo) {
                 bf16 *dst = out + ((((size_t)b * p.Xo + x) * p.Yo + (y0 + gy)) * p.Zo + (z0 + gz)) * p.out_pitch + p.out_c0 + c0;
                 uint32_t pk[8];
 #pragma unroll
@@ -289,7 +332,10 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+      if (lane == 0) {
+        if constexpr (PAIR) tc::mbar_arrive_cluster(&tm_empty[q], 0);
+        else tc::mbar_arrive(&tm_empty[q]);
+      }
     }
     if constexpr (STATS) {  // a thread saw at most a few dozen rows: fp32 partials, fp64 across threads
       warp_reduce64(ssum, lane);
@@ -305,7 +351,12 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (PAIR) {
+    tc::cluster_sync();
+    if (warp == 5) tc::tmem_dealloc2(tmem_base, p.tmem_cols);
+  } else {
+    if (warp == 5) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 // [tap][Cb][Cs] (generic packed) -> resident tiles [tile][K/8][N][8]; gather: Cin=Cb, Nout=Cs; scatter: Cin=Cs, Nout=Cb.
@@ -313,14 +364,16 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
 // Columns n >= Nout are zero.
 __global__ void repack_prog_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wb, int Cb, int Cs, int scatter,
                                    const __grid_constant__ ProgPlan p) {
-  const int K = p.paired ? 16 : p.Cin, N = p.Nmma;
+  // CTA pairs: [half][tile][K/8][N/2][8], half = n / (N/2)
+  const int K = p.paired ? 16 : p.Cin, N = p.Nmma, nh = p.pair ? 2 : 1, Nl = N / nh;
   const int64_t total = (int64_t)p.nbt * K * N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i & 7);
     int64_t t = i >> 3;
-    const int n = (int)(t % N); t /= N;
-    const int cc = (int)(t % (K >> 3));
-    const int tile = (int)(t / (K >> 3));
+    const int nl = (int)(t % Nl); t /= Nl;
+    const int cc = (int)(t % (K >> 3)); t /= (K >> 3);
+    const int tile = (int)(t % p.nbt);
+    const int n = (int)(t / p.nbt) * Nl + nl;
     const int nn = p.stack ? n % p.N : n;  // stacked: row n = phase * N + channel
     const int tap = p.stack ? p.tile_phase_tap[tile][n / p.N] : (p.paired ? p.tile_tap[tile][cc] : tile);
     const int ci = p.paired ? c8 : cc * 8 + c8;
@@ -499,11 +552,17 @@ static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &be
   p.nbt = paired ? taps / 2 + (g.k == 3 ? 9 : 0) : taps;  // upper bound; build_program fixes the exact count
   p.btile_bytes = (uint32_t)(paired ? 16 : Cin) * N * 2;
   p.Nmma = N; p.acc_stride = 0; p.mt_stride = N;  // acc_stride of the unstacked layout depends on mtiles (set below)
+  // CTA pairs: one TMA box per slab (swizzled whole voxels or the 8-channel critic slabs) and N/2 a multiple of 16
+  static int pair_off = -1;
+  if (pair_off < 0) pair_off = getenv("CGAN3D_NO_PAIR") ? 1 : 0;
+  const bool pair_base = !pair_off && (paired || Cin <= 64);
+  p.pair = (pair_base && N % 32 == 0) ? 1 : 0;
+  if (p.pair) p.btile_bytes /= 2;
   if (scatter && 8 * N <= 256) {
     const int ncombo = g.k == 3 ? 8 : 27;
-    const uint32_t tile = (uint32_t)Cin * 8 * N * 2;
+    const uint32_t tile = (uint32_t)Cin * 8 * N * 2 / (pair_base ? 2 : 1);
     if ((ncombo * tile + 1023) / 1024 * 1024 + 40000 <= kSmemLimitProg) {
-      p.stack = 1; p.Nmma = 8 * N; p.nbt = ncombo; p.btile_bytes = tile;
+      p.stack = 1; p.Nmma = 8 * N; p.nbt = ncombo; p.btile_bytes = tile; p.pair = pair_base ? 1 : 0;
     }
   }
   const uint32_t b_total = (p.nbt * p.btile_bytes + 1023) / 1024 * 1024;
@@ -568,7 +627,7 @@ size_t tc_prog_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   ProgPlan p;
   int nsplit = 1;
   if (!plan_prog(g, op, p, &nsplit)) return 0;
-  return (((size_t)p.nbt * p.btile_bytes + 255) / 256 * 256) * nsplit + 256;
+  return (((size_t)p.nbt * p.btile_bytes * (p.pair ? 2 : 1) + 255) / 256 * 256) * nsplit + 256;
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -587,7 +646,7 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
   ProgPlan p;
   int nsplit = 1;
   if (!plan_prog(g, scatter, p, &nsplit)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: no tiling for this shape");
-  const size_t part_bytes = ((size_t)p.nbt * p.btile_bytes + 255) / 256 * 256;
+  const size_t part_bytes = ((size_t)p.nbt * p.btile_bytes * (p.pair ? 2 : 1) + 255) / 256 * 256;
   const size_t need = part_bytes * nsplit;
   if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 strided conv: workspace %zu < %zu", ws_bytes, need);
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
@@ -611,15 +670,16 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (strided) failed with %d", (int)r);
   const long long total = (long long)p.B * p.nzt * p.nslabs * p.Xg;
-  const int grid = (int)mn<long long>(total, (long long)num_sms());
+  const int grid = p.pair ? 2 * (int)mn<long long>((total + 1) / 2, (long long)(num_sms() / 2)) : (int)mn<long long>(total, (long long)num_sms());
   if (bn_sums && p.Nout > 64) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: fused BatchNorm statistics need <= 64 channels per launch");
-  auto launch_s = [&](auto ks_tag, auto mt_tag, auto st_tag) -> int {
+  auto launch_s = [&](auto ks_tag, auto mt_tag, auto st_tag, auto pair_tag) -> int {
     constexpr int KS = decltype(ks_tag)::value;
     constexpr int MT = decltype(mt_tag)::value;
     constexpr bool ST = decltype(st_tag)::value;
+    constexpr bool PR = decltype(pair_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_prog_tc_kernel<KS, MT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(conv_prog_tc_kernel<KS, MT, ST, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kSmemLimitProg + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_prog_tc_kernel)");
       attr_set = true;
@@ -629,13 +689,43 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
       bf16 *wb = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + part * part_bytes);
       repack_prog_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wb, g.Cb, g.Cs, scatter, p);
       CG_LAUNCH_CHECK("repack_prog");
-      conv_prog_tc_kernel<KS, MT, ST><<<grid, 192, p.smem_bytes + 1024, st>>>(tm, wb, reinterpret_cast<bf16 *>(outp), p, bn_sums);
+      CUtensorMap tmw{};
+      if (PR) {  // the repacked half tiles as rows of 256 bytes
+        const cuuint64_t wdim[2] = {64, (cuuint64_t)2 * p.nbt * (p.btile_bytes >> 8)};
+        const cuuint64_t wstr[1] = {256};
+        const cuuint32_t wbox[2] = {64, (cuuint32_t)(p.btile_bytes >> 8)};
+        const cuuint32_t we[2] = {1, 1};
+        CUresult rw = enc(&tmw, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, wb, wdim, wstr, wbox, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, tc_l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rw != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (strided, filters) failed with %d", (int)rw);
+      }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(192);
+      cfg.dynamicSmemBytes = p.smem_bytes + 1024;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = PR ? 2 : 1;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, conv_prog_tc_kernel<KS, MT, ST, PR>, tm, tmw, (const bf16 *)wb, reinterpret_cast<bf16 *>(outp), p,
+                                         bn_sums);
+      if (e != cudaSuccess) return cuda_fail(e, "conv_prog_tc_kernel launch");
       CG_LAUNCH_CHECK("conv_prog_tc_kernel");
     }
     return 0;
   };
   auto launch = [&](auto ks_tag, auto mt_tag) -> int {
-    return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}) : launch_s(ks_tag, mt_tag, std::false_type{});
+    if (p.pair) {
+      if constexpr (decltype(ks_tag)::value <= 4)
+        return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}, std::true_type{}) : launch_s(ks_tag, mt_tag, std::false_type{}, std::true_type{});
+      else
+        return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: CTA pairs need Cin <= 64");
+    }
+    return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}, std::false_type{}) : launch_s(ks_tag, mt_tag, std::false_type{}, std::false_type{});
   };
   auto by_mt = [&](auto ks_tag) -> int {
     switch (p.mtiles) {

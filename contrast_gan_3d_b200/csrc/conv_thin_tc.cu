@@ -823,7 +823,7 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
       const double eff = (double)p.Xo * p.Yo / ((double)nxt * nyt * mt * 128);
       const double halo = (double)(Xh * Yh) / (Xt * Yt);
       static double halo_w = -1;
-      if (halo_w < 0) { const char *e = getenv("CGAN3D_THIN_HALO_W"); halo_w = e ? atof(e) : 0.05; }
+      if (halo_w < 0) { const char *e = getenv("CGAN3D_THIN_HALO_W"); halo_w = e ? atof(e) : 0.02; }
       const double score = eff / (1.0 + halo_w * halo) * (nslots >= 3 ? 1.0 : 0.8);
       if (score > best_score + 1e-9) {
         best_score = score; found = true;

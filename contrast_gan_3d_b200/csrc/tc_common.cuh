@@ -177,12 +177,14 @@ __device__ __forceinline__ void tma_load_2d_2cta(void *dst, const CUtensorMap *m
                ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
                : "memory");
 }
-// arrive on the mbarrier at this offset in the shared memory of CTA `rank` of the cluster
+// arrive on the mbarrier at this offset in the shared memory of CTA `rank` of the cluster.  RELAXED on purpose: the callers
+// only hand back TMEM buffers whose tcgen05.ld have already completed (tcgen05.wait::ld); a release at cluster scope would
+// also wait for the epilogue's global stores to drain, which put ~1 us on the critical path of every short step.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }

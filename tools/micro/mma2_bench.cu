@@ -15,12 +15,12 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 
 template <int UNROLL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-bench2(int N, int nacc, int iters, int sw, int a_stride16, long long *out) {
+bench2(int N, int nacc, int iters, int sw, int a_stride16, int commit_every, int mask, long long *out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, dummy;
   __shared__ uint32_t tmem_ptr;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
-  if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+  if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::mbar_init(&dummy, 1); tc::fence_barrier_init(); }
   tc::fence_proxy_async();
   __syncthreads();
   cluster_sync_all();
@@ -56,6 +56,11 @@ bench2(int N, int nacc, int iters, int sw, int a_stride16, long long *out) {
                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                 ::"r"(tb + acc * N), "l"(a_d + (uint64_t)(u * a_stride16)), "l"(b_d), "r"(idesc), "r"(1u)
                 : "memory");
+            if (commit_every && ((it * UNROLL + u + 1) & (commit_every - 1)) == 0)
+              asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                               tc::smem_u32(&dummy)),
+                           "h"((uint16_t)mask)
+                           : "memory");
           }
         }
         __syncwarp();
@@ -88,12 +93,22 @@ int main() {
       for (int nacc : {1, 2})
         for (int astr : {0, 128}) {
           if (nacc * N > 512) continue;
-          bench2<U><<<2, 128, 200 * 1024>>>(N, nacc, iters, sw, astr, d);
+          bench2<U><<<2, 128, 200 * 1024>>>(N, nacc, iters, sw, astr, 0, 3, d);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
           long long c;
           cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
           printf("%d %d %d %d %.1f\n", N, nacc, sw, astr, (double)c / (iters * U));
         }
+  printf("commit overhead (N=64, sw=128): commit_every mask cycles_per_mma\n");
+  for (int mask : {3, 1})
+    for (int ce : {0, 1, 2, 4, 8, 16, 64}) {
+      bench2<U><<<2, 128, 200 * 1024>>>(64, 2, iters, 128, 128, ce, mask, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+      long long c;
+      cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+      printf("%d %d %.1f\n", ce, mask, (double)c / (iters * U));
+    }
   return 0;
 }
