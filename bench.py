@@ -231,17 +231,38 @@ def main():
 
     trace = os.environ.get("BENCH_E2E_TRACE")
 
+    loss_pinned = torch.empty(2, dtype=torch.float32).pin_memory()
+
     def timed(batches, steps, read_loss):
+        """K steps between two events.  read_loss (the end-to-end leg): every step's result is copied device->host into
+        pinned memory inside the timed region and consumed one step later (after its own event), the way a training loop
+        logs its losses, so the host can enqueue step i+1 while step i runs; the next step's input is prefetched as
+        Trainer.fit does.  All K results are read before the closing event's synchronize returns."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pending = None  # (slot, event) of the previous step's device->host copy
+        losses = []
         sync()
         e0.record()
         for it in range(steps):
             t0 = time.perf_counter()
             logs = tr.train_step(batches, 0)  # iteration 0: critic AND generator are trained
             if read_loss:
-                _ = float(logs["G-full"].detach())  # device->host read of the step's result
+                if it + 1 < steps:
+                    tr.prefetch(batches)  # the next step's input crosses PCIe under this step's kernels
+                slot = it & 1
+                loss_pinned[slot:slot + 1].copy_(logs["G-full"].detach().reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    losses.append(float(loss_pinned[pending[0]]))
+                pending = (slot, ev)
                 if trace:
                     print(f"[trace] e2e step {it}: {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
+        if pending is not None:
+            pending[1].synchronize()
+            losses.append(float(loss_pinned[pending[0]]))
+            assert len(losses) == steps and all(v == v for v in losses), losses
         e1.record()
         sync()
         ms = e0.elapsed_time(e1) / steps
@@ -264,6 +285,11 @@ def main():
     for _ in range(max(args.warmup, 5)):  # warm the end-to-end path too (side-stream upload pool, pinned-memory registration)
         tr.train_step(host, 0)
     ms_e2e, logs = timed(host, args.steps, read_loss=True)
+    if os.environ.get("BENCH_E2E_ABLATE"):  # where does the end-to-end overhead come from?
+        for name, (bt, rl) in {"host,no-read": (host, False), "resident,read": (resident, True), "resident,no-read": (resident, False),
+                               "host,read": (host, True)}.items():
+            m, _ = timed(bt, args.steps, read_loss=rl)
+            print(f"[ablate] {name}: {m:.3f} ms/step", file=sys.stderr)
     e2e_retry = None
     if ms_e2e > 1.3 * ms:
         # the step itself is unchanged (same kernels as `value`), so an end-to-end time far above value + upload time is a

@@ -199,7 +199,7 @@ class Trainer:
         out[a.shape[0]:].copy_(b, non_blocking=True)
         return out
 
-    def _side_upload(self, key: str, parts: List[Tensor]):
+    def _side_upload(self, key: str, parts: List[Tensor], consumed_now: bool = True):
         """Host->device copy of `torch.cat(parts)` on a side stream, so that tensors that are only needed later in the step
         (the real batch for the critic, the masks for the generator loss) cross PCIe while G's forward pass runs.
         The destination is a persistent per-key staging tensor (no cross-stream traffic through the caching allocator):
@@ -209,7 +209,9 @@ class Trainer:
             return (parts[0] if len(parts) == 1 else torch.cat(parts)), None
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._staging, self._staging_done = {}, {}
+            self._staging, self._staging_done, self._staging_used = {}, {}, set()
+        if consumed_now:
+            self._staging_used.add(key)
         main = torch.cuda.current_stream(self.device)
         shape = (sum(t.shape[0] for t in parts), *parts[0].shape[1:])
         buf = self._staging.get(key)
@@ -234,10 +236,37 @@ class Trainer:
         if getattr(self, "_copy_stream", None) is None:
             return
         main = torch.cuda.current_stream(self.device)
-        for key in self._staging:
+        # only the buffers this step has read: the one `prefetch` is about to fill for the next step was released a step ago
+        for key in getattr(self, "_staging_used", ()):
             ev = torch.cuda.Event()
             ev.record(main)
             self._staging_done[key] = ev
+        self._staging_used = set()
+
+    def prefetch(self, patches: List[dict]) -> None:
+        """Start the host->device copy of the NEXT step's generator input (the [low; high] batch, the one upload that
+        `train_step` needs before it can launch anything) on the side stream while the current step is still running.
+        `fit` calls this with the batch it has just drawn for the following iteration; `train_step` recognises the batch by
+        the identity of its host tensors and only waits on the copy's event.  Two alternating staging tensors: the step in
+        flight still reads the other one (the similarity loss uses the input until the end of the step)."""
+        _, low, high = patches
+        parts = [low["data"], high["data"]]
+        if all(t.device == self.device for t in parts):
+            return
+        flip = 1 - getattr(self, "_prefetch_flip", 1)
+        self._prefetch_flip = flip
+        key = f"subopt{flip}"
+        buf, ev = self._side_upload(key, parts, consumed_now=False)
+        self._prefetched = (tuple(id(t) for t in parts), buf, ev, key)
+
+    def _take_prefetched(self, low: dict, high: dict):
+        pf = getattr(self, "_prefetched", None)
+        self._prefetched = None
+        if pf is None or pf[0] != (id(low["data"]), id(high["data"])):
+            return None
+        torch.cuda.current_stream(self.device).wait_event(pf[2])
+        self._staging_used.add(pf[3])
+        return pf[1]
 
     def _generate(self, subopt: Tensor):
         if hasattr(self.generator, "forward_corrected"):
@@ -250,7 +279,9 @@ class Trainer:
         do_train_generator = iteration % self.train_generator_every == 0
         do_train_critic = iteration % self.train_critic_every == 0
         main = torch.cuda.current_stream(self.device)
-        subopt = self._upload_cat(low["data"], high["data"])  # needed first: on the compute stream
+        subopt = self._take_prefetched(low, high)  # copied during the previous step when `prefetch` was called with this batch
+        if subopt is None:
+            subopt = self._upload_cat(low["data"], high["data"])  # needed first: on the compute stream
         opt_t, opt_ev = self._side_upload("opt", [opt["data"]]) if do_train_critic else (None, None)
         mask_t, mask_ev = self._side_upload("mask", [low["seg"], high["seg"]]) if do_train_generator else (None, None)
         attenuation, opt_hat = self._generate(subopt)
@@ -281,9 +312,16 @@ class Trainer:
         self.critic.train()
         augmenters = {"train": train_loaders, "val": val_loaders}
         self._manage_augmenters(augmenters, "start")
+        draw = lambda: [next(train_loaders[st]) for st in SCAN_TYPE_ORDER]
+        upcoming = draw() if self.iteration < self.train_iterations else None
         for iteration in range(self.iteration, self.train_iterations):
-            patches = [next(train_loaders[st]) for st in SCAN_TYPE_ORDER]
+            patches = upcoming
             self.train_step(patches, iteration)
+            # same draw order as the reference loop (Trainer.py:206-209), one iteration early: the next batch crosses PCIe
+            # while this step's kernels run
+            upcoming = draw() if iteration + 1 < self.train_iterations else None
+            if upcoming is not None:
+                self.prefetch(upcoming)
             if self.val_every is not None and iteration != 0 and iteration % self.val_every == 0:
                 self.validate(val_loaders, iteration)
             if self.checkpoint_every is not None and iteration != 0 and iteration % self.checkpoint_every == 0:

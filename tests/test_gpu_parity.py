@@ -354,6 +354,63 @@ def test_train_step_against_oracle_other_shape():
         assert_close32(v, r, rtol=2e-3, atol=2 * 2e-4 * 2, msg=k)
 
 
+def test_fit_prefetches_next_batch_with_identical_results():
+    """`fit` draws the next batch one iteration early and copies it under the running step (Trainer.prefetch).  The staged
+    generator input must be exactly the host batch both when the step starts and when it ends (the next prefetch must not
+    touch the buffer in flight), and the trained weights must match (to atomic-summation noise) those of calling train_step
+    batch by batch (reference loop, trainer/Trainer.py:206-209)."""
+    patch = (32, 32, 32)
+
+    def loaders(seed, steps):
+        gen = torch.Generator().manual_seed(seed)
+        rows = [[], [], []]
+        for _ in range(steps):
+            opt, low, high, ml, mh = _batches(gen, patch)
+            rows[0].append(dict(data=opt.pin_memory(), seg=None, name=[]))
+            rows[1].append(dict(data=low.pin_memory(), seg=ml.pin_memory(), name=[]))
+            rows[2].append(dict(data=high.pin_memory(), seg=mh.pin_memory(), name=[]))
+        return rows
+
+    steps = 4
+    a, b = _make_trainer(torch.bfloat16), _make_trainer(torch.bfloat16)
+    a.train_iterations = b.train_iterations = steps
+    a.val_every = b.val_every = None
+    rows = loaders(5, steps)
+    a.generator.train(); a.critic.train()
+    for it in range(steps):
+        a.train_step([rows[0][it], rows[1][it], rows[2][it]], it)
+    rows = loaders(5, steps)
+    seen_begin, seen_end = [], []
+    gen_fwd, gen_step = b._generate, b.train_generator
+
+    def spy_generate(subopt):
+        seen_begin.append(subopt.clone())
+        return gen_fwd(subopt)
+
+    def spy_generator_step(inputs, recon, masks):
+        out = gen_step(inputs, recon, masks)
+        seen_end.append(inputs.clone())
+        return out
+
+    b._generate, b.train_generator = spy_generate, spy_generator_step
+    b.fit({0: iter(rows[0]), -1: iter(rows[1]), 1: iter(rows[2])}, {})
+    assert getattr(b, "_prefetch_flip", None) is not None, "fit did not prefetch"
+    torch.cuda.synchronize()
+    assert len(seen_begin) == steps and len(seen_end) == steps
+    for it in range(steps):
+        want = torch.cat([rows[1][it]["data"], rows[2][it]["data"]]).to(DEV)
+        assert torch.equal(seen_begin[it], want), f"step {it}: staged input differs at the start of the step"
+        assert torch.equal(seen_end[it], want), f"step {it}: staged input was overwritten during the step"
+    # the weight gradients are summed with floating-point atomics, so two runs agree to rounding noise, not bit for bit:
+    # 4 Adam steps of 2e-4 bound the drift of one weight by 1.6e-3
+    for (k, va), vb in zip(a.generator.state_dict().items(), b.generator.state_dict().values()):
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert_close32(va, vb, rtol=0, atol=1.7e-3, msg=k)
+    d = (a.generator.state_dict()["model.first.conv.weight"] - b.generator.state_dict()["model.first.conv.weight"]).abs().mean()
+    assert float(d) < 2e-4, float(d)
+
+
 def test_generator_only_iterations_and_cadence():
     tr = _make_trainer(torch.float32)
     tr.train_generator_every = 2
