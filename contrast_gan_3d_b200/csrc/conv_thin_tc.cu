@@ -350,10 +350,13 @@ struct ThinBPlan {
 struct SegIter {
   long long idx, end;
   int Xo;
-  __device__ __forceinline__ SegIter(long long ncols, int Xo_) : Xo(Xo_) {
-    const long long total = ncols * Xo;
-    idx = total * blockIdx.x / gridDim.x;
-    end = total * (blockIdx.x + 1) / gridDim.x;
+  // pair = true: the two CTAs of a cluster share one range over COLUMN PAIRS (the caller maps pair column j to columns
+  // 2j + rank), so both walk identical (x0, xlen) segments in lockstep
+  __device__ __forceinline__ SegIter(long long ncols, int Xo_, bool pair = false) : Xo(Xo_) {
+    const long long nblk = pair ? gridDim.x >> 1 : gridDim.x, blk = pair ? blockIdx.x >> 1 : blockIdx.x;
+    const long long total = (pair ? (ncols + 1) / 2 : ncols) * Xo;
+    idx = total * blk / nblk;
+    end = total * (blk + 1) / nblk;
   }
   __device__ __forceinline__ bool next(int &col, int &x0, int &xlen) {
     if (idx >= end) return false;
@@ -365,10 +368,10 @@ struct SegIter {
   }
 };
 
-template <int MT>
+template <int MT, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
-conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restrict__ wT, bf16 *__restrict__ out,
-                    const __grid_constant__ ThinBPlan p) {
+conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const bf16 *__restrict__ wT,
+                    bf16 *__restrict__ out, const __grid_constant__ ThinBPlan p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *bres = smem;                                                   // 7 resident filter tiles (14 KB)
   uint8_t *ring = smem + 14336;                                            // slab slots (multiple of 256 B)
@@ -381,54 +384,80 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
   if (threadIdx.x == 0) {
     tc::mbar_init(b_ready, 1);
     for (int i = 0; i < p.nslots; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], PAIR ? 16 : 8); }
     tc::fence_barrier_init();
   }
+  constexpr uint32_t kTileB = PAIR ? kTileBytesB / 2 : kTileBytesB;  // a CTA of a pair holds 32 of the 64 N rows of a tile
+  const uint32_t cta_rank = PAIR ? tc::cluster_ctarank() : 0u;
+  if constexpr (PAIR) {
+    __syncthreads();
+    tc::cluster_sync();
+  }
   if (warp == 9) {
-    tc::tmem_alloc(tmem_ptr, p.tmem_cols);
-    tc::tmem_relinquish();
+    if constexpr (PAIR) { tc::tmem_alloc2(tmem_ptr, p.tmem_cols); tc::tmem_relinquish2(); }
+    else { tc::tmem_alloc(tmem_ptr, p.tmem_cols); tc::tmem_relinquish(); }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) tc::cluster_sync();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const long long ncols = (long long)p.B * p.nyt * p.nzt;
-  auto decode = [&](int col, int &b, int &y0, int &ylen, int &z0, int &zlen) {
+  auto decode = [&](int col, int &b, int &y0, int &ylen, int &z0, int &zlen) -> bool {
+    bool live = true;
+    if constexpr (PAIR) {
+      col = 2 * col + (int)cta_rank;
+      if (col >= ncols) { col = (int)ncols - 1; live = false; }
+    }
     const int zt = col % p.nzt; col /= p.nzt;
     const int yt = col % p.nyt;
     b = col / p.nyt;
     y0 = yt * p.Yt; ylen = min(p.Yt, p.Yo - y0);
     z0 = zt * p.Zt; zlen = min(p.Zt, p.Zo - z0);
+    return live;
   };
 
   if (warp == 8) {
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmA);
-      tc::mbar_expect_tx(b_ready, kTapTilesB * kTileBytesB);
-      tc::bulk_g2s(bres, wT, kTapTilesB * kTileBytesB, b_ready);
+      if constexpr (PAIR) {
+        // SWIZZLE_32B repeats every 256 bytes, so rows 32r..32r+31 of a tile are simply its r-th kilobyte (4 map rows)
+        if (cta_rank == 0) tc::mbar_expect_tx(b_ready, 2 * kTapTilesB * kTileB);
+        for (int t = 0; t < kTapTilesB; ++t) tc::tma_load_2d_2cta(bres + (size_t)t * kTileB, &tmW, b_ready, 0, t * 8 + (int)cta_rank * 4);
+      } else {
+        tc::mbar_expect_tx(b_ready, kTapTilesB * kTileBytesB);
+        tc::bulk_g2s(bres, wT, kTapTilesB * kTileBytesB, b_ready);
+      }
       uint32_t e = 0;
       int col, x0, xlen;
-      for (SegIter it(ncols, p.Xo); it.next(col, x0, xlen);) {
+      for (SegIter it(ncols, p.Xo, PAIR); it.next(col, x0, xlen);) {
         int b, y0, ylen, z0, zlen;
         decode(col, b, y0, ylen, z0, zlen);
         for (int i = 0; i < xlen + 6; ++i, ++e) {
           const uint32_t slot = e % p.nslots, use = e / p.nslots;
           if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
+          if constexpr (PAIR) {
+            if (cta_rank == 0) tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
+            tc::tma_load_5d_2cta(ring + (size_t)slot * p.slot_bytes, &tmA, &s_full[slot], 0, z0 - p.P, y0 - p.P, x0 - p.P + i, b);
+            continue;
+          }
           tc::mbar_expect_tx(&s_full[slot], p.box_bytes);
           tc::tma_load_5d(ring + (size_t)slot * p.slot_bytes, &tmA, &s_full[slot], 0, z0 - p.P, y0 - p.P, x0 - p.P + i, b);
         }
       }
     }
+  } else if (warp == 9 && cta_rank != 0) {
+    // odd CTA of a pair: the rank-0 CTA issues the MMAs of both
   } else if (warp == 9) {
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 256 : 128, 64, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
     const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc_sw(0, 256, 32);
     tc::mbar_wait(b_ready, 0);
     tc::tc_fence_after();
     uint32_t e = 0;
     int col, x0, xlen;
-    for (SegIter it(ncols, p.Xo); it.next(col, x0, xlen);) {
+    for (SegIter it(ncols, p.Xo, PAIR); it.next(col, x0, xlen);) {
       for (int i = 0; i < xlen + 6; ++i, ++e) {
         const uint32_t q = e & 1, uq = e >> 1, slot = e % p.nslots;
         if (uq > 0) tc::mbar_wait(&tm_empty[q], (uq - 1) & 1);
@@ -441,12 +470,15 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
           for (int dy = 0; dy < 7; ++dy) {
             if (p.debug & 1) continue;
             const uint64_t a0 = a_hi | (uint64_t)((a_slot + 2u * (uint32_t)(dy * kPitchB)) & 0x3FFF);  // 32-byte rows
-            const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)dy * kTileBytesB) >> 4) & 0x3FFF);
+            const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)dy * kTileB) >> 4) & 0x3FFF);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) tc::umma_bf16(d_base + mt * 64, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(dy != 0));
+            for (int mt = 0; mt < MT; ++mt) {
+              if constexpr (PAIR) tc::umma_bf16_2cta(d_base + mt * 64, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(dy != 0));
+              else tc::umma_bf16(d_base + mt * 64, a0 + (uint64_t)(mt * 256), b0, idesc, (uint32_t)(dy != 0));
+            }
           }
-          tc::umma_commit(&s_empty[slot]);
-          tc::umma_commit(&tm_full[q]);
+          if constexpr (PAIR) { tc::umma_commit_2cta(&s_empty[slot], 3); tc::umma_commit_2cta(&tm_full[q], 3); }
+          else { tc::umma_commit(&s_empty[slot]); tc::umma_commit(&tm_full[q]); }
         }
         __syncwarp();
       }
@@ -458,9 +490,9 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
     const int qd = warp & 3, grp = warp >> 2;
     uint32_t e = 0;
     int col, x0, xlen;
-    for (SegIter it(ncols, p.Xo); it.next(col, x0, xlen);) {
+    for (SegIter it(ncols, p.Xo, PAIR); it.next(col, x0, xlen);) {
       int b, y0, ylen, z0, zlen;
-      decode(col, b, y0, ylen, z0, zlen);
+      const bool live = decode(col, b, y0, ylen, z0, zlen);
       float win[NK][7];
       bool valid[NK];
       uint32_t off[NK];
@@ -470,7 +502,7 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         for (int j = 0; j < 7; ++j) win[k][j] = 0.f;
         const int mt = 2 * k + grp;
         const int yy = mt * 4 + qd;
-        valid[k] = mt < MT && yy < ylen && lane < zlen;
+        valid[k] = live && mt < MT && yy < ylen && lane < zlen;
         off[k] = (uint32_t)((y0 + yy) * p.Zo + (z0 + lane));
       }
       for (int i = 0; i < xlen + 6; ++i, ++e) {
@@ -506,13 +538,21 @@ conv7_to1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const bf16 *__restr
         }
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tm_empty[q]);
+        if (lane == 0) {
+          if constexpr (PAIR) tc::mbar_arrive_cluster(&tm_empty[q], 0);
+          else tc::mbar_arrive(&tm_empty[q]);
+        }
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 9) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (PAIR) {
+    tc::cluster_sync();
+    if (warp == 9) tc::tmem_dealloc2(tmem_base, p.tmem_cols);
+  } else {
+    if (warp == 9) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 // T[dy][n = dx*8 + dz][ci] = w(dx,dy,dz,ci) for dx, dz < 7, else 0 (same flip convention as toeplitz_a_kernel), stored as
@@ -999,19 +1039,48 @@ static int run_thin_b(const cgan3d_conv_geom &g, int op, const void *in, const v
   const cuuint32_t box[5] = {16, (cuuint32_t)p.Zh, (cuuint32_t)p.Yh, 1, 1};
   int r = encode_map(&tm, in, 5, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_32B);
   if (r) return r;
-  const long long total = (long long)p.B * p.nyt * p.nzt * p.Xo;
-  const int grid = (int)mn<long long>(total, (long long)num_sms());
-  auto launch = [&](auto mt_tag) -> int {
+  static int pair_off = -1;
+  if (pair_off < 0) pair_off = getenv("CGAN3D_NO_PAIR") ? 1 : 0;
+  const bool pair = !pair_off;
+  CUtensorMap tmw{};
+  if (pair) {  // the 7 filter tiles as rows of 256 bytes (8 rows per tile, 4 per CTA half)
+    const cuuint64_t wdim[2] = {64, (cuuint64_t)(kTapTilesB * kTileBytesB / 256)};
+    const cuuint64_t wstr[1] = {256};
+    const cuuint32_t wbox[2] = {64, 4};
+    r = encode_map_raw(&tmw, wt, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, wdim, wstr, wbox);
+    if (r) return r;
+  }
+  const long long ncols = (long long)p.B * p.nyt * p.nzt;
+  const long long total = (pair ? (ncols + 1) / 2 : ncols) * p.Xo;
+  const int grid = pair ? 2 * (int)mn<long long>(total, (long long)(num_sms() / 2)) : (int)mn<long long>(total, (long long)num_sms());
+  auto launch_p = [&](auto mt_tag, auto pair_tag) -> int {
     constexpr int MT = decltype(mt_tag)::value;
+    constexpr bool PR = decltype(pair_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv7_to1_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
+      cudaError_t e = cudaFuncSetAttribute(conv7_to1_tc_kernel<MT, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
       if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv7_to1_tc_kernel)");
       attr_set = true;
     }
-    conv7_to1_tc_kernel<MT><<<grid, 320, p.smem_bytes + 1024, st>>>(tm, wt, reinterpret_cast<bf16 *>(outp), p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = p.smem_bytes + 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PR ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv7_to1_tc_kernel<MT, PR>, tm, tmw, (const bf16 *)wt, reinterpret_cast<bf16 *>(outp), p);
+    if (e != cudaSuccess) return cuda_fail(e, "conv7_to1_tc_kernel launch");
     CG_LAUNCH_CHECK("conv7_to1_tc_kernel");
     return 0;
+  };
+  auto launch = [&](auto mt_tag) -> int {
+    return pair ? launch_p(mt_tag, std::true_type{}) : launch_p(mt_tag, std::false_type{});
   };
   switch (p.mtiles) {
     case 1: return launch(std::integral_constant<int, 1>{});
