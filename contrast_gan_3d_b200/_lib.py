@@ -54,6 +54,7 @@ SIGNATURES = {
     "cgan3d_bn_finalize": (_i, [_vp, _i64, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "cgan3d_bn_eval_params": (_i, [_vp, _vp, _i, _f, _vp, _vp]),
     "cgan3d_bn_apply": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "cgan3d_bn_apply_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _i, _vp]),
     "cgan3d_bn_backward_reduce": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "cgan3d_bn_backward_apply": (_i, [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "cgan3d_bias_act": (_i, [_vp, _vp, _i, _i64, _i, _vp, _i, _f, _vp]),

@@ -82,12 +82,14 @@ class ConvBlock(nn.Module):
                                  pad=padding, reflect=padding_mode == "reflect", out_pad=output_padding)
         self.compute_dtype = kwargs.get("compute_dtype", torch.float32)
 
-    def forward_cl(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+    def forward_cl(self, x: Tensor, residual: Optional[Tensor] = None, pad_out: int = 0) -> Tensor:
+        """pad_out > 0 returns the output with the reflection padding of its consumer already applied (fused into the
+        normalise + activation pass); the consumer must then be told that its input is pre-padded."""
         bn = self.normalization if isinstance(self.normalization, nn.BatchNorm3d) else None
         cfg = ops.BlockCfg(spec=self.spec, act=self.act_code, slope=self.negative_slope, dtype=self.compute_dtype,
                            training=self.training or (bn is not None and not bn.track_running_stats),
                            momentum=0.1 if bn is None or bn.momentum is None else bn.momentum,
-                           eps=1e-5 if bn is None else bn.eps)
+                           eps=1e-5 if bn is None else bn.eps, pad_out=pad_out)
         if bn is not None:
             return ops.ConvBlockFn.apply(x, self.conv.weight, None, bn.weight, bn.bias, residual, bn.running_mean,
                                          bn.running_var, bn.num_batches_tracked, cfg)

@@ -63,12 +63,16 @@ class ResnetGenerator(nn.Module):
             h = blk.forward_cl(h)
         for blk in self.model.resnet_backbone:
             h = blk.forward_cl(h)
-        for blk in self.model.upsampling:
-            h = blk.forward_cl(h)
+        ups = list(self.model.upsampling)
+        for i, blk in enumerate(ups):
+            # the last up-sampling block writes its output already reflection-padded for last_conv (reference
+            # generator.py:77-83: Conv3d(padding=3, padding_mode="reflect")): `_tail` then takes it as is
+            h = blk.forward_cl(h, pad_out=self._tail_spec.pad if i == len(ups) - 1 else 0)
         return h
 
     def _tail(self, h, subopt: Optional[torch.Tensor]):
-        cfg = ops.BlockCfg(spec=self._tail_spec, act=_lib.ACT_TANH, dtype=self.compute_dtype)
+        cfg = ops.BlockCfg(spec=self._tail_spec, act=_lib.ACT_TANH, dtype=self.compute_dtype,
+                           pre_padded=len(self.model.upsampling) > 0)
         return ops.GenTailFn.apply(h, self.model.last_conv.weight, self.model.last_conv.bias, subopt, cfg)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -230,6 +230,8 @@ class BlockCfg:
     training: bool = True
     momentum: float = 0.1
     eps: float = 1e-5
+    pad_out: int = 0          # > 0: return reflect_pad(output, pad_out) -- the padding of the consumer, fused into the normalise pass
+    pre_padded: bool = False  # the input already carries this layer's reflection padding (produced with pad_out)
 
 
 class ConvBlockFn(torch.autograd.Function):
@@ -255,6 +257,7 @@ class ConvBlockFn(torch.autograd.Function):
         else:
             y = conv_scatter(g, xin, wp) if spec.transposed else conv_gather(g, xin, wp)
         mi = None
+        padded = False
         if gamma is not None:
             mi = torch.empty(2 * Co, dtype=torch.float32, device=x.device)
             if cfg.training:
@@ -265,12 +268,20 @@ class ConvBlockFn(torch.autograd.Function):
                      _p(running_var), _p(nbt), _st())
             else:
                 call("cgan3d_bn_eval_params", _p(running_mean), _p(running_var), Co, cfg.eps, _p(mi), _st())
-            z = torch.empty_like(y)
             res = None
             if residual is not None:
                 res = cast(residual.detach().contiguous(), cfg.dtype)
-            call("cgan3d_bn_apply", _p(y), _p(z), dt, n_rows, Co, _p(mi), _p(gamma.detach()), _p(beta.detach()),
-                 cfg.act, cfg.slope, _p(res), _st())
+            po = cfg.pad_out
+            if po and res is None and not cfg.out_f32 and Co % 8 == 0:
+                # normalise + activate straight into the consumer's reflection-padded input
+                z = torch.empty((B, out_sp[0] + 2 * po, out_sp[1] + 2 * po, out_sp[2] + 2 * po, Co), dtype=y.dtype, device=y.device)
+                call("cgan3d_bn_apply_pad", _p(y), _p(z), dt, B, out_sp[0], out_sp[1], out_sp[2], Co, _p(mi), _p(gamma.detach()),
+                     _p(beta.detach()), cfg.act, cfg.slope, po, _st())
+                padded = True
+            else:
+                z = torch.empty_like(y)
+                call("cgan3d_bn_apply", _p(y), _p(z), dt, n_rows, Co, _p(mi), _p(gamma.detach()), _p(beta.detach()),
+                     cfg.act, cfg.slope, _p(res), _st())
         else:
             assert residual is None
             if bias is None and cfg.act == _lib.ACT_NONE:
@@ -279,6 +290,8 @@ class ConvBlockFn(torch.autograd.Function):
                 z = torch.empty_like(y)
                 call("cgan3d_bias_act", _p(y), _p(z), dt, n_rows, Co, _p(None if bias is None else bias.detach()),
                      cfg.act, cfg.slope, _st())
+        if cfg.pad_out and not padded:
+            z = reflect_pad(z, cfg.pad_out)
         if cfg.out_f32:
             z = cast(z, torch.float32)
         ctx.cfg, ctx.g = cfg, g
@@ -296,6 +309,8 @@ class ConvBlockFn(torch.autograd.Function):
         xin, wp, y, mi, gamma, beta, bias = ctx.saved_tensors
         dt = _dt(cfg.dtype)
         dz = cast(dz.contiguous(), cfg.dtype)
+        if cfg.pad_out:
+            dz = reflect_pad_backward(dz, cfg.pad_out)  # adjoint of the consumer's padding
         Co = spec.cout
         n_rows = y.numel() // Co
         dgamma = dbeta = dbias = None
@@ -346,7 +361,10 @@ class GenTailFn(torch.autograd.Function):
         spec = cfg.spec
         B, X, Y, Z, Cin = x.shape
         xin = cast(x.detach().contiguous(), cfg.dtype)
-        if spec.reflect:
+        if cfg.pre_padded:  # the producer wrote its output already reflection-padded (BlockCfg.pad_out)
+            assert spec.reflect
+            X, Y, Z = X - 2 * spec.pad, Y - 2 * spec.pad, Z - 2 * spec.pad
+        elif spec.reflect:
             xin = reflect_pad(xin, spec.pad)
         g, _ = spec.geometry(B, (X, Y, Z))
         wp = pack_weights(weight, cfg.dtype)
@@ -386,7 +404,7 @@ class GenTailFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = conv_scatter(g, dy, wp)
-            if spec.reflect:
+            if spec.reflect and not cfg.pre_padded:
                 dx = reflect_pad_backward(dx, spec.pad)
             dx = cast(dx, ctx.x_dtype)
         dw = conv_wgrad(g, xin, dy) if ctx.needs_input_grad[1] else None

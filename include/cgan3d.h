@@ -126,6 +126,12 @@ int cgan3d_bn_eval_params(const float *running_mean, const float *running_var, i
 int cgan3d_bn_apply(const void *y, void *z, int dtype, int64_t n_rows, int C, const float *mean_invstd,
                     const float *gamma, const float *beta, int act, float slope, const void *residual,
                     void *stream);
+/* bn_apply fused with the consumer's reflection padding (nn.Conv3d(padding_mode="reflect"), reference
+ * model/generator.py:77-83 after model/blocks.py:45-53): z_padded[B, X+2p, Y+2p, Z+2p, C] = reflect_pad(act(bn(y)), p).
+ * C % 8 == 0; otherwise CGAN3D_E_UNSUPPORTED (the caller pads separately).                            */
+int cgan3d_bn_apply_pad(const void *y, void *z_padded, int dtype, int B, int X, int Y, int Z, int C,
+                        const float *mean_invstd, const float *gamma, const float *beta, int act, float slope,
+                        int pad, void *stream);
 /* backward of bn_apply (train mode): given dz, y -> dy, dgamma, dbeta.
  * Pass 1 (reduce): sums[0..C) = sum g, sums[C..2C) = sum g*xhat, g = dz * act'(.)          */
 int cgan3d_bn_backward_reduce(const void *dz, const void *y, int dtype, int64_t n_rows, int C,

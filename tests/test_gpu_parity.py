@@ -354,6 +354,27 @@ def test_train_step_against_oracle_other_shape():
         assert_close32(v, r, rtol=2e-3, atol=2 * 2e-4 * 2, msg=k)
 
 
+@pytest.mark.parametrize("C,dtype,act", [(16, torch.bfloat16, "relu"), (8, torch.float32, "lrelu"), (64, torch.bfloat16, "none")])
+def test_bn_apply_fused_with_reflect_pad(C, dtype, act):
+    """cgan3d_bn_apply_pad == reflect_pad(bn_apply(y)) bit for bit (same arithmetic, only the store address changes)."""
+    from contrast_gan_3d_b200 import _lib, ops
+    B, X, Y, Z, p = 2, 9, 12, 10, 3
+    gen = torch.Generator().manual_seed(3)
+    y = torch.randn((B, X, Y, Z, C), generator=gen).to(DEV).to(dtype)
+    mi = torch.cat([torch.randn(C, generator=gen) * 0.1, torch.rand(C, generator=gen) + 0.5]).to(DEV)
+    gamma, beta = (torch.rand(C, generator=gen) + 0.5).to(DEV), (torch.randn(C, generator=gen) * 0.1).to(DEV)
+    code = {"relu": _lib.ACT_RELU, "lrelu": _lib.ACT_LRELU, "none": _lib.ACT_NONE}[act]
+    dt = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+    z = torch.empty_like(y)
+    ops.call("cgan3d_bn_apply", ops._p(y), ops._p(z), dt, B * X * Y * Z, C, ops._p(mi), ops._p(gamma), ops._p(beta), code, 0.2, None, ops._st())
+    want = ops.reflect_pad(z, p)
+    got = torch.empty((B, X + 2 * p, Y + 2 * p, Z + 2 * p, C), dtype=dtype, device=DEV)
+    ops.call("cgan3d_bn_apply_pad", ops._p(y), ops._p(got), dt, B, X, Y, Z, C, ops._p(mi), ops._p(gamma), ops._p(beta), code, 0.2, p, ops._st())
+    assert torch.equal(got, want)
+    ref = torch.nn.functional.pad(z.permute(0, 4, 1, 2, 3).float(), (p,) * 6, mode="reflect").permute(0, 2, 3, 4, 1).to(dtype)
+    assert torch.equal(got, ref)
+
+
 def test_fit_prefetches_next_batch_with_identical_results():
     """`fit` draws the next batch one iteration early and copies it under the running step (Trainer.prefetch).  The staged
     generator input must be exactly the host batch both when the step starts and when it ends (the next prefetch must not
