@@ -271,9 +271,7 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
               pk[j] = *reinterpret_cast<uint32_t *>(&h);
             }
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
-            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            tc::st_global_v8(dst + c0, pk);  // N % 16 == 0: 32-byte aligned
           };
           if (p.N <= 64) {  // up to four 16-channel chunks: all TMEM loads in flight before one wait
             uint32_t v[4][16];
@@ -507,8 +505,8 @@ static int run_s1(const cgan3d_conv_geom &g, int flip, const void *in, const voi
   if (!plan_s1(g.B, g.Xb, g.Yb, g.Zb, Cin, N, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 conv: no tiling for this shape");
   const size_t need = (size_t)27 * Cin * N * 2;
   if (ws == nullptr || ws_bytes < need) return fail(CGAN3D_E_WORKSPACE, "tcgen05 conv: workspace %zu < %zu", ws_bytes, need);
-  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 15))
-    return fail(CGAN3D_E_ARG, "tcgen05 conv: pointers must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 31) || (reinterpret_cast<uintptr_t>(ws) & 15))
+    return fail(CGAN3D_E_ARG, "tcgen05 conv: input / workspace must be 16-byte aligned, the output 32-byte aligned (256-bit stores)");
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   bf16 *wb = reinterpret_cast<bf16 *>(ws);

@@ -264,8 +264,12 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           pk[j] = *reinterpret_cast<uint32_t *>(&h);
         }
         uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (cc * 16 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (cc * 16 + 8 < p.Nout && (p.out_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+          tc::st_global_v8(dst, pk);  // 32-byte aligned: out_pitch and out_c0 are multiples of 16 channels
+        } else {
+          d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (cc * 16 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
         if constexpr (STATS) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -304,9 +308,13 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[0][2 * j]), __uint_as_float(v[0][2 * j + 1]));
                   pk[j] = *reinterpret_cast<uint32_t *>(&h);
                 }
-                uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-                d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                if ((p.out_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+                  tc::st_global_v8(dst, pk);
+                } else {
+                  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+                  d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
               }
             }
           }

@@ -189,6 +189,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank
       : "memory");
 }
 
+// one 32-byte global store (sm_100 256-bit vector store): a full sector per lane instead of two half-sector requests
+__device__ __forceinline__ void st_global_v8(void *p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleaved" 8x16B core matrices), version 1 (sm_100):
 //   K-major operand : 8 rows x 16 B core matrix; LBO = byte distance between the two K-adjacent core matrices,
