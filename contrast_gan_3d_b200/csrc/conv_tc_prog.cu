@@ -77,7 +77,7 @@ struct ProgPlan {
 // statistics, reference model/blocks.py:45) into bn_sums (fp64 [2 * out_pitch], Nout <= 64).
 // PAIR: CTA pairs as in conv_tc.cu -- the two CTAs of a cluster process consecutive steps in lockstep, each holds half of
 // the rows of every resident filter tile, the rank-0 CTA issues the MMAs of both.
-template <int KSTEPS, int MT, bool STATS, bool PAIR>
+template <int KSTEPS, int MT, int STATS, bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const bf16 *__restrict__ wB,
                     bf16 *__restrict__ out, const __grid_constant__ ProgPlan p, double *__restrict__ bn_sums) {
@@ -235,10 +235,11 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------------------------ epilogue (warps 0..3 <-> TMEM lanes 32*warp..)
     uint32_t acc = 0;
-    float ssum[STATS ? 64 : 1], ssq[STATS ? 64 : 1];
+    // STATS = channels tracked per thread (0, 32 or 64): 2 x 64 partial sums next to four 16-column TMEM chunks spilled
+    float ssum[STATS ? STATS : 1], ssq[STATS ? STATS : 1];
     if (STATS) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+      for (int j = 0; j < STATS; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
     }
     for (int st = s_begin; st < s_end; ++st, ++acc) {
       int b, z0, zlen, y0, ylen, x;
@@ -270,7 +271,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           if (cc * 16 + 8 < p.Nout) d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
-        if constexpr (STATS) {
+        if constexpr (STATS > cc * 16) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float f = __uint_as_float(v[j]);  // padded columns (>= Nout) hold exact zeros
@@ -294,7 +295,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (16 < p.Nout) emit(v[1], 0, mt, std::integral_constant<int, 1>{});
           if (32 < p.Nout) emit(v[2], 0, mt, std::integral_constant<int, 2>{});
           if (48 < p.Nout) emit(v[3], 0, mt, std::integral_constant<int, 3>{});
-          if constexpr (!STATS) {
+          if constexpr (STATS == 0) {
             for (int c0 = 64; c0 < p.Nout; c0 += 16) {  // wide layers (no fused statistics): one chunk at a time
               tc::tmem_ld16(t_mt + c0, v[0]);
               tc::tmem_ld_wait();
@@ -345,15 +346,18 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else tc::mbar_arrive(&tm_empty[q]);
       }
     }
-    if constexpr (STATS) {  // a thread saw at most a few dozen rows: fp32 partials, fp64 across threads
-      warp_reduce64(ssum, lane);
-      warp_reduce64(ssq, lane);
+    if constexpr (STATS > 0) {  // a thread saw at most a few dozen rows: fp32 partials, fp64 across threads
+      float r0[64], r1[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) { r0[j] = j < STATS ? ssum[j < STATS ? j : 0] : 0.f; r1[j] = j < STATS ? ssq[j < STATS ? j : 0] : 0.f; }
+      warp_reduce64(r0, lane);
+      warp_reduce64(r1, lane);
       const int ch = warp_reduce64_channel(lane);
 #pragma unroll
       for (int i = 0; i < 2; ++i)
         if (ch + i < p.Nout) {
-          atomicAdd(&bn_sums[p.out_c0 + ch + i], (double)ssum[i]);
-          atomicAdd(&bn_sums[p.out_pitch + p.out_c0 + ch + i], (double)ssq[i]);
+          atomicAdd(&bn_sums[p.out_c0 + ch + i], (double)r0[i]);
+          atomicAdd(&bn_sums[p.out_pitch + p.out_c0 + ch + i], (double)r1[i]);
         }
     }
   }
@@ -683,7 +687,7 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
   auto launch_s = [&](auto ks_tag, auto mt_tag, auto st_tag, auto pair_tag) -> int {
     constexpr int KS = decltype(ks_tag)::value;
     constexpr int MT = decltype(mt_tag)::value;
-    constexpr bool ST = decltype(st_tag)::value;
+    constexpr int ST = decltype(st_tag)::value;
     constexpr bool PR = decltype(pair_tag)::value;
     static bool attr_set = false;
     if (!attr_set) {
@@ -726,14 +730,21 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
     }
     return 0;
   };
+  using S0 = std::integral_constant<int, 0>;
+  using S32 = std::integral_constant<int, 32>;
+  using S64 = std::integral_constant<int, 64>;
+  auto launch_st = [&](auto ks_tag, auto mt_tag, auto pair_tag) -> int {
+    if (!bn_sums) return launch_s(ks_tag, mt_tag, S0{}, pair_tag);
+    return p.Nout <= 32 ? launch_s(ks_tag, mt_tag, S32{}, pair_tag) : launch_s(ks_tag, mt_tag, S64{}, pair_tag);
+  };
   auto launch = [&](auto ks_tag, auto mt_tag) -> int {
     if (p.pair) {
       if constexpr (decltype(ks_tag)::value <= 4)
-        return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}, std::true_type{}) : launch_s(ks_tag, mt_tag, std::false_type{}, std::true_type{});
+        return launch_st(ks_tag, mt_tag, std::true_type{});
       else
         return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 strided conv: CTA pairs need Cin <= 64");
     }
-    return bn_sums ? launch_s(ks_tag, mt_tag, std::true_type{}, std::false_type{}) : launch_s(ks_tag, mt_tag, std::false_type{}, std::false_type{});
+    return launch_st(ks_tag, mt_tag, std::false_type{});
   };
   auto by_mt = [&](auto ks_tag) -> int {
     switch (p.mtiles) {
