@@ -275,13 +275,27 @@ def main():
     for _ in range(args.warmup):
         tr.train_step(resident, 0)
     sync()
-    ops.enable_conv_timing(True)
-    n0 = _lib.launch_count
+    # Pass 1 (not the headline): per-kernel device times, two CUDA events around every convolution call.  It runs first so
+    # that its host cost (~300 event records per step) cannot touch the headline loop, and it doubles as further warm-up:
+    # on some boxes the first K-step loop after W = 3 warm-up steps ran 20-35 % slower than every later one (cause not
+    # identified; same kernels, same clocks).
+    # nvidia-smi needs ~0.15 s to deliver its first sample and the headline loop lasts ~0.2 s: the sampler is started before
+    # pass 1 and runs through both passes (same kernels, same load)
     with ClockSampler(local_rank) as clk:
+        ops.enable_conv_timing(True)
+        ms_instr, _ = timed(resident, args.steps, read_loss=False)
+        conv_t = ops.conv_timing_summary()
+        ops.enable_conv_timing(False)
+        # Pass 2: the headline loop, exactly K steps between two events
+        n0 = _lib.launch_count
         ms, logs = timed(resident, args.steps, read_loss=False)
-    launches = _lib.launch_count - n0
-    conv_t = ops.conv_timing_summary()
-    ops.enable_conv_timing(False)
+        launches = _lib.launch_count - n0
+        value_retry = None
+        if ms > 1.15 * ms_instr:  # the same kernels ran faster WITH instrumentation: this loop was disturbed; measure again
+            value_retry = ms
+            n0 = _lib.launch_count
+            ms, logs = timed(resident, args.steps, read_loss=False)
+            launches = _lib.launch_count - n0
     for _ in range(max(args.warmup, 5)):  # warm the end-to-end path too (side-stream upload pool, pinned-memory registration)
         tr.train_step(host, 0)
     ms_e2e, logs = timed(host, args.steps, read_loss=True)
@@ -291,6 +305,13 @@ def main():
             m, _ = timed(bt, args.steps, read_loss=rl)
             print(f"[ablate] {name}: {m:.3f} ms/step", file=sys.stderr)
     e2e_retry = None
+    if ms > 1.15 * ms_e2e and value_retry is None:
+        # the resident loop cannot be slower than the same step fed from the host: it ran host-bound (a busy host on this
+        # box); re-measure it once and keep the first number in the line
+        value_retry = ms
+        with ClockSampler(local_rank) as clk:
+            timed(resident, args.steps, read_loss=False)
+            ms, _ = timed(resident, args.steps, read_loss=False)
     if ms_e2e > 1.3 * ms:
         # the step itself is unchanged (same kernels as `value`), so an end-to-end time far above value + upload time is a
         # disturbed host->device path (seen on some boxes right after start-up): re-measure once and keep both numbers
@@ -364,6 +385,7 @@ def main():
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "pinned_h2d_gbps": round(h2d_gbps, 1), "first_try_ms_per_step": e2e_retry},
+        "value_first_try_ms_per_step": value_retry,  # set when the resident loop ran host-bound (busy host) and was re-measured
         "gpu_launches": launches, "gpu_launches_note": "libcgan3d entry-point calls in the timed region; each enqueues >= 1 kernel",
         "roofline": roof, "cpu_baseline": cpu,
         "losses_last_step": {k: float(v.detach()) for k, v in logs.items()},
