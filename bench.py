@@ -346,6 +346,7 @@ def main():
                 "kernel": {"op": key[0], "impl": "tcgen05" if impl == 2 else "generic-cuda-core", "geom": list(key[2:]),
                            "launches_per_step": n / args.steps, "avg_ms": tot_ms / n},
                 "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms, "tcgen05_ms_per_step": tc_ms,
+                "instrumented_pass_ms_per_step": ms_instr,  # the pass these per-kernel times come from (events around every conv)
                 "step_tflops": pairs_per_step / world * PAIR_GFLOP_128 * (args.patch / 128) ** 3 / (ms * 1e-3) / 1e3,
                 }
         roof["step_frac_of_peak"] = roof["step_tflops"] / pk["bf16_sustained"]
