@@ -1,7 +1,9 @@
 """Micro-benchmark of the convolution kernels (BASELINE config C5 style): per-op device time with CUDA events.
 
-    python tools/bench_conv.py [--cases res,down,...] [--impls tc,generic] [--iters 20]
+    python tools/bench_conv.py [--cases res,down,...] [--impls tc,generic,cudnn] [--iters 20]
 Prints one JSON line per (case, op, impl): TFLOP/s of algorithmic 2*MAC work and the fraction of the measured bf16 peak.
+`cudnn` is the comparison line of SURVEY §8d: aten::convolution / convolution_backward in bf16 channels_last_3d with
+cudnn.benchmark = True on the same shapes (library code, never on the product path; non-transposed cases only).
 """
 from __future__ import annotations
 
@@ -63,6 +65,36 @@ def main():
         for opn in args.ops.split(","):
             opi = {"gather": 0, "scatter": 1, "wgrad": 2}[opn]
             for impl in args.impls.split(","):
+                if impl == "cudnn":
+                    if tr:
+                        continue
+                    torch.backends.cudnn.benchmark = True
+                    xc = big.permute(0, 4, 1, 2, 3)   # NCDHW view of the channels-last tensor (channels_last_3d strides)
+                    yc = small.permute(0, 4, 1, 2, 3)
+                    wc = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+                    st3, pd3 = [s, s, s], [p, p, p]
+                    bwd = torch.ops.aten.convolution_backward
+                    fn = {"gather": lambda: torch.ops.aten.convolution(xc, wc, None, st3, pd3, [1, 1, 1], False, [0, 0, 0], 1),
+                          "scatter": lambda: bwd(yc, xc, wc, None, st3, pd3, [1, 1, 1], False, [0, 0, 0], 1, [True, False, False]),
+                          "wgrad": lambda: bwd(yc, xc, wc, None, st3, pd3, [1, 1, 1], False, [0, 0, 0], 1, [False, True, False])}[opn]
+                    try:
+                        for _ in range(3):
+                            fn()
+                    except Exception as e:  # cuDNN has no engine for some thin shapes
+                        print(json.dumps({"case": name, "op": opn, "impl": impl, "error": str(e)[:120]}), flush=True)
+                        continue
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(args.iters):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / args.iters
+                    tf = flops / (ms * 1e-3) / 1e12
+                    print(json.dumps({"case": name, "op": opn, "impl": impl, "ms": round(ms, 4), "tflops": round(tf, 2),
+                                      "frac_of_bf16_burst_peak": round(tf / peak, 4), "gflop": round(flops / 1e9, 2)}), flush=True)
+                    continue
                 ii = {"tc": _lib.IMPL_TC, "generic": _lib.IMPL_GENERIC}[impl]
                 if impl == "tc" and _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, opi) != 2:
                     continue
