@@ -33,6 +33,7 @@ struct TcPlan {
   int Yt, nslabs, Yh;
   int xseg, nxseg;
   int mtiles, rows_alloc, nitems, b_stages;
+  int tps;  // filter taps per weight stage (3 = the dz taps of one (dx,dy): one barrier round trip and one commit per three taps)
   uint32_t plane_bytes, btile_bytes, box_bytes, tmem_cols, smem_bytes;
   int a_swz;  // 0: plane slab in Cin/8 chunks (SWIZZLE_NONE); 32/64/128: whole voxels, [row][Cin] in the matching swizzle mode
   int pair;   // 1: CTA pairs (cta_group::2): two columns per pair, each CTA holds half of the weight rows
@@ -91,7 +92,8 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *planes = smem;
   uint8_t *bt = planes + (size_t)kPlaneSlots * p.plane_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(bt + (size_t)p.b_stages * p.btile_bytes);
+  const uint32_t stage_bytes = (uint32_t)p.tps * p.btile_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bt + (size_t)p.b_stages * stage_bytes);
   uint64_t *plane_full = bars, *plane_empty = bars + kPlaneSlots;
   uint64_t *b_full = bars + 2 * kPlaneSlots, *b_empty = b_full + p.b_stages;
   uint64_t *tm_full = b_empty + p.b_stages, *tm_empty = tm_full + 2;
@@ -158,17 +160,18 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int wrows = (int)(p.btile_bytes >> 8);  // 256-byte rows of the weight map per (tap, half) tile
       for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen, live);) {
         for (int i = 0; i < xlen; ++i)
-          for (int tap = 0; tap < taps; ++tap, ++t) {
+          for (int tap = 0; tap < taps; tap += p.tps, ++t) {
             const uint32_t s = t % p.b_stages, use = t / p.b_stages;
             if (use > 0) tc::mbar_wait(&b_empty[s], (use - 1) & 1);
+            uint8_t *dst = bt + (size_t)s * stage_bytes;
             if constexpr (PAIR) {
-              if (cta_rank == 0) tc::mbar_expect_tx(&b_full[s], 2 * p.btile_bytes);
-              tc::tma_load_2d_2cta(bt + (size_t)s * p.btile_bytes, &tmW, &b_full[s], 0, (tap * 2 + (int)cta_rank) * wrows);
+              if (cta_rank == 0) tc::mbar_expect_tx(&b_full[s], 2 * stage_bytes);
+              for (int j = 0; j < p.tps; ++j)
+                tc::tma_load_2d_2cta(dst + (size_t)j * p.btile_bytes, &tmW, &b_full[s], 0, ((tap + j) * 2 + (int)cta_rank) * wrows);
               continue;
             }
-            tc::mbar_expect_tx(&b_full[s], p.btile_bytes);
-            tc::bulk_g2s(bt + (size_t)s * p.btile_bytes, reinterpret_cast<const uint8_t *>(wB) + (size_t)tap * p.btile_bytes,
-                         p.btile_bytes, &b_full[s]);
+            tc::mbar_expect_tx(&b_full[s], stage_bytes);
+            tc::bulk_g2s(dst, reinterpret_cast<const uint8_t *>(wB) + (size_t)tap * p.btile_bytes, stage_bytes, &b_full[s]);
           }
       }
     }
@@ -197,6 +200,8 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint64_t b_desc_hi = tc::make_desc(0, b_lbo, 128);
       const uint32_t a_kstep = p.a_swz ? 2u : (2 * a_lbo) >> 4, b_kstep = (2 * b_lbo) >> 4;  // descriptor address units (16 B)
       uint32_t e_base = 0, t = 0, acc = 0;
+      const bool grouped = p.tps == 3;
+      auto last_of_stage = [&](uint32_t j) { return !grouped || j == 2u; };
       int b, z0, zlen, y0, ylen, x0, xlen;
       bool live;
       for (ItemIter it(p); it.next(p, b, z0, zlen, y0, ylen, x0, xlen, live);) {
@@ -210,12 +215,14 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc::tc_fence_after();
             const uint32_t a_plane = (planes_u32 + slot * p.plane_bytes) >> 4;
             for (int dy = 0; dy < 3; ++dy)
-              for (int dz = 0; dz < 3; ++dz, ++t) {
+              for (int dz = 0; dz < 3; ++dz) {
                 const int tap = (dx * 3 + dy) * 3 + dz;
-                const uint32_t s = t % p.b_stages;
-                tc::mbar_wait(&b_full[s], (t / p.b_stages) & 1);
-                tc::tc_fence_after();
-                const uint64_t b_desc0 = b_desc_hi | (uint64_t)(((bt_u32 + s * p.btile_bytes) >> 4) & 0x3FFF);
+                const uint32_t s = t % p.b_stages, j = grouped ? (uint32_t)dz : 0u;  // tps is 1 or 3
+                if (j == 0) {
+                  tc::mbar_wait(&b_full[s], (t / p.b_stages) & 1);
+                  tc::tc_fence_after();
+                }
+                const uint64_t b_desc0 = b_desc_hi | (uint64_t)(((bt_u32 + s * stage_bytes + j * p.btile_bytes) >> 4) & 0x3FFF);
                 const uint32_t a_tap = a_plane + (uint32_t)(dy * p.Zh + dz) * a_row;
                 const uint64_t a_desc0 = a_desc_hi | (uint64_t)(a_tap & 0x3FFF);
                 const uint32_t d_tmem0 = tmem_base + q * (MT * p.N);
@@ -227,9 +234,10 @@ conv_s1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                       mma(d_tmem0 + mt * p.N, a_desc0 + (uint64_t)(mt * 128 * a_row + kk * a_kstep), b_desc0 + (uint64_t)(kk * b_kstep),
                           (uint32_t)((tap | kk) != 0));
                   }
-                  commit(&b_empty[s]);
+                  if (last_of_stage(j)) commit(&b_empty[s]);
                 }
                 __syncwarp();
+                if (last_of_stage(j)) ++t;
               }
             if (dx == 0 && leader) commit(&plane_empty[slot]);  // last use of input plane x-1
           }
@@ -408,7 +416,13 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
   p.Zt = (Z + p.nzt - 1) / p.nzt;
   p.Zh = p.Zt + 2;
   p.btile_bytes = (uint32_t)Cin * N * 2 / (p.pair ? 2 : 1);
-  p.b_stages = p.btile_bytes <= 8192 ? 4 : (p.btile_bytes <= 16384 ? 3 : 2);
+  {
+    static int tps_env = -1;
+    if (tps_env < 0) { const char *e = getenv("CGAN3D_TPS"); tps_env = e ? atoi(e) : 0; }
+    p.tps = tps_env == 1 ? 1 : (3 * p.btile_bytes <= 16384 ? 3 : 1);
+  }
+  const uint32_t stage_b = (uint32_t)p.tps * p.btile_bytes;
+  p.b_stages = stage_b <= 8192 ? 4 : (stage_b <= 16384 ? 3 : 2);
   double best_eff = 0;
   bool found = false;
   for (int Yt = 1; Yt <= Y && Yt + 2 <= 256; ++Yt) {
@@ -416,7 +430,7 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
     if (2 * mt * N > 512 || mt > 4) break;
     const int rows_alloc = ((mt * 128 + 2 * p.Zh + 2) + 31) / 32 * 32;  // 2*Cin*rows_alloc is a multiple of 1024 (swizzle atom)
     const uint32_t plane_bytes = (uint32_t)(Cin / 8) * rows_alloc * 16;
-    const uint32_t smem = kPlaneSlots * plane_bytes + p.b_stages * p.btile_bytes + 512;
+    const uint32_t smem = kPlaneSlots * plane_bytes + p.b_stages * stage_b + 512;
     if (rows_alloc * 16 > 16383 * 16) break;
     if (smem > kSmemLimit) break;
     const int nslabs = (Y + Yt - 1) / Yt;
@@ -435,7 +449,7 @@ static bool plan_s1(int B, int X, int Y, int Z, int Cin, int N, TcPlan &best) {
      // CTA pair at Cin = 64), well below the L2 latency of the next tile
     static int max_stages = -1;
     if (max_stages < 0) { const char *e = getenv("CGAN3D_B_STAGES"); max_stages = e ? atoi(e) : 12; }
-    while (q.b_stages < max_stages && q.smem_bytes + q.btile_bytes <= kSmemLimit) { q.b_stages += 1; q.smem_bytes += q.btile_bytes; }
+    while (q.b_stages < max_stages && q.smem_bytes + q.tps * q.btile_bytes <= kSmemLimit) { q.b_stages += 1; q.smem_bytes += q.tps * q.btile_bytes; }
   }
   q.a_swz = Cin <= 64 ? 2 * Cin : 0;
   q.box_bytes = (q.a_swz ? (uint32_t)q.a_swz : 16u) * q.Zh * q.Yh;
