@@ -42,6 +42,7 @@ struct WsPlan {
   int8_t acc_tap[kMaxWsMma][2][4];  // (dy*k+dz) of [MMA][M block][N block]; -1 = discard
   uint32_t rowbytesA, rowbytesB, a_bytes, srcB_bytes, stage_bytes, boxA_bytes, boxB_bytes, smem_bytes, tmem_cols;
   int debug;
+  int m128;  // stride-1, Cs == 64: M = 128 = dY[z-1] | dY[z] (two z-adjacent taps per MMA), N = 2 views (shift 0 and 2)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -106,7 +107,7 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
     }
   } else if (warp == 5) {
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(64, ncol, 1, 1);
+    const uint32_t idesc = tc::make_idesc_bf16(p.m128 ? 128 : 64, ncol, 1, 1);
     const uint64_t a_hi = tc::make_desc_sw_mn(0, p.rowbytesA, 8 * p.rowbytesA, p.rowbytesA);
     const uint64_t b_hi = tc::make_desc_sw_mn(0, p.lboB, 8 * p.rowbytesB, p.rowbytesB);
     const uint32_t stage0 = tc::smem_u32(stage_mem);
@@ -119,7 +120,7 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
       const uint32_t a0 = (stage0 + s * p.stage_bytes) >> 4, b0 = (stage0 + s * p.stage_bytes + p.a_bytes) >> 4;
       if (leader) {
         for (int j = 0; j < p.nmma; ++j) {
-          const uint32_t d = tmem_base + (uint32_t)((j >> 1) * ncol) + ((uint32_t)((j & 1) * 16) << 16);
+          const uint32_t d = p.m128 ? tmem_base + (uint32_t)(j * ncol) : tmem_base + (uint32_t)((j >> 1) * ncol) + ((uint32_t)((j & 1) * 16) << 16);
           uint64_t a_desc = a_hi | (uint64_t)(a0 & 0x3FFF);
           uint64_t b_desc = b_hi | (uint64_t)((b0 + ((uint32_t)p.row_shift[j] * p.rowbytesB >> 4)) & 0x3FFF);
           tc::umma_bf16(d, a_desc, b_desc, idesc, n != 0 ? 1u : 0u);
@@ -140,6 +141,23 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
     // epilogue: TMEM lane 32*warp + l: l < 16 -> accumulator 2g row 16*warp + l, l >= 16 -> accumulator 2g + 1
     tc::mbar_wait(done, 0);
     tc::tc_fence_after();
+    if (p.m128) {  // M = 128: TMEM lane 32*warp + l is accumulator row 32*warp + l = (block, channel)
+      const int m = warp * 32 + lane;
+      const int cs = m & 63, blk = m >> 6;
+      for (int j = 0; j < p.nmma; ++j)
+        for (int c0 = 0; c0 < ncol; c0 += 16) {
+          uint32_t v[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * ncol + c0), v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int nn = c0 + c;
+            const int src = nn / p.Cb, cb = nn - src * p.Cb;
+            const int t2 = p.acc_tap[j][blk][src];
+            if (t2 >= 0 && !p.debug) atomicAdd(&dw[((size_t)cs * p.Cb + cb) * p.taps + dx * p.k * p.k + t2], __uint_as_float(v[c]));
+          }
+        }
+    } else {
     const int m = warp * 16 + (lane & 15);
     const int cs = m % p.Cs, blk = m / p.Cs;
     const int ngroups = (p.nmma + 1) >> 1;
@@ -159,6 +177,7 @@ wgrad_s2_sw_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constan
           }
         }
       }
+    }
     }
   }
   tc::tc_fence_before();
@@ -216,6 +235,21 @@ static bool plan_ws(const cgan3d_conv_geom &g, WsPlan &p) {
         p.row_shift[nm] = (uint16_t)(by * p.Zh + bz);
         ++nm;
       }
+  } else if (g.Cs == 64 && !getenv("CGAN3D_WS_M64")) {
+    // M = 128: block 0 = dY[z-1], block 1 = dY[z] (the slab one row later); N blocks = the X halo slab 0 and 2 voxels later.
+    // (block 1, shift s) is tap dz = s, (block 0, shift s) is tap dz = s + 1: dz = 0, 1, 2 from one MMA of N = 2*Cb, which
+    // costs 84.5 cycles instead of the 96.9 of an M = 64, N = 3*Cb MMA that leaves half of the tensor rows idle.
+    p.m128 = 1; p.nblkA = 2;
+    p.nsrc = 1; p.nblkB = 2;
+    for (int dy = 0; dy < 3; ++dy) {
+      for (int blk = 0; blk < 2; ++blk)
+        for (int nb = 0; nb < 4; ++nb) {
+          const int dz = nb < 2 ? (blk == 1 ? 2 * nb : 2 * nb + 1) : -1;
+          p.acc_tap[nm][blk][nb] = (int8_t)((dz >= 0 && dz < 3) ? dy * 3 + dz : -1);
+        }
+      p.row_shift[nm] = (uint16_t)(dy * p.Zh);
+      ++nm;
+    }
   } else {
     p.nsrc = 1; p.nblkB = 3;
     for (int dy = 0; dy < 3; ++dy) {  // N block dz = the halo slab dz voxels later
@@ -226,7 +260,7 @@ static bool plan_ws(const cgan3d_conv_geom &g, WsPlan &p) {
     }
   }
   p.nmma = nm;
-  const int ngroups = (nm + 1) / 2;
+  const int ngroups = p.m128 ? nm : (nm + 1) / 2;
   const int ncol = p.nblkB * g.Cb;
   if (ngroups * ncol > 512 || ncol > 256) return false;
   auto sizes = [&](int Yt, int &kpad, int &rowsA, int &rowsB) {
@@ -254,7 +288,7 @@ static bool plan_ws(const cgan3d_conv_geom &g, WsPlan &p) {
   sizes(p.Yt, p.kpad, p.rowsA, p.rowsB);
   p.a_bytes = ((uint32_t)p.rowsA * p.rowbytesA + 1023) / 1024 * 1024;
   p.srcB_bytes = ((uint32_t)p.rowsB * p.rowbytesB + 1023) / 1024 * 1024;
-  p.lboB = s == 2 ? p.srcB_bytes : p.rowbytesB;
+  p.lboB = s == 2 ? p.srcB_bytes : (p.m128 ? 2 * p.rowbytesB : p.rowbytesB);
   p.stage_bytes = p.a_bytes + p.nsrc * p.srcB_bytes;
   p.boxA_bytes = p.rowbytesA * p.Zh * p.Yt;
   p.boxB_bytes = p.rowbytesB * p.Zh * p.Yh;
