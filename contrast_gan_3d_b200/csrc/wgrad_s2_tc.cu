@@ -212,6 +212,7 @@ static bool plan_ws(const cgan3d_conv_geom &g, WsPlan &p) {
   int nm = 0;
   if (s == 2) {
     p.nsrc = 4; p.nblkB = 4;
+    if (g.Cs == 64 && !getenv("CGAN3D_WS_M64")) { p.nblkA = 2; p.m128 = 1; }  // M = 128: dY[z-1] | dY[z], as for Cs == 32 at M = 64
     // MMA program: sub-grid shift (sy, sz) in {0,1}^2; tap d has parity class (d-1)&1 and shift (d - 1 + class) / 2
     auto cls = [](int d) { return (d - 1) & 1; };
     auto shf = [&](int d) { return (d - 1 + cls(d)) / 2; };
