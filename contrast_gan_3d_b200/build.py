@@ -14,7 +14,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "build"
 LIB = PKG / "libcgan3d.so"
-SOURCES = ["api_misc.cu", "conv_api.cu", "conv_generic.cu", "conv_tc.cu", "conv_tc_prog.cu", "conv_thin_tc.cu", "conv_d1_tc.cu", "wgrad_tc.cu", "wgrad_s2_tc.cu", "norm_act.cu", "loss_optim.cu"]
+SOURCES = ["api_misc.cu", "conv_api.cu", "conv_generic.cu", "conv_tc.cu", "conv_tc_prog.cu", "conv_tc_prog_ks1.cu", "conv_tc_prog_ks2.cu", "conv_tc_prog_ks4.cu", "conv_tc_prog_ks8.cu", "conv_thin_tc.cu", "conv_d1_tc.cu", "wgrad_tc.cu", "wgrad_s2_tc.cu", "norm_act.cu", "loss_optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "--expt-extended-lambda", "-I", str(ROOT / "include"), "-I", str(CSRC)]
 
@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(r.stderr)
         return str(obj)
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     r = subprocess.run([nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
