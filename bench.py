@@ -10,8 +10,9 @@ One "pair" = one opt + one subopt patch through that iteration = 363.417 GFLOP o
 
 Printed keys: see the task contract; `value` = device-timed with inputs resident in HBM, `e2e` = the same step
 through Trainer.train_step from pinned host buffers plus a device->host read of the loss.
-`--impl reference` times the reference algorithm's CPU path (the oracle port; the reference is pure Python over
-ATen and cannot travel to the GPU box) on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference `Trainer.train_step` on the host cores (the verbatim copy of the
+reference package that `oracle/make_ref.py` puts into the git-ignored `oracle/_ref/`, imported through
+`oracle/ref_shim.py`; the oracle port only when that copy is absent) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -133,36 +134,110 @@ def synth_batch(gen, n_opt, n_low, n_high, patch, pin=False):
     return [dict(data=opt, seg=None, name=[]), dict(data=low, seg=mm(n_low), name=[]), dict(data=high, seg=mm(n_high), name=[])]
 
 
-def run_reference(args):
-    """Reference arm: the reference algorithm's own CPU path (oracle port), all host threads, bounded sample."""
+def _reference_trainer(patch, n_sub):
+    """The UNMODIFIED reference Trainer (from oracle/_ref or /root/reference through oracle/ref_shim.py) on CPU, built the
+    way tests/golden/make_golden.py builds it: default G and D, Adam(2e-4, (0.5, 0.999)), weight clip 0.01, generator
+    trained every iteration.  Returns None when no copy of the reference is present."""
+    import numpy as np
     import torch
-    from oracle import cgan_oracle as O
+    from oracle import ref_shim
 
+    if not ref_shim.available():
+        return None
+    ref, T = ref_shim.load(), ref_shim.load_trainer()
+
+    class _NullLogger:
+        class _L:
+            @staticmethod
+            def log_loss(*a, **k):
+                pass
+
+        logger = _L()
+
+        def __call__(self, *a, **k):
+            pass
+
+        def end_hook(self):
+            pass
+
+    torch.manual_seed(0)
+    G = partial(ref.generator.ResnetGenerator, n_resnet_blocks=4, n_updownsample_blocks=2, init_channels_out=16)
+    D = partial(ref.discriminator.PatchGANDiscriminator, channels_in=1, init_channels_out=8, discriminator_depth=3,
+                negative_slope=0.2)
+    lo, hi = ref.scaler.FactorZeroCenterScaler(-1024, 1500, 600)(np.array([350, 450]))
+    adam = partial(torch.optim.Adam, lr=2e-4, betas=(0.5, 0.999))
+    tr = T.Trainer(10 ** 9, 2, None, 1, 1, 10 ** 9, 10 ** 9, G, D, adam, adam, ref.loss.HULoss(float(lo), float(hi), (n_sub, 1, *patch)),
+                   _NullLogger(), torch.device("cpu"), weight_clip=0.01, checkpoint_every=None)
+    tr.generator.train(); tr.critic.train()
+    return tr
+
+
+def _time_cpu_steps(patch, n_opt, n_low, n_high, warmup, steps, threads):
+    """Median seconds per full G+D step of the reference on CPU (reference Trainer when a copy is present, else the oracle
+    port), fp32, `threads` torch threads.  Returns (seconds, kind)."""
+    import statistics
+
+    import torch
+
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(1)
+    b = synth_batch(gen, n_opt, n_low, n_high, patch)
+    tr = _reference_trainer(patch, n_low + n_high)
+    if tr is not None:
+        kind = "reference"
+        b[0]["seg"] = torch.zeros_like(b[0]["data"], dtype=torch.bool)
+        step = lambda it: tr.train_step(b, it + 1)  # every iteration trains critic AND generator; it >= 1 never logs
+    else:
+        from oracle import cgan_oracle as O
+
+        kind = "port"
+        st = O.StepState(seed=0)
+        step = lambda it: O.train_step(st, b[0]["data"], b[1]["data"], b[2]["data"], b[1]["seg"], b[2]["seg"], it)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        step(it)
+        times.append(time.perf_counter() - t0)
+    return statistics.median(times[warmup:]), kind
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the step (its unmodified Trainer.train_step, copied into
+    oracle/_ref by oracle/make_ref.py; the oracle port only if that copy is missing), every host core this process may
+    use, on a bounded sample of the C3 workload (2 pairs of 128^3 per step; a 16-pair CPU step would take ~1 min).
+    The process hides the GPUs from torch: the reference's HULoss places its constants on cuda:current whenever CUDA is
+    available (model/loss.py:52-61), which would break its own CPU path."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    os.environ.pop("OMP_NUM_THREADS", None)  # torchrun exports OMP_NUM_THREADS=1 to its workers
+    real_stdout, sys.stdout = sys.stdout, sys.stderr  # the reference logs to stdout; keep stdout for the one JSON line
+    import torch
+
+    cores = len(os.sched_getaffinity(0))
     patch = (args.patch,) * 3
-    n_opt, n_low, n_high = 2, 1, 1  # bounded sample of the C3 workload: 2 pairs per step
-    pairs = n_opt
-    st = O.StepState(seed=0)
-    gen = torch.Generator().manual_seed(1)
-    b = synth_batch(gen, n_opt, n_low, n_high, patch)
-    times = []
-    for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        O.train_step(st, b[0]["data"], b[1]["data"], b[2]["data"], b[1]["seg"], b[2]["seg"], it)
-        times.append(time.perf_counter() - t0)
-    t = sum(times[args.warmup:]) / args.steps
-    v = pairs / t
-    sample = f"{n_opt} opt + {n_low} low + {n_high} high patches of 1x{args.patch}^3 per step, fp32, torch CPU"
+    n_opt, n_low, n_high = 2, 1, 1
+    steps = max(args.steps, 5) if not args.quick_cpu else args.steps
+    warmup = max(args.warmup, 2) if not args.quick_cpu else args.warmup
+    t, kind = _time_cpu_steps(patch, n_opt, n_low, n_high, warmup, steps, cores)
+    v = n_opt / t
+    one = None
+    if not args.quick_cpu:  # 1-thread line on BASELINE config C1 (2 pairs of 64^3): a 128^3 step takes ~30 s on one core
+        t1, _ = _time_cpu_steps((64,) * 3, 2, 1, 1, 1, 3, 1)
+        one = {"value": 2 / t1, "unit": "pairs/s", "cores": 1, "sample": "2 opt + 1 low + 1 high patches of 1x64^3 (C1), median of 3 after 1 warm-up"}
+        torch.set_num_threads(cores)
+    sample = (f"{n_opt} opt + {n_low} low + {n_high} high patches of 1x{args.patch}^3 per step, fp32, torch CPU, "
+              f"median of {steps} steps after {warmup} warm-ups")
     print(json.dumps({
         "impl": "reference", "metric": "patch_pairs_per_sec_gd_train_step", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"G+D WGAN train step (weight clip, Adam), 1x{args.patch}^3 HU-scaled patches", "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
+                         "one_thread": one},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=real_stdout)
 
 
 def main():
@@ -176,6 +251,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--conv-impl", default="auto", choices=["auto", "generic", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick-cpu", action="store_true", help="reference arm: exactly --steps/--warmup steps, no 1-thread line")
     ap.add_argument("--breakdown", default=None, help="write the per-conv-kernel device-time table of the timed region here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -362,18 +438,19 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        from oracle import cgan_oracle as O
-        st = O.StepState(seed=0)
-        g2 = torch.Generator().manual_seed(1)
-        b = synth_batch(g2, 2, 1, 1, patch)
-        ts = []
-        for it in range(3):
-            t0 = time.perf_counter()
-            O.train_step(st, b[0]["data"], b[1]["data"], b[2]["data"], b[1]["seg"], b[2]["seg"], it)
-            ts.append(time.perf_counter() - t0)
-        t = sum(ts[1:]) / 2
-        cpu = {"value": 2 / t, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"2 opt + 1 low + 1 high patches of 1x{args.patch}^3 per step (1 warm-up + 2 timed), fp32 torch CPU oracle"}
+        # The reference's CPU step, timed in a child process that hides the GPUs (see run_reference) and may use every core
+        # of this box: 2 warm-ups + 5 timed steps of 2 pairs at this patch size, median.
+        env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE")}
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count()))  # the child inherits the affinity: give it the whole box
+        except OSError:
+            pass
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "5", "--warmup", "2",
+                            "--patch", str(args.patch), "--quick-cpu"], capture_output=True, text=True, env=env, timeout=1200)
+        try:
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception:
+            cpu = {"error": (r.stderr or r.stdout)[-300:]}
 
     out = {
         "metric": "patch_pairs_per_sec_gd_train_step", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "cgan3d_tile_extract": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "cgan3d_tile_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cgan3d_tile_finalize": (_i, [_vp, _vp, _vp, _i64, _f, _f, _vp]),
+    "cgan3d_sub_resized": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None
@@ -83,11 +84,22 @@ launch_count = 0  # number of library entry-point calls that enqueue at least on
 
 
 def _ensure_built() -> Path:
-    if LIB_PATH.exists() and not os.environ.get("CGAN3D_REBUILD"):
-        return LIB_PATH
-    from . import build as _build  # nvcc required
+    """Path of an up-to-date libcgan3d.so.  The library is git-ignored and travels separately from the sources, so an
+    existing file is only trusted when its build stamp equals the digest of the current csrc/ + cgan3d.h (a stale binary
+    would be called through ctypes signatures that no longer match its ABI).  With nvcc present a mismatch triggers a
+    rebuild; without nvcc it is an error."""
+    from . import build as _build
 
-    return _build.build()
+    if os.environ.get("CGAN3D_REBUILD"):
+        return _build.build(force=True)
+    if LIB_PATH.exists() and _build.is_current():
+        return LIB_PATH
+    if _build.have_nvcc():
+        return _build.build()  # a no-op when the stamp matches
+    if LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} does not match the sources (build stamp != source digest) and nvcc is not available "
+                           f"to rebuild it")
+    raise RuntimeError(f"{LIB_PATH} is missing and nvcc is not available")
 
 
 def lib() -> C.CDLL:

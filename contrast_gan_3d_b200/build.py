@@ -35,10 +35,27 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "cgan3d.h"]
+def _deps():
+    return list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "cgan3d.h"]
+
+
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def is_current() -> bool:
+    """True when libcgan3d.so exists and was built from exactly the sources that are in the tree now."""
     stamp = OBJ / "stamp"
-    dig = _digest(deps)
+    return LIB.exists() and stamp.exists() and stamp.read_text() == _digest(_deps())
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    stamp = OBJ / "stamp"
+    dig = _digest(_deps())
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
         return LIB
     OBJ.mkdir(exist_ok=True)

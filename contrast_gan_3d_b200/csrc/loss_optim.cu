@@ -242,6 +242,26 @@ tile_finalize_kernel(const float *__restrict__ acc, const float *__restrict__ cn
     out[i] = (acc[i] / cnt[i]) * factor + shift;
 }
 
+// out = x - nearest_resize(att): the corrector's `patch - nn.Upsample(size=patch)(G(patch))` branch
+// (reference eval/CCTAContrastCorrector.py:42-52,79); index law of aten::upsample_nearest3d (legacy "nearest").
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
+  if (in_size == out_size) return dst;
+  if (out_size == 2 * in_size) return dst >> 1;
+  const float scale = (float)in_size / (float)out_size;
+  const int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+__global__ void __launch_bounds__(256)
+sub_resized_kernel(const float *__restrict__ x, const float *__restrict__ att, float *__restrict__ out, int B, int X, int Y, int Z,
+                   int Xa, int Ya, int Za) {
+  const int64_t total = (int64_t)B * X * Y * Z;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % Z), y = (int)((i / Z) % Y), xx = (int)((i / ((int64_t)Z * Y)) % X), b = (int)(i / ((int64_t)Z * Y * X));
+    const int64_t j = (((int64_t)b * Xa + nearest_src(xx, Xa, X)) * Ya + nearest_src(y, Ya, Y)) * Za + nearest_src(z, Za, Z);
+    out[i] = x[i] - att[j];
+  }
+}
+
 static inline int ew_blocks2(int64_t n) { return (int)mx<int64_t>(1, mn<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16)); }
 
 }  // namespace cg
@@ -379,6 +399,17 @@ int cgan3d_tile_accumulate(const float *tile, float *acc, float *cnt, int X, int
   const int64_t total = (int64_t)PX * PY * PZ;
   tile_accumulate_kernel<<<ew_blocks2(total), 256, 0, as_stream(stream)>>>(tile, acc, cnt, X, Y, Z, x0, y0, z0, PX, PY, PZ);
   CG_LAUNCH_CHECK("tile_accumulate");
+  return 0;
+}
+
+int cgan3d_sub_resized(const float *x, const float *att, float *out, int B, int X, int Y, int Z, int Xa, int Ya, int Za,
+                       void *stream) {
+  CG_CHECK_ARG(x && att && out, "sub_resized: NULL pointer");
+  CG_CHECK_SHAPE(B >= 0 && X > 0 && Y > 0 && Z > 0 && Xa > 0 && Ya > 0 && Za > 0, "sub_resized: bad sizes");
+  const int64_t total = (int64_t)B * X * Y * Z;
+  if (total == 0) return 0;
+  sub_resized_kernel<<<ew_blocks2(total), 256, 0, as_stream(stream)>>>(x, att, out, B, X, Y, Z, Xa, Ya, Za);
+  CG_LAUNCH_CHECK("sub_resized");
   return 0;
 }
 

@@ -14,8 +14,21 @@ from ._lib import call
 
 class FusedAdam(Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clip: float = 0.0):
-        defaults = dict(lr=lr, betas=betas, eps=eps, clip=clip)
+        # the torch.optim.Adam keys are carried (at their no-op values) so that a checkpoint written here can be stepped by
+        # the reference's torch.optim.Adam after load_state_dict, and vice versa (reference trainer/Trainer.py:311-339)
+        defaults = dict(lr=lr, betas=betas, eps=eps, clip=clip, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
         super().__init__(params, defaults)
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for group in self.param_groups:  # param groups loaded from a torch.optim.Adam checkpoint have no "clip"
+            group.setdefault("clip", 0.0)
+            if group.get("weight_decay", 0) or group.get("amsgrad", False) or group.get("maximize", False):
+                raise NotImplementedError("FusedAdam implements Adam without weight decay / amsgrad / maximize (the reference's settings)")
+        for st in self.state.values():  # torch.optim.Adam stores `step` as a tensor
+            if torch.is_tensor(st.get("step")):
+                st["step"] = int(st["step"].item())
 
     @torch.no_grad()
     def step(self, closure=None, clip: float | None = None):
@@ -25,7 +38,7 @@ class FusedAdam(Optimizer):
                 loss = closure()
         for group in self.param_groups:
             b1, b2 = group["betas"]
-            c = group["clip"] if clip is None else clip
+            c = group.get("clip", 0.0) if clip is None else clip
             by_step = {}  # tensors that share a step count go into one multi-tensor launch
             for p in group["params"]:
                 if p.grad is None:
@@ -35,6 +48,8 @@ class FusedAdam(Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if torch.is_tensor(st["step"]):
+                    st["step"] = int(st["step"].item())
                 st["step"] += 1
                 g = p.grad
                 if g.dtype != torch.float32 or not g.is_contiguous():

@@ -92,6 +92,10 @@ class Trainer:
     ):
         self.rng = rng
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            # an index-less "cuda" never compares equal to a tensor's "cuda:N": pin it down once so that device-resident
+            # batches are recognised as such
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.debug = debug
         self.train_log_sample_size, self.val_log_sample_size = None, None
         self.train_iterations = train_iterations
@@ -205,7 +209,7 @@ class Trainer:
         The destination is a persistent per-key staging tensor (no cross-stream traffic through the caching allocator):
         the copy waits for the previous step's consumers, the consumer stream must wait on the returned event.
         Returns (device tensor, event or None)."""
-        if all(t.device == self.device for t in parts):
+        if all(self._on_device(t) for t in parts):
             return (parts[0] if len(parts) == 1 else torch.cat(parts)), None
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -222,6 +226,9 @@ class Trainer:
         done = self._staging_done.get(key)
         if done is not None:
             self._copy_stream.wait_event(done)
+        if any(t.is_cuda for t in parts):
+            # a device-resident part was produced by kernels on the compute stream: the side-stream copy must see them
+            self._copy_stream.wait_stream(main)
         with torch.cuda.stream(self._copy_stream):
             o = 0
             for t in parts:
@@ -230,6 +237,9 @@ class Trainer:
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return buf, ev
+
+    def _on_device(self, t: Tensor) -> bool:
+        return t.is_cuda == (self.device.type == "cuda") and (not t.is_cuda or t.device.index == self.device.index)
 
     def _release_staging(self):
         """Mark the staging tensors as consumed by everything enqueued so far on the compute stream."""
@@ -251,7 +261,7 @@ class Trainer:
         flight still reads the other one (the similarity loss uses the input until the end of the step)."""
         _, low, high = patches
         parts = [low["data"], high["data"]]
-        if all(t.device == self.device for t in parts):
+        if all(self._on_device(t) for t in parts):
             return
         flip = 1 - getattr(self, "_prefetch_flip", 1)
         self._prefetch_flip = flip
@@ -340,19 +350,30 @@ class Trainer:
         self.generator.eval()
         z = torch.zeros(4, dtype=torch.float32, device=self.device)
         loss_sim, loss_G, loss_real_C, loss_fake_C = z.chunk(4)
+        loggable = []
         with torch.no_grad():
-            for _ in range(self.val_iterations):
+            for i in range(self.val_iterations):
                 for st in SCAN_TYPE_ORDER:
                     batch = next(val_loaders[st])
                     sample = batch["data"].to(self.device, non_blocking=True)
                     if st == 0:
                         loss_real_C -= self.loss_GAN(self.critic(sample))
                     else:
-                        _, sample_hat = self._generate(sample)
+                        attenuation, sample_hat = self._generate(sample)
                         loss_fake = self.loss_GAN(self.critic(sample_hat))
                         loss_fake_C += loss_fake
                         loss_G -= loss_fake
                         loss_sim += self.loss_similarity(sample_hat, sample)
+                    if i == 0 and st != 0 and loggable is not None:
+                        # first validation iteration: the LOW and HIGH batches go to the image logger (reference
+                        # Trainer.py:278-296)
+                        loggable.append([batch, sample_hat, attenuation])
+                        if len(loggable) == len(SCAN_TYPE_ORDER) - 1:
+                            patches, reconstructions, attenuations = list(zip(*loggable))
+                            self.maybe_set_log_images_sample_size("val", patches[0]["data"].shape)
+                            self.logger_interface(patches, list(reconstructions), list(attenuations), list(SCAN_TYPE_ORDER)[1:],
+                                                  train_iteration, "validation", self.val_log_sample_size)
+                            loggable = None
         self.critic.train()
         self.generator.train()
         val_loss = {"D": (loss_real_C + loss_fake_C) / self.val_iterations,

@@ -206,6 +206,11 @@ int cgan3d_tile_accumulate(const float *tile, float *acc, float *cnt, int X, int
                            int PX, int PY, int PZ, void *stream);
 int cgan3d_tile_finalize(const float *acc, const float *cnt, float *out, int64_t n, float shift, float factor,
                          void *stream);
+/* out[B][X][Y][Z] = x - nearest_resize(att[B][Xa][Ya][Za] -> [X][Y][Z]): the corrector's `patch - nn.Upsample(size=
+ * inference_patch_size)(G(patch))` branch, taken when the generator does not round-trip the patch size
+ * (eval/CCTAContrastCorrector.py:42-52,79); aten::upsample_nearest3d index law (src = floor(dst * in/out)).        */
+int cgan3d_sub_resized(const float *x, const float *att, float *out, int B, int X, int Y, int Z, int Xa, int Ya, int Za,
+                       void *stream);
 
 #ifdef __cplusplus
 }

@@ -500,7 +500,10 @@ def correct_scan_3d(params, buffers, ccta: np.ndarray, patch=(128, 128, 128), ba
                 p = ccta[x:x + patch[0], y:y + patch[1], z:z + patch[2]].astype(np.float32)
                 xs.append(torch.from_numpy(scale_hu(p).astype(np.float32))[None])
             xb = torch.stack(xs)
-            corrected = xb - generator_forward(params, buffers, xb, layers, train=True)
+            att = generator_forward(params, buffers, xb, layers, train=True)
+            if att.shape[2:] != xb.shape[2:]:  # nn.Upsample(size=inference_patch_size), default mode "nearest" (:42-52)
+                att = F.interpolate(att, size=tuple(patch))
+            corrected = xb - att
             for (x, y, z), c in zip(chunk, corrected):
                 acc[x:x + patch[0], y:y + patch[1], z:z + patch[2]] += c[0]
                 cnt[x:x + patch[0], y:y + patch[1], z:z + patch[2]] += 1

@@ -8,8 +8,9 @@ optional third-party packages at import time that are not installed in this imag
 `eval/CCTAContrastCorrector.py:7-8`), so we register empty stand-ins in
 `sys.modules` and import the reference modules unmodified.
 
-Only `tests/golden/make_golden.py` and reference-vs-oracle CPU tests use this; the
-reference tree does not exist on the GPU box, so nothing at run time may need it.
+`tests/golden/make_golden.py`, the reference-vs-oracle CPU tests and `bench.py`'s reference
+arm / `cpu_baseline` leg use this.  `/root/reference` does not exist on the GPU box: there the
+shim resolves to `oracle/_ref/` (a verbatim copy made by `oracle/make_ref.py`).
 """
 from __future__ import annotations
 
@@ -19,7 +20,11 @@ import sys
 import types
 from pathlib import Path
 
-REFERENCE_ROOT = Path("/root/reference")
+# The reference tree itself in the authoring container; on the GPU box (no /root/reference) the verbatim copy made by
+# oracle/make_ref.py (git-ignored, shipped with the snapshot).
+_LIVE = Path("/root/reference")
+_COPY = Path(__file__).resolve().parent / "_ref"
+REFERENCE_ROOT = _LIVE if (_LIVE / "contrast_gan_3D").is_dir() else _COPY
 
 _STUBS = {
     "batchgenerators": [],

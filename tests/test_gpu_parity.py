@@ -310,8 +310,13 @@ def test_train_steps_fp32_against_reference_golden(golden_dir, name, patch, step
     # logit means).  Later steps run from weights that went through Adam, whose first updates are
     # lr*g/(|g|+eps) ~ lr*sign(g): summation-order noise of 1e-7 in a near-zero gradient moves that weight by up to
     # 2*lr, so two correct fp32 implementations drift apart by O(lr) per step; the criterion is relaxed accordingly.
-    assert np.all(np.abs(losses[0] - ref[0]) <= 1e-4 * np.abs(ref[0]) + 1e-5), f"\n{losses}\n{ref}"
-    assert np.all(np.abs(losses[1:] - ref[1:]) <= 2e-3 * np.abs(ref[1:]) + 1e-4), f"\n{losses}\n{ref}"
+    # The control run tests/test_oracle_golden.py::test_fp32_multi_step_drift_control_against_fp64 shows ATen's own fp32 vs
+    # fp64 difference using 78 % of the strict criterion at step 2; the later steps are held to 5x the strict criterion.
+    strict = 1e-4 * np.abs(ref) + 1e-5
+    use = np.abs(losses - ref) / strict
+    print(f"fraction of the strict fp32 criterion used per step / loss:\n{use}")
+    assert np.all(use[0] <= 1.0), f"\n{losses}\n{ref}"
+    assert np.all(use[1:] <= 5.0), f"\n{losses}\n{ref}\n{use}"
     lr = 2e-4
     for prefix, mod in (("G/", tr.generator), ("D/", tr.critic)):
         for k, v in mod.state_dict().items():
@@ -347,7 +352,7 @@ def test_train_step_against_oracle_other_shape():
         logs = tr.train_step([dict(data=opt, seg=None, name=[]), dict(data=low, seg=ml, name=[]),
                               dict(data=high, seg=mh, name=[])], it)
         for k in KEYS:
-            rt, at = (1e-4, 1e-5) if it == 0 else (2e-3, 1e-4)  # see test_train_steps_fp32_against_reference_golden
+            rt, at = (1e-4, 1e-5) if it == 0 else (5e-4, 5e-5)  # see test_train_steps_fp32_against_reference_golden
             assert abs(float(logs[k].detach()) - ref[k]) <= rt * abs(ref[k]) + at, (it, k, float(logs[k].detach()), ref[k])
     for k, v in tr.generator.state_dict().items():
         r = {**st.gp, **st.gb}[k]
@@ -483,6 +488,57 @@ def test_corrector_against_oracle_small_volume():
     assert_close32(got, ref, rtol=1e-4, atol=2e-2, msg="corrected HU")  # HU units: 2e-2 HU == 3e-5 network units
 
 
+def test_corrector_upsample_branch_and_return_types():
+    """A patch size that the strided convs do not round-trip (30 -> 15 -> 8 -> 16 -> 32): the reference resizes the
+    attenuation map with nn.Upsample(size=patch) before subtracting it (eval/CCTAContrastCorrector.py:42-52,79).  Also the
+    reference's call surface: `correct_scan` alias, correct_scan_3D returns [1, W, H, D] network units on the device."""
+    from contrast_gan_3d_b200.data import FactorZeroCenterScaler
+    from contrast_gan_3d_b200.eval import CCTAContrastCorrector
+    from contrast_gan_3d_b200.model import ResnetGenerator
+
+    torch.manual_seed(0)
+    gp, gb = O.init_params(O.generator_layers())
+    rng = np.random.default_rng(1)
+    patch = (30, 32, 28)
+    ccta = np.clip(rng.normal(100, 300, size=(60, 32, 56)), -1024, 1500).astype(np.int16)
+    ref = O.correct_scan_3d(gp, gb, ccta, patch=patch, batch_size=2)
+    torch.manual_seed(0)
+    sc = FactorZeroCenterScaler(-1024, 1500, 600)
+    corr = CCTAContrastCorrector(partial(ResnetGenerator, 4, 2, 16), sc, torch.device(DEV), inference_patch_size=patch)
+    assert isinstance(corr.upsampler, torch.nn.Upsample) and corr.correct_scan == corr.correct_scan_3D
+    got = corr(ccta, batch_size=2)
+    assert_close32(got, ref, rtol=1e-4, atol=2e-2, msg="corrected HU (upsample branch)")
+    torch.manual_seed(0)
+    corr2 = CCTAContrastCorrector(partial(ResnetGenerator, 4, 2, 16), sc, torch.device(DEV), inference_patch_size=patch)
+    net = corr2.correct_scan(ccta, 2)
+    assert net.shape == (1, *ccta.shape) and net.is_cuda
+    assert_close32(sc.unscale(net).squeeze().cpu(), ref, rtol=1e-4, atol=2e-2, msg="correct_scan_3D return value")
+
+
+def test_corrector_c2_shape_quarter_volume_bf16():
+    """BASELINE config C2's tiling at a quarter of the volume (256 x 256 x 128 in 128^3 tiles, batches of 4: several
+    batches, so the train-mode BatchNorm grouping and the tile order matter), bf16 generator, against the fp32 oracle:
+    corrected HU within 2e-2 of the attenuation range (600 HU) => 12 HU + rtol."""
+    from contrast_gan_3d_b200.data import FactorZeroCenterScaler
+    from contrast_gan_3d_b200.eval import CCTAContrastCorrector
+    from contrast_gan_3d_b200.model import ResnetGenerator
+
+    torch.manual_seed(0)
+    gp, gb = O.init_params(O.generator_layers())
+    rng = np.random.default_rng(2)
+    ccta = np.clip(rng.normal(100, 300, size=(256, 256, 128)), -1024, 1500).astype(np.int16)
+    ref = O.correct_scan_3d(gp, gb, ccta, patch=(128, 128, 128), batch_size=4)
+    torch.manual_seed(0)
+    corr = CCTAContrastCorrector(partial(ResnetGenerator, 4, 2, 16, compute_dtype=torch.bfloat16),
+                                 FactorZeroCenterScaler(-1024, 1500, 600), torch.device(DEV), inference_patch_size=(128, 128, 128))
+    got = corr(ccta, batch_size=4)
+    assert got.shape == ccta.shape
+    err = (got - ref).abs()
+    att_ref = (ref - torch.from_numpy(ccta.astype(np.float32))).abs()  # |600 * G(x)|
+    assert float(err.max()) <= 2e-2 * 600 + 2e-2 * float(att_ref.max()), (float(err.max()), float(att_ref.max()))
+    assert float(err.mean()) <= 2.0, float(err.mean())  # HU
+
+
 # ------------------------------------------------------------------------------------------------------------
 # tcgen05 implicit-GEMM path
 # ------------------------------------------------------------------------------------------------------------
@@ -580,7 +636,7 @@ def test_tcgen05_strided_and_transposed_convs(case):
     if _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, bwd_op) == 2:
         pairs.append((bwd(_lib.IMPL_TC), bwd(_lib.IMPL_GENERIC), gx_ref, "dgrad"))
     else:
-        assert name == "critic_mid_k4" or "odd" in name or True
+        assert "odd" in name, f"{name}: dgrad of this layer should run on the tcgen05 path"
     torch.cuda.synchronize()
     for got, gen_, ref, nm in pairs:
         assert torch.isfinite(got.float()).all(), nm

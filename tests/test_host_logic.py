@@ -1,5 +1,6 @@
 """CPU-only tests: host logic of the package, the state_dict / init contract against the golden fixtures, and the
 C-ABI library (loads, exports every symbol include/cgan3d.h declares; no compute calls without a GPU)."""
+import copy
 import ctypes
 import re
 from functools import partial
@@ -154,3 +155,40 @@ def test_trainer_checkpoint_roundtrip_and_reference_layout(tmp_path):
     with pytest.raises(NotImplementedError):
         Trainer(10, 2, None, 1, 1, 1, 0, partial(ResnetGenerator, 1, 1, 4), partial(PatchGANDiscriminator, 1, 4, 1),
                 partial(FusedAdam), partial(FusedAdam), HULoss(0.1, 0.3), NullLogger(), torch.device("cpu"), weight_clip=None)
+
+
+def test_optimizer_state_cross_loads_with_torch_adam():
+    """Checkpoints are exchanged with the reference, whose optimizers are torch.optim.Adam (reference
+    experiments/basic_conf.py:55,67, trainer/Trainer.py:311-339): a state_dict of either optimizer must load into the
+    other and leave it able to step."""
+    from contrast_gan_3d_b200.optim import FusedAdam
+
+    torch.manual_seed(0)
+    p_ref = [torch.randn(5, requires_grad=True), torch.randn(3, 2, requires_grad=True)]
+    adam = torch.optim.Adam(p_ref, lr=2e-4, betas=(0.5, 0.999))
+    for p in p_ref:
+        p.grad = torch.randn_like(p)
+    adam.step(); adam.step()
+    # reference -> ours
+    p_my = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    fused = FusedAdam(p_my, lr=1e-3)
+    fused.load_state_dict(copy.deepcopy(adam.state_dict()))  # load_state_dict aliases same-dtype tensors
+    g = fused.param_groups[0]
+    assert g["clip"] == 0.0 and g["lr"] == 2e-4 and tuple(g["betas"]) == (0.5, 0.999)
+    for p, q in zip(p_my, p_ref):
+        st = fused.state[p]
+        assert isinstance(st["step"], int) and st["step"] == 2
+        assert torch.equal(st["exp_avg"], adam.state[q]["exp_avg"]) and torch.equal(st["exp_avg_sq"], adam.state[q]["exp_avg_sq"])
+    # ours -> reference: torch Adam must be able to STEP after loading (it reads weight_decay, amsgrad, maximize, ...)
+    adam2 = torch.optim.Adam([p.detach().clone().requires_grad_(True) for p in p_ref], lr=1e-3)
+    adam2.load_state_dict(copy.deepcopy(fused.state_dict()))
+    for p, q in zip(adam2.param_groups[0]["params"], p_ref):
+        p.grad = q.grad.clone()
+    adam2.step()
+    adam.step()
+    for p, q in zip(adam2.param_groups[0]["params"], p_ref):
+        assert torch.allclose(p, q, rtol=0, atol=0), "torch Adam resumed from a FusedAdam state_dict took a different step"
+    with pytest.raises(NotImplementedError):
+        sd = adam.state_dict()
+        sd["param_groups"][0]["amsgrad"] = True
+        fused.load_state_dict(sd)

@@ -188,3 +188,39 @@ def test_oracle_validate_against_reference_golden(golden_dir):
     ref = dict(zip(("D", "G", "sim"), g["val"]))
     for k in ref:
         assert abs(got[k] - ref[k]) <= 1e-4 * abs(ref[k]) + 1e-6, (k, got[k], ref[k])
+
+
+def test_fp32_multi_step_drift_control_against_fp64():
+    """Control run for the multi-step fp32 tolerance of tests/test_gpu_parity.py: the SAME oracle (ATen CPU) in fp32 and in
+    fp64 from identical seeded weights and inputs, three full G+D steps at 32^3.
+
+    Step 0 runs from identical weights and agrees to ~1e-6 relative.  From step 1 on the fp32 run has been through Adam,
+    whose first updates are lr * sign(g): rounding noise in near-zero gradients flips whole weight updates, and the
+    fp32-vs-fp64 loss difference grows by two orders of magnitude.  It uses most of the strict single-step criterion
+    |d| <= 1e-4 |ref| + 1e-5 (here: 78 % of it on the HU loss of step 2; asserted > 30 % to allow for other CPUs), so a second, independent fp32
+    implementation (another summation order: our CUDA kernels) cannot be held to that criterion after step 0; the GPU tests
+    use 5x the strict criterion for the later steps."""
+    def run(dt):
+        st = O.StepState(seed=0)
+        for d in (st.gp, st.gb, st.dp, st.db):
+            for k in d:
+                if d[k].is_floating_point():
+                    d[k] = d[k].to(dt)
+        st.opt_g, st.opt_d = O.AdamState(st.gp), O.AdamState(st.dp)
+        gen = torch.Generator().manual_seed(1)
+        rows = []
+        for it in range(3):
+            opt, low, high = (O.synthetic_patches(gen, (n, 1, 32, 32, 32)).to(dt) for n in (2, 1, 1))
+            ml, mh = (O.synthetic_masks(gen, (1, 1, 32, 32, 32)) for _ in range(2))
+            r = O.train_step(st, opt, low, high, ml, mh, it)
+            rows.append([r[k] for k in ("D", "G", "G-full", "sim", "HU")])
+        return np.array(rows)
+
+    a, b = run(torch.float32), run(torch.float64)
+    strict = 1e-4 * np.abs(b) + 1e-5
+    use = np.abs(a - b) / strict  # fraction of the strict criterion consumed by fp32 rounding alone
+    assert use[0].max() < 0.05, use[0]
+    assert use[1:].max() > 0.3, use            # the reference's own arithmetic nearly exhausts the strict criterion ...
+    assert use[1:].max() < 5.0, use            # ... and stays inside the relaxed one (5x) used for steps >= 1
+    rel = np.abs(a - b) / np.abs(b)
+    assert rel[1:].max() > 20 * rel[0].max(), rel  # the drift is produced by the optimizer steps, not by one forward pass
