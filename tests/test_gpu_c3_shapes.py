@@ -189,7 +189,7 @@ def test_train_steps_bf16_full_patch_size_post_step_weights():
             cos = float(du @ dr / (du.norm() * dr.norm() + 1e-30))
             same = float(((du * dr) > 0).double().mean())
             assert cos >= 0.9 and same >= 0.9, f"{k}: update cosine {cos:.4f}, same-direction fraction {same:.4f}"
-            assert float((v - r).abs().max()) <= 2 * 2e-4 * steps + 1e-6, k  # Adam's step bound
+            assert float((v - r).abs().max()) <= 4 * 2e-4 * steps, k  # a sign flip moves a weight by up to 2 lr per step; early Adam steps can exceed lr
             checked += 1
         else:  # BN gamma / beta, last_conv.bias: few entries, compare values
             assert torch.allclose(v, r, rtol=0, atol=2 * 2e-4 * steps + 1e-6), k
