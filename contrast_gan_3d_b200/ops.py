@@ -163,14 +163,63 @@ def conv_bnstats(g: ConvGeom, x, wp, transposed: bool):
     return out, sums
 
 
-def conv_wgrad(g: ConvGeom, big, small, impl=None):
+def conv_wgrad(g: ConvGeom, big, small, impl=None, out=None):
+    """dW (fp32, torch layout [Cs, Cb, k, k, k]); with `out` the kernel ACCUMULATES into it (beta = 1)."""
     dt = _dt(big.dtype)
-    dw = torch.empty((g.Cs, g.Cb, g.k, g.k, g.k), dtype=torch.float32, device=big.device)
+    dw = out if out is not None else torch.empty((g.Cs, g.Cb, g.k, g.k, g.k), dtype=torch.float32, device=big.device)
+    if out is not None and (out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != g.Cs * g.Cb * g.k ** 3):
+        raise ValueError("conv_wgrad: `out` must be a contiguous fp32 tensor of the weight's size")
     ws, n = _workspace(g, dt, _lib.OP_WGRAD, big.device)
     with _timed("wgrad", g, dt):
-        call("cgan3d_conv_wgrad", C.byref(g), dt, _p(big), _p(small), _p(dw), 0.0, _p(ws), n,
+        call("cgan3d_conv_wgrad", C.byref(g), dt, _p(big), _p(small), _p(dw), 0.0 if out is None else 1.0, _p(ws), n,
              _CONV_IMPL if impl is None else impl, _st())
     return dw
+
+
+# Weight-gradient sink (parallel.GradBucketReducer between prepare() and finish()): the wgrad kernel accumulates straight
+# into the parameter's gradient-bucket slice on a side stream instead of returning a fresh tensor to autograd, so that it
+# overlaps the HBM-bound BatchNorm-backward passes that follow on the compute stream.
+_GRAD_SINK = None
+_FWD_USES = {}  # id(weight) -> forward applications whose weight gradient has not been produced yet
+
+
+def set_grad_sink(sink) -> None:
+    global _GRAD_SINK
+    _GRAD_SINK = sink
+
+
+def _note_forward_use(weight) -> None:
+    _FWD_USES[id(weight)] = _FWD_USES.get(id(weight), 0) + 1
+
+
+def forget_forward_uses(params) -> None:
+    for p in params:
+        _FWD_USES.pop(id(p), None)
+
+
+def _weight_grad(weight, g: ConvGeom, big, small):
+    """The weight gradient of one conv application: returned to autograd, or (sink active) accumulated in place on the
+    sink's side stream, in which case None is returned and the sink is told when the parameter's last pending
+    application has been handled."""
+    sink = _GRAD_SINK
+    if sink is None or weight is None or not sink.accepts(weight):
+        if weight is not None:
+            n = _FWD_USES.get(id(weight), 0)
+            if n > 0:
+                _FWD_USES[id(weight)] = n - 1
+        return conv_wgrad(g, big, small)
+    main = torch.cuda.current_stream(big.device)
+    side = sink.side_stream(big.device)
+    side.wait_stream(main)  # `big` / `small` were produced on the compute stream
+    with torch.cuda.stream(side):
+        conv_wgrad(g, big, small, out=weight.grad)
+    big.record_stream(side)
+    small.record_stream(side)
+    left = _FWD_USES.get(id(weight), 1) - 1
+    _FWD_USES[id(weight)] = max(left, 0)
+    if left <= 0:
+        sink.direct_done(weight)
+    return None
 
 
 def reflect_pad(x, pad):
@@ -295,6 +344,9 @@ class ConvBlockFn(torch.autograd.Function):
         if cfg.out_f32:
             z = cast(z, torch.float32)
         ctx.cfg, ctx.g = cfg, g
+        ctx.wparam = weight if ctx.needs_input_grad[1] else None  # the parameter itself: its .grad may be the wgrad sink
+        if ctx.wparam is not None:
+            _note_forward_use(weight)
         ctx.x_dtype = x.dtype
         ctx.has_res = residual is not None
         ctx.res_dtype = None if residual is None else residual.dtype
@@ -347,7 +399,7 @@ class ConvBlockFn(torch.autograd.Function):
             dx = cast(dx, ctx.x_dtype)
         dw = None
         if ctx.needs_input_grad[1]:
-            dw = conv_wgrad(g, dy, xin) if spec.transposed else conv_wgrad(g, xin, dy)
+            dw = _weight_grad(ctx.wparam, g, dy, xin) if spec.transposed else _weight_grad(ctx.wparam, g, xin, dy)
         return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None
 
 
@@ -379,6 +431,9 @@ class GenTailFn(torch.autograd.Function):
             opt_hat = torch.empty_like(att)
         call("cgan3d_tanh_residual", _p(y), _p(bias.detach()), _p(sub), _p(att), _p(opt_hat), _dt(cfg.dtype), n, _st())
         ctx.cfg, ctx.g, ctx.x_dtype = cfg, g, x.dtype
+        ctx.wparam = weight if ctx.needs_input_grad[1] else None
+        if ctx.wparam is not None:
+            _note_forward_use(weight)
         ctx.save_for_backward(xin, wp, att)
         if opt_hat is None:
             return att, att.new_empty(0)
@@ -407,7 +462,7 @@ class GenTailFn(torch.autograd.Function):
             if spec.reflect and not cfg.pre_padded:
                 dx = reflect_pad_backward(dx, spec.pad)
             dx = cast(dx, ctx.x_dtype)
-        dw = conv_wgrad(g, xin, dy) if ctx.needs_input_grad[1] else None
+        dw = _weight_grad(ctx.wparam, g, xin, dy) if ctx.needs_input_grad[1] else None
         return dx, dw, dbias, None, None
 
 

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
+from .. import ops
 from ..model.loss import HULoss, WassersteinLoss, ZNCCLoss, fused_similarity_and_hu
 from ..optim import FusedAdam
 
@@ -130,6 +131,11 @@ class Trainer:
         self.loss_HU = hu_loss_instance
         self.logger_interface = logger_interface
         self.grad_reducer = grad_reducer
+        if grad_reducer is None and self.device.type == "cuda":
+            # world size 1: no collective; the reducer is only the side-stream weight-gradient sink (parallel.py)
+            from ..parallel import GradBucketReducer
+
+            self.grad_reducer = GradBucketReducer()
 
         self.iteration = 0
         self.checkpoint_every = checkpoint_every
@@ -286,6 +292,7 @@ class Trainer:
 
     def train_step(self, patches: List[dict], iteration: int) -> Dict[str, Tensor]:
         opt, low, high = patches
+        ops.forget_forward_uses(self.generator.parameters())  # a generator graph of a critic-only iteration is never back-propagated
         do_train_generator = iteration % self.train_generator_every == 0
         do_train_critic = iteration % self.train_critic_every == 0
         main = torch.cuda.current_stream(self.device)
