@@ -183,7 +183,8 @@ def test_train_steps_bf16_full_patch_size_post_step_weights():
         if k.endswith("num_batches_tracked"):
             assert int(v) == int(r) == steps, k
         elif "running_" in k:
-            assert torch.allclose(v, r, rtol=2e-2, atol=2e-3 * float(r.abs().max()) + 1e-6), (k, float((v - r).abs().max()))
+            # the stated bf16 criterion: |d| <= 2e-2 |ref| + 2e-2 max|ref|
+            assert torch.allclose(v, r, rtol=2e-2, atol=2e-2 * float(r.abs().max()) + 1e-6), (k, float((v - r).abs().max()))
         elif k.endswith("conv.weight") or k.endswith("last_conv.weight"):
             du, dr = (v - g0[k]).flatten().double(), (r - g0[k]).flatten().double()
             cos = float(du @ dr / (du.norm() * dr.norm() + 1e-30))
@@ -199,7 +200,7 @@ def test_train_steps_bf16_full_patch_size_post_step_weights():
         if k.endswith("num_batches_tracked"):
             assert int(v) == int(r) == 3 * steps, k  # three critic forward passes per step (Trainer.py:114,116,151)
         elif "running_" in k:
-            assert torch.allclose(v, r, rtol=3e-2, atol=3e-3 * float(r.abs().max()) + 1e-6), (k, float((v - r).abs().max()))
+            assert torch.allclose(v, r, rtol=2e-2, atol=2e-2 * float(r.abs().max()) + 1e-6), (k, float((v - r).abs().max()))
         else:
             assert float(v.abs().max()) <= 0.01 + 1e-7, k  # weight clip (Trainer.py:136-138)
             if k.endswith("conv.weight") or k == "model.last.weight":
