@@ -883,6 +883,7 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
 
 static bool plan_thin_c(const cgan3d_conv_geom &g, ThinCPlan &p);
 static size_t thin_c_workspace(const ThinCPlan &p);
+bool thin_w2_supported(const cgan3d_conv_geom &g);  // wgrad7_v2.cu
 
 // op 0: gather with Cb == 16, Cs == 1;  op 1: scatter with Cb == 1, Cs == 16
 static bool thin_b_shape(const cgan3d_conv_geom &g, int op) {
@@ -926,7 +927,7 @@ bool thin_supported(const cgan3d_conv_geom &g, int dtype, int op) {
   }
   if (op == 2) {
     ThinCPlan pc;
-    return plan_thin_c(g, pc);
+    return thin_w2_supported(g) || plan_thin_c(g, pc);
   }
   return false;
 }
@@ -940,6 +941,7 @@ size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   ThinBPlan pb;
   if ((op == 0 || op == 1) && plan_thin_b(g, op, pb)) return (size_t)kTapTilesB * kTileBytesB + 256;
   ThinCPlan pc;
+  if (op == 2 && thin_w2_supported(g)) return 0;
   if (op == 2 && plan_thin_c(g, pc)) return thin_c_workspace(pc);
   return 0;
 }
@@ -1123,8 +1125,13 @@ static bool plan_thin_c(const cgan3d_conv_geom &g, ThinCPlan &p) {
 
 static size_t thin_c_workspace(const ThinCPlan &p) { return (size_t)p.B * p.Xe * p.Ye * p.Zs * 16 + 256; }
 
+// wgrad7_v2.cu: the z-expansion is built in shared memory (no workspace), M = 128 x N = 128 MMAs
+bool thin_w2_supported(const cgan3d_conv_geom &g);
+int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st);
+
 int thin_wgrad_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, void *ws, size_t ws_bytes,
                    cudaStream_t st) {
+  if (thin_w2_supported(g)) return thin_w2_run(g, big, small, dw, beta, st);
   ThinCPlan p;
   if (!plan_thin_c(g, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin wgrad: shape not supported");
   const size_t need = thin_c_workspace(p);
