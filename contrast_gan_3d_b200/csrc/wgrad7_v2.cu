@@ -26,8 +26,11 @@ namespace cg {
 
 using bf16 = __nv_bfloat16;
 constexpr uint32_t kSmemLimitW2 = 232448 - 1024;
-constexpr int kRingW2 = 10;    // logical S16 plane slots (8 live + 2 in flight)
-constexpr int kMaxPrefW2 = 12; // staged 32-bit words per builder thread and step
+constexpr int kMaxRingW2 = 14;  // logical S16 plane slots: 8 live + 4 or 6 in flight (TMA runs 2 - 3 steps ahead of the MMAs)
+constexpr int kMaxPrefW2 = 22;    // staged 32-bit words per fetch thread and step
+constexpr int kBuildWarpsW2 = 6;  // warps 0-3 (also the epilogue), 6, 7 expand the operand
+constexpr int kFetchersW2 = 64;   // warps 8, 9 fetch and stage the raw Q1 words
+constexpr int kBuildersW2 = 256;  // threads on the named barrier shared by the build and fetch warps (see bar_sync_builders)
 
 struct ThinW2Plan {
   int B, Xs, Ys, Zs;  // S16 extents
@@ -37,8 +40,10 @@ struct ThinW2Plan {
   int Zt, Yt, nyt, L; // z rows per line (multiple of 16, >= Zs), S16 lines per step, y tiles, E lines per step (Yt + 7)
   int LW;             // staged words per Q1 line segment
   int rows, kblocks;  // rows per S16 slot (Yt * Zt), K blocks per step
-  int nphys, npairs;
+  int ring, nphys, npairs;  // logical ring size; physical slots (>= ring: the first nphys - ring slots are mirrored)
+  int nb16, inv_nb16;       // 16-row blocks per line and ceil(65536 / nb16)
   uint32_t slot_bytes, e2_bytes, box_bytes, stage_words, smem_bytes;
+  int debug;  // CGAN3D_W2_DEBUG (profiling aid, results are wrong): 1 = skip the operand build, 2 = skip the MMAs
 };
 
 struct SegIterW2 {
@@ -59,9 +64,9 @@ struct SegIterW2 {
   }
 };
 
-__device__ __forceinline__ void bar_sync_builders() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_builders() { static_assert(kBuildersW2 == 256, "barrier count"); asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__restrict__ q1, float *__restrict__ dw,
                  const __grid_constant__ ThinW2Plan p) {
   extern __shared__ uint8_t smem_raw[];
@@ -69,13 +74,13 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
   uint8_t *e2 = ring + (size_t)p.nphys * p.slot_bytes;          // 2 stages of the expanded operand, [L * Zt rows][2][8], SWIZZLE_32B
   uint32_t *stage = reinterpret_cast<uint32_t *>(e2 + 2 * (size_t)p.e2_bytes);  // raw Q1 line segments [2][L][LW]
   uint64_t *bars = reinterpret_cast<uint64_t *>(stage + p.stage_words);
-  uint64_t *s_full = bars, *s_empty = bars + kRingW2, *e_full = s_empty + kRingW2, *e_empty = e_full + 2, *done = e_empty + 2;
+  uint64_t *s_full = bars, *s_empty = bars + kMaxRingW2, *e_full = s_empty + kMaxRingW2, *e_empty = e_full + 2, *done = e_empty + 2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRingW2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&e_full[i], 4); tc::mbar_init(&e_empty[i], 1); }
+    for (int i = 0; i < kMaxRingW2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&e_full[i], kBuildWarpsW2); tc::mbar_init(&e_empty[i], 1); }
     tc::mbar_init(done, 1);
     tc::fence_barrier_init();
   }
@@ -99,18 +104,18 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
 
   if (warp == 4) {
     // ------------------------------------------------ S16 plane producer (TMA).  Planes are numbered by the order in which
-    // this CTA loads them (q): slot q % 10, mirrored at 10 + slot when that exists.  A segment loads its 6 warm-up planes
-    // and then two planes per step, always one step ahead of the MMAs.
+    // this CTA loads them (q): slot q % ring, mirrored at ring + slot when that exists.  A segment loads its 6 warm-up
+    // planes and then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmS);
       uint32_t q = 0;
       auto load_plane = [&](int xs, int b, int y0) {
-        const uint32_t slot = q % kRingW2, use = q / kRingW2;
+        const uint32_t slot = q % (uint32_t)p.ring, use = q / (uint32_t)p.ring;
         if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
-        const bool mirror = (int)slot + kRingW2 < p.nphys;
+        const bool mirror = (int)slot + p.ring < p.nphys;
         tc::mbar_expect_tx(&s_full[slot], mirror ? 2 * p.box_bytes : p.box_bytes);
         tc::tma_load_5d(ring + (size_t)slot * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
-        if (mirror) tc::tma_load_5d(ring + (size_t)(slot + kRingW2) * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
+        if (mirror) tc::tma_load_5d(ring + (size_t)(slot + p.ring) * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
         ++q;
       };
       int col, p0, plen;
@@ -137,7 +142,7 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
       w0 = waited;  // the segment's first window starts at its first warm-up plane
       for (int i = 0; i < plen; ++i, ++n, w0 += 2) {
         while (waited < w0 + 8) {
-          tc::mbar_wait(&s_full[waited % kRingW2], (waited / kRingW2) & 1);
+          tc::mbar_wait(&s_full[waited % (uint32_t)p.ring], (waited / (uint32_t)p.ring) & 1);
           ++waited;
         }
         const uint32_t st = n & 1;
@@ -146,12 +151,12 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
         const uint32_t a0 = (e2_u32 + st * p.e2_bytes) >> 4;
         uint32_t j = 0;
         while (j < 8) {  // runs of window planes that are contiguous in the (mirrored) ring
-          const uint32_t slot = (w0 + j) % kRingW2;
+          const uint32_t slot = (w0 + j) % (uint32_t)p.ring;
           const uint32_t run = mn<uint32_t>(8 - j, (uint32_t)p.nphys - slot);
           const uint32_t idesc = tc::make_idesc_bf16(128, (int)(16 * run), 1, 1);
           const uint32_t b0 = (ring_u32 + slot * p.slot_bytes) >> 4;
           const uint32_t d = tmem_base + 16 * j;
-          if (leader) {
+          if (leader && !(p.debug & 2)) {
             uint64_t a_desc = a_hi | (uint64_t)(a0 & 0x3FFF), b_desc = b_hi | (uint64_t)(b0 & 0x3FFF);
 #pragma unroll 4
             for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -165,108 +170,132 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
         }
         if (leader) {
           tc::umma_commit(&e_empty[st]);
-          tc::umma_commit(&s_empty[w0 % kRingW2]);        // the two oldest planes leave the window
-          tc::umma_commit(&s_empty[(w0 + 1) % kRingW2]);
+          tc::umma_commit(&s_empty[w0 % (uint32_t)p.ring]);        // the two oldest planes leave the window
+          tc::umma_commit(&s_empty[(w0 + 1) % (uint32_t)p.ring]);
         }
         __syncwarp();
       }
       // the six planes still resident belong to this segment only
       if (leader)
-        for (uint32_t k = 0; k < 6; ++k) tc::umma_commit(&s_empty[(w0 + k) % kRingW2]);
+        for (uint32_t k = 0; k < 6; ++k) tc::umma_commit(&s_empty[(w0 + k) % (uint32_t)p.ring]);
       __syncwarp();
     }
     if (leader) tc::umma_commit(done);
     __syncwarp();
   } else {
-    // ------------------------------------------------ warps 0..3: build the expanded operand, then the epilogue
-    const int tid = threadIdx.x;  // 0..127
-    const int zq0w = -p.P / 2;    // staged word 0 holds Q1 z elements (-P, -P + 1); P is even
+    // ------------------------------------------------ warps 0..3, 6, 7: build the expanded operand (0..3 then run the
+    // epilogue); warps 8, 9: fetch the raw Q1 words two steps ahead and stage them in shared memory.  The roles are split
+    // because the generic->async proxy fence that publishes the operand compiles to MEMBAR.ALL.CTA, which waits for every
+    // outstanding global load of the executing thread: a warp that prefetches AND builds exposes the full load latency
+    // (~1 us under load) in every step.
     const int ZqW = p.Zq >> 1;
-    const int total_words = 2 * p.L * p.LW;
-    uint32_t pref[kMaxPrefW2];
-    int meta[kMaxPrefW2];  // which (word, line, plane) of a step's staging area this thread fetches: the same every step
-#pragma unroll
-    for (int i = 0; i < kMaxPrefW2; ++i) {
-      const int idx = tid + 128 * i;
-      meta[i] = -1;
-      if (idx < total_words) {
-        const int w = idx % p.LW, hl = idx / p.LW;
-        meta[i] = w | ((hl % p.L) << 12) | ((hl / p.L) << 20);
-      }
-    }
-    auto fetch = [&](int b, int y0, int pair) {  // raw Q1 words of step (b, y0, pair) -> registers
+    // this CTA's steps are the flat (column, plane pair) indices [idx0, idx0 + total)
+    SegIterW2 range(ncols, p.npairs);
+    const long long idx0 = range.idx;
+    const uint32_t total = (uint32_t)(range.end - range.idx);
+    uint32_t n = 0;
+    if (warp >= 8) {
+      const int tid = (warp - 8) * 32 + lane;  // 0..63
+      const int total_words = 2 * p.L * p.LW;
+      // word i of this thread: staging index tid + 64 i = (h, l, w); rel = its offset from the step's base pointer; the
+      // z-range check does not depend on the step (meta < 0: never loaded)
+      int meta[kMaxPrefW2], rel[kMaxPrefW2];
 #pragma unroll
       for (int i = 0; i < kMaxPrefW2; ++i) {
-        uint32_t v = 0;
-        if (meta[i] >= 0) {
-          const int w = meta[i] & 0xFFF, l = (meta[i] >> 12) & 0xFF, h = meta[i] >> 20;
-          const int xq = 2 * pair + h - p.P, yq = y0 + l - p.P, wq = zq0w + w;
-          if ((unsigned)xq < (unsigned)p.Xq && (unsigned)yq < (unsigned)p.Yq && (unsigned)wq < (unsigned)ZqW)
-            v = __ldg(q1 + (((size_t)b * p.Xq + xq) * p.Yq + yq) * ZqW + wq);
+        const int idx = tid + kFetchersW2 * i;
+        meta[i] = -1; rel[i] = 0;
+        if (idx < total_words) {
+          const int w = idx % p.LW, hl = idx / p.LW, l = hl % p.L, h = hl / p.L;
+          const int wq = w - p.P / 2;  // staged word 0 holds Q1 z elements (-P, -P + 1); P is even
+          if ((unsigned)wq < (unsigned)ZqW) { meta[i] = l | (h << 8); rel[i] = (h * p.Yq + l) * ZqW + w; }
         }
-        pref[i] = v;
       }
-    };
-    uint32_t n = 0;
-    bool have = false;
-    int col, p0, plen;
-    SegIterW2 it(ncols, p.npairs);
-    bool more = it.next(col, p0, plen);
-    int i = 0;
-    if (more) {
-      const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
-      fetch(b, y0, p0);
-      have = true;
-    }
-    while (more) {
-      // 1. staged words of this step -> shared memory
-      bar_sync_builders();  // everybody has finished reading the previous step's staging area
+      auto fetch = [&](uint32_t k, uint32_t (&pref)[kMaxPrefW2]) {  // raw Q1 words of this CTA's step k -> registers
+        const long long flat = idx0 + k;
+        const int col = (int)(flat / p.npairs), pair = (int)(flat - (long long)col * p.npairs);
+        const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
+        const int xb = 2 * pair - p.P, yb = y0 - p.P;
+        // base may point outside the tensor (halo): it is only dereferenced for in-range (plane, line)
+        const uint32_t *base = q1 + ((long long)b * p.Xq * p.Yq + (long long)xb * p.Yq + yb) * ZqW - p.P / 2;
+        const bool hv0 = (unsigned)xb < (unsigned)p.Xq, hv1 = (unsigned)(xb + 1) < (unsigned)p.Xq;
 #pragma unroll
-      for (int k = 0; k < kMaxPrefW2; ++k) {
-        const int idx = tid + 128 * k;
-        if (idx < total_words) stage[idx] = pref[k];
-      }
-      bar_sync_builders();
-      // 2. prefetch the next step's words (their latency hides behind the build below)
-      int ncol = col, np0 = p0, nplen = plen, ni = i + 1;
-      bool nmore = true;
-      if (ni >= plen) { nmore = it.next(ncol, np0, nplen); ni = 0; }
-      if (nmore) {
-        const int nb = ncol / p.nyt, ny0 = (ncol - nb * p.nyt) * p.Yt;
-        fetch(nb, ny0, np0 + ni);
-      }
-      // 3. expanded rows: E2[l * Zt + r][h][j] = line(h, l)[r + j], j = 0..7
-      const uint32_t st = n & 1;
-      if (n >= 2) tc::mbar_wait(&e_empty[st], ((n >> 1) - 1) & 1);
-      uint8_t *dst = e2 + (size_t)st * p.e2_bytes;
-      const int rblocks = (p.Zt + 31) >> 5;
-      const int tasks = 2 * p.L * rblocks;
-      for (int t = warp; t < tasks; t += 4) {
-        const int rb = t % rblocks, hl = t / rblocks;
-        const int l = hl % p.L, h = hl / p.L;
-        const int r = rb * 32 + lane;
-        if (r < p.Zt) {
-          const uint32_t *line = stage + (size_t)(h * p.L + l) * p.LW + (r >> 1);
-          const uint32_t a0 = line[0], a1 = line[1], a2 = line[2], a3 = line[3], a4 = line[4];
-          const uint32_t sh = (uint32_t)(r & 1) << 4;
-          uint4 o;
-          o.x = __funnelshift_r(a0, a1, sh);
-          o.y = __funnelshift_r(a1, a2, sh);
-          o.z = __funnelshift_r(a2, a3, sh);
-          o.w = __funnelshift_r(a3, a4, sh);
-          const int row = l * p.Zt + r;
-          *reinterpret_cast<uint4 *>(dst + (size_t)row * 32 + (size_t)((h ^ ((row >> 2) & 1)) << 4)) = o;
+        for (int i = 0; i < kMaxPrefW2; ++i) {
+          uint32_t v = 0;
+          if (meta[i] >= 0) {
+            const bool hv = (meta[i] >> 8) ? hv1 : hv0;
+            if (hv && (unsigned)(yb + (meta[i] & 0xFF)) < (unsigned)p.Yq) v = __ldg(base + rel[i]);
+          }
+          pref[i] = v;
         }
+      };
+      auto put = [&](uint32_t k, uint32_t (&pref)[kMaxPrefW2]) {
+        bar_sync_builders();  // the builders have finished reading the previous step's staging area
+#pragma unroll
+        for (int i = 0; i < kMaxPrefW2; ++i)
+          if (tid + kFetchersW2 * i < total_words) stage[tid + kFetchersW2 * i] = pref[i];
+        bar_sync_builders();
+        if (k + 2 < total) fetch(k + 2, pref);
+      };
+      uint32_t prefA[kMaxPrefW2], prefB[kMaxPrefW2];
+      if (total > 0) fetch(0, prefA);
+      if (total > 1) fetch(1, prefB);
+      while (n < total) {
+        put(n, prefA);
+        if (++n >= total) break;
+        put(n, prefB);
+        ++n;
       }
-      tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&e_full[st]);
-      ++n;
-      col = ncol; p0 = np0; plen = nplen; i = ni; more = nmore;
+    } else {
+      const int bw = warp < 4 ? warp : warp - 2;  // builder warp 0..5
+      // E2[l * Zt + r][h][j] = line(h, l)[r + j], j = 0..7.  A warp iteration = 32 rows of one staged line (h, l): 5
+      // conflict-free LDS (neighbouring lanes read overlapping words), one funnel shift per output word (odd rows start
+      // in the upper half-word), one 16-byte STS (SWIZZLE_32B makes the 8 rows of a quarter-warp hit 8 different 16-byte
+      // bank groups).  The 2 L ipl iterations of a step are dealt to the 6 builder warps as contiguous ranges.
+      const int ipl = (p.Zt + 31) >> 5, iters = 2 * p.L * ipl, per = (iters + kBuildWarpsW2 - 1) / kBuildWarpsW2;
+      const int it0 = bw * per, it1 = mn(iters, it0 + per);
+      const int hl0 = it0 / ipl, rb0 = it0 - hl0 * ipl;
+      const uint32_t stage_u32 = tc::smem_u32(stage) + (uint32_t)(lane >> 1) * 4u;
+      const uint32_t lane_dst = (uint32_t)lane * 32u;
+      const uint32_t swz = (uint32_t)((lane >> 2) & 1);  // rows advance by 32 per iteration: the swizzle phase is the lane's
+      const uint32_t sh = (uint32_t)(lane & 1) << 4;
+      for (; n < total; ++n) {
+        bar_sync_builders();
+        bar_sync_builders();  // the fetch warps have written this step's staging area
+        const uint32_t st = n & 1;
+        if (n >= 2) tc::mbar_wait(&e_empty[st], ((n >> 1) - 1) & 1);
+        if (!(p.debug & 1)) {
+          const uint32_t dst_u32 = tc::smem_u32(e2) + st * p.e2_bytes + lane_dst;
+          int it = it0, hl = hl0, rb = rb0;
+          while (it < it1) {
+            const int h = hl >= p.L ? 1 : 0, l = hl - h * p.L;
+            uint32_t src = stage_u32 + (uint32_t)(hl * p.LW + rb * 16) * 4u;
+            uint32_t d = dst_u32 + (uint32_t)(l * p.Zt + rb * 32) * 32u + (((uint32_t)h ^ swz) << 4);
+            int r = rb * 32 + lane;
+#pragma unroll 2
+            for (; rb < ipl && it < it1; ++rb, ++it, src += 64, d += 1024, r += 32) {
+              if (r < p.Zt) {
+                uint32_t a0, a1, a2, a3, a4;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a0) : "r"(src));
+                asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(a1) : "r"(src));
+                asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(a2) : "r"(src));
+                asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(a3) : "r"(src));
+                asm volatile("ld.shared.b32 %0, [%1+16];" : "=r"(a4) : "r"(src));
+                const uint32_t o0 = __funnelshift_r(a0, a1, sh), o1 = __funnelshift_r(a1, a2, sh), o2 = __funnelshift_r(a2, a3, sh),
+                               o3 = __funnelshift_r(a3, a4, sh);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+              }
+            }
+            rb = 0;
+            ++hl;
+          }
+        }
+        tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&e_full[st]);
+      }
     }
-    (void)have;
     // epilogue: TMEM lane m = (dy = m >> 4, dx_lo = (m >> 3) & 1, dz = m & 7); column = 16 * j + c, dx = 6 - j + dx_lo
-    if (n > 0) {
+    if (n > 0 && warp < 4) {
       tc::mbar_wait(done, 0);
       tc::tc_fence_after();
       const int m = warp * 32 + lane, dy = m >> 4, dxl = (m >> 3) & 1, dz = m & 7;
@@ -313,20 +342,25 @@ static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
   p.Zt = (p.Zs + 15) / 16 * 16;
   if (p.Zt > 256) return false;
   p.LW = (p.Zt + 8) / 2 + 1;
+  p.nb16 = p.Zt / 16;
+  p.inv_nb16 = (65536 + p.nb16 - 1) / p.nb16;
   for (int Yt = mn(p.Ys, 8); Yt >= 1; --Yt) {
     const int L = Yt + 7;
-    if (2 * L * p.LW > 128 * kMaxPrefW2) continue;
+    if (2 * L * p.LW > kFetchersW2 * kMaxPrefW2) continue;
     const uint32_t slot = (uint32_t)Yt * p.Zt * 32u;
     const uint32_t e2b = ((uint32_t)L * p.Zt * 32u + 1023u) / 1024u * 1024u;
     const uint32_t stage_words = ((uint32_t)(2 * L * p.LW) + 3u) & ~3u;
     const uint32_t fixed = 2 * e2b + stage_words * 4 + 512;
     if (slot % 1024) continue;
-    int nphys = 16;
-    while (nphys >= kRingW2 && fixed + (uint32_t)nphys * slot > kSmemLimitW2) --nphys;
-    if (nphys < kRingW2) continue;
-    // prefer the mirrored ring (one MMA per window) over a larger y tile: 14 slots already keep 4 of 5 windows whole
-    if (nphys < 14 && Yt > 1) continue;
-    p.Yt = Yt; p.L = L; p.nphys = nphys;
+    int nphys = (int)((kSmemLimitW2 - mn(kSmemLimitW2, fixed)) / slot);
+    if (nphys > kMaxRingW2 + 6) nphys = kMaxRingW2 + 6;
+    // ring of 14 (TMA three steps ahead) when at least four of its slots can be mirrored, else 12; a mirrored slot keeps the
+    // window of 8 planes contiguous, so most steps need ONE N = 128 MMA per K block
+    const int ring = nphys >= kMaxRingW2 + 4 ? kMaxRingW2 : 12;
+    if (nphys < ring + 2 && Yt > 1) continue;
+    if (nphys < ring) continue;
+    if (nphys > ring + 6) nphys = ring + 6;  // windows start at even slots <= ring - 2: six mirrors make every window contiguous
+    p.Yt = Yt; p.L = L; p.nphys = nphys; p.ring = ring;
     p.slot_bytes = slot; p.e2_bytes = e2b; p.stage_words = stage_words;
     p.smem_bytes = fixed + (uint32_t)nphys * slot;
     break;
@@ -347,6 +381,7 @@ bool thin_w2_supported(const cgan3d_conv_geom &g) {
 int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, float *dw, float beta, cudaStream_t st) {
   ThinW2Plan p;
   if (!plan_w2(g, p)) return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin wgrad v2: shape not supported");
+  if (const char *e = getenv("CGAN3D_W2_DEBUG")) p.debug = atoi(e);
   const bool first = p.flip == 0;
   const void *s16 = first ? small : big, *q1 = first ? big : small;
   if ((reinterpret_cast<uintptr_t>(s16) & 15) || (reinterpret_cast<uintptr_t>(q1) & 3))
@@ -375,7 +410,7 @@ int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, f
   }
   const long long total = (long long)p.B * p.nyt * p.npairs;
   const int grid = (int)mn<long long>(total, (long long)num_sms());
-  wgrad7_v2_kernel<<<grid, 192, p.smem_bytes + 1024, st>>>(tmS, reinterpret_cast<const uint32_t *>(q1), dw, p);
+  wgrad7_v2_kernel<<<grid, 320, p.smem_bytes + 1024, st>>>(tmS, reinterpret_cast<const uint32_t *>(q1), dw, p);
   CG_LAUNCH_CHECK("wgrad7_v2_kernel");
   return 0;
 }

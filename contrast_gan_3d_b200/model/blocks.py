@@ -58,8 +58,8 @@ class ConvBlock(nn.Module):
             raise NotImplementedError("2D variant (conf_2D.py) is outside the B200 hot path (SURVEY §8f rank 4)")
         if norm_layer is None:
             norm_layer = nn.BatchNorm3d
-        if norm_layer not in (nn.BatchNorm3d, nn.Identity):
-            raise NotImplementedError("only BatchNorm3d / Identity norms are on the hot path (LayerNorm: §8f rank 4)")
+        if norm_layer not in (nn.BatchNorm3d, nn.Identity, nn.LayerNorm):
+            raise NotImplementedError(f"norm layer {norm_layer} is not supported (BatchNorm3d, Identity, LayerNorm are)")
         if padding_mode not in ("zeros", "reflect"):
             raise NotImplementedError(f"padding_mode {padding_mode!r}")
         args = {}
@@ -69,7 +69,13 @@ class ConvBlock(nn.Module):
             conv_class = nn.ConvTranspose3d
         self.conv = conv_class(channels_in, channels_out, kernel_size, stride=stride, bias=norm_layer == nn.Identity,
                                padding_mode=padding_mode, padding=padding, **args)
-        self.normalization = norm_layer(channels_out)
+        # reference blocks.py:40-45: LayerNorm over the layer's whole output [C, W, H, D] when a patch size is given
+        norm_shape, norm_args = channels_out, {}
+        if norm_layer == nn.LayerNorm and (ps := kwargs.get("patch_size")):
+            norm_shape = list(ps)
+            if (affine := kwargs.get("elementwise_affine")) is not None:
+                norm_args["elementwise_affine"] = affine
+        self.normalization = norm_layer(norm_shape, **norm_args)
         activation_kwargs = {}
         self.negative_slope = 0.0
         if (ns := kwargs.get("negative_slope")) is not None:
@@ -95,7 +101,34 @@ class ConvBlock(nn.Module):
                                          bn.running_var, bn.num_batches_tracked, cfg)
         return ops.ConvBlockFn.apply(x, self.conv.weight, self.conv.bias, None, None, residual, None, None, None, cfg)
 
+    def forward_cl_differentiable(self, x: Tensor) -> Tensor:
+        """act(norm(conv(x))) built from the twice-differentiable conv Functions (ops.ConvGatherFn / ScatterFn / WgradFn)
+        for critics WITHOUT BatchNorm (Identity or LayerNorm: the WGAN-GP configurations, reference
+        experiments/gradient_penalty_conf.py:14, gp_layernorm.py:10-13).  The convolutions are libcgan3d kernels in every
+        derivative order; bias / LayerNorm / LeakyReLU are plain ATen element-wise ops, which autograd differentiates twice."""
+        y = ops.conv_differentiable(x, self.conv.weight, self.spec, self.compute_dtype)
+        if self.conv.bias is not None:
+            y = y + self.conv.bias.to(y.dtype)
+        if isinstance(self.normalization, nn.LayerNorm):
+            ln = self.normalization
+            C = y.shape[-1]
+            if tuple(ln.normalized_shape) != (C, *y.shape[1:4]):
+                raise ValueError(f"LayerNorm shape {tuple(ln.normalized_shape)} does not match the layer output {(C, *y.shape[1:4])}")
+            # same element set as the reference's [C, W, H, D]; affine parameters are stored in that layout
+            wt = None if ln.weight is None else ln.weight.permute(1, 2, 3, 0)
+            bs = None if ln.bias is None else ln.bias.permute(1, 2, 3, 0)
+            y = torch.nn.functional.layer_norm(y.float(), y.shape[1:], wt, bs, ln.eps).to(y.dtype)
+        elif not isinstance(self.normalization, nn.Identity):
+            raise NotImplementedError("the twice-differentiable path has no BatchNorm (the reference pairs WGAN-GP with Identity / LayerNorm)")
+        if self.act_code == _lib.ACT_LRELU:
+            y = torch.nn.functional.leaky_relu(y, self.negative_slope)
+        elif self.act_code == _lib.ACT_RELU:
+            y = torch.relu(y)
+        return y
+
     def forward(self, x: Tensor) -> Tensor:
+        if isinstance(self.normalization, nn.LayerNorm):
+            return from_channels_last(self.forward_cl_differentiable(to_channels_last(x)).float())
         return from_channels_last(self.forward_cl(to_channels_last(x)).float())
 
 

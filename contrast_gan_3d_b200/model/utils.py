@@ -1,9 +1,37 @@
 """Shape arithmetic kept bit-compatible with reference model/utils.py:47-105."""
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Callable, List, Optional, Union
 
-from torch import nn
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+
+def wgan_gradient_penalty(real_batch: Tensor, fake_batch: Tensor, critic: nn.Module, device: Union[torch.device, str] = "cpu",
+                          lambda_: float = 10, rng: Optional[np.random.Generator] = None,
+                          eps_fn: Optional[Callable[[int], Tensor]] = None) -> Tensor:
+    """lambda * mean((||d critic(x~) / d x~||_2 - 1)^2) on random interpolates x~ = eps * real + (1 - eps) * fake, one eps per
+    sample (reference model/utils.py:12-41).  The critic must be twice differentiable: here that is a critic without
+    BatchNorm, whose convolutions are ops.ConvGatherFn / ConvScatterFn / ConvWgradFn in every derivative order.
+    `eps_fn(n)` (ours, optional) supplies the n interpolation coefficients; default torch.rand on `device`, as the reference."""
+    interp_sample_size, *t_shape = real_batch.shape
+    if len(real_batch) != len(fake_batch):
+        interp_sample_size = min(len(real_batch), len(fake_batch))
+        rng = rng or np.random.default_rng()
+        real_batch = real_batch[rng.integers(len(real_batch), size=interp_sample_size)]
+        fake_batch = fake_batch[rng.integers(len(fake_batch), size=interp_sample_size)]
+    shape = (interp_sample_size,) + (1,) * len(t_shape)
+    eps = torch.rand(shape, device=device) if eps_fn is None else eps_fn(interp_sample_size).reshape(shape).to(device)
+    eps = eps.expand_as(real_batch)
+    interpolation = eps * real_batch + (1 - eps) * fake_batch
+    if not interpolation.requires_grad:
+        interpolation.requires_grad_(True)
+    critic_logits = critic(interpolation)
+    gradients, *_ = torch.autograd.grad(outputs=critic_logits, inputs=interpolation, grad_outputs=torch.ones_like(critic_logits),
+                                        create_graph=True)
+    gradients_norm = gradients.reshape(gradients.shape[0], -1).norm(2, dim=-1)
+    return lambda_ * (gradients_norm - 1).square().mean()
 
 
 def convolution_output_shape(dims: List[int], c_out: int, kernel_size: int, padding: int, stride: int, dilation: int = 1,

@@ -536,3 +536,73 @@ class GenLossFn(torch.autograd.Function):
 def adam_step(p, g, m, v, lr, b1, b2, eps, step, clip=0.0):
     call("cgan3d_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(b1), float(b2), float(eps),
          int(step), float(clip), _st())
+
+
+# ------------------------------------------------------------------------------------------
+# Convolution primitives closed under differentiation (WGAN-GP: reference model/utils.py:12-41 differentiates the
+# critic's input gradient once more; Trainer.py:122-133).  A convolution is bilinear in (input, filter); its three
+# operators are each other's derivatives:
+#     gather (x, w) -> y       d/dx = scatter(gy, w)    d/dw = wgrad(x, gy)
+#     scatter(y, w) -> x       d/dy = gather (gx, w)    d/dw = wgrad(gx, y)
+#     wgrad  (x, y) -> w       d/dx = scatter(y, gw)    d/dy = gather (x, gw)
+# so every backward below is expressed through `.apply` of the other two and can itself be differentiated.
+# x / y are channels-last activations in the compute dtype, w the fp32 master filter [Cs, Cb, k, k, k].
+# ------------------------------------------------------------------------------------------
+class ConvGatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, big, w, g: ConvGeom):
+        _need_cuda(big, w)
+        ctx.g, ctx.dtype = g, big.dtype
+        ctx.save_for_backward(big, w)
+        return conv_gather(g, big.contiguous(), pack_weights(w.float(), big.dtype))
+
+    @staticmethod
+    def backward(ctx, gsmall):
+        big, w = ctx.saved_tensors
+        gsmall = gsmall.to(ctx.dtype)
+        dbig = ConvScatterFn.apply(gsmall, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dw = ConvWgradFn.apply(big, gsmall, ctx.g) if ctx.needs_input_grad[1] else None
+        return dbig, dw, None
+
+
+class ConvScatterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, small, w, g: ConvGeom):
+        _need_cuda(small, w)
+        ctx.g, ctx.dtype = g, small.dtype
+        ctx.save_for_backward(small, w)
+        return conv_scatter(g, small.contiguous(), pack_weights(w.float(), small.dtype))
+
+    @staticmethod
+    def backward(ctx, gbig):
+        small, w = ctx.saved_tensors
+        gbig = gbig.to(ctx.dtype)
+        dsmall = ConvGatherFn.apply(gbig, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dw = ConvWgradFn.apply(gbig, small, ctx.g) if ctx.needs_input_grad[1] else None
+        return dsmall, dw, None
+
+
+class ConvWgradFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, big, small, g: ConvGeom):
+        _need_cuda(big, small)
+        ctx.g = g
+        ctx.save_for_backward(big, small)
+        return conv_wgrad(g, big.contiguous(), small.contiguous())
+
+    @staticmethod
+    def backward(ctx, gw):
+        big, small = ctx.saved_tensors
+        dbig = ConvScatterFn.apply(small, gw, ctx.g) if ctx.needs_input_grad[0] else None
+        dsmall = ConvGatherFn.apply(big, gw, ctx.g) if ctx.needs_input_grad[1] else None
+        return dbig, dsmall, None
+
+
+def conv_differentiable(x: torch.Tensor, weight: torch.Tensor, spec: ConvSpec, dtype: torch.dtype) -> torch.Tensor:
+    """conv(x, weight) for a (non-transposed, zero-padded) layer through the twice-differentiable Functions."""
+    if spec.transposed or spec.reflect:
+        raise NotImplementedError("the twice-differentiable path covers the critic's zero-padded convolutions")
+    B, X, Y, Z, Cin = x.shape
+    assert Cin == spec.cin
+    g, _ = spec.geometry(B, (X, Y, Z))
+    return ConvGatherFn.apply(x.to(dtype), weight, g)

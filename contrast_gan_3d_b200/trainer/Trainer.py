@@ -23,6 +23,7 @@ from torch import Tensor, nn
 
 from .. import ops
 from ..model.loss import HULoss, WassersteinLoss, ZNCCLoss, fused_similarity_and_hu
+from ..model.utils import wgan_gradient_penalty
 from ..optim import FusedAdam
 
 logger = logging.getLogger(__name__)
@@ -111,8 +112,7 @@ class Trainer:
         self.gan_loss_w = gan_loss_weight
         self.gp_w = gp_weight
         self.weight_clip = weight_clip
-        if weight_clip is None:
-            raise NotImplementedError("WGAN-GP (weight_clip=None) needs double-backward convs: SURVEY §8f rank 1")
+        self.gp_eps_fn = None  # optional source of the WGAN-GP interpolation coefficients (tests); default torch.rand
 
         # construction order G then D matters for seeded-init parity (reference Trainer.py:83,89)
         self.generator: nn.Module = generator_class().to(self.device)
@@ -154,17 +154,24 @@ class Trainer:
         real_logits = self.critic(real)
         fake_logits = self.critic(reconstructions.detach())
         loss_critic = self.gan_loss_w * self.loss_GAN(fake_logits, real_logits)
+        if self.weight_clip is None:
+            # WGAN-GP (reference Trainer.py:122-130).  The reference passes `reconstructions` un-detached, which also sends the
+            # penalty's gradient into the generator; those generator gradients are dead (train_generator zeroes them before
+            # its own backward, Trainer.py:147), so the interpolates are built from the detached reconstructions here.
+            loss_critic = loss_critic + wgan_gradient_penalty(real, reconstructions.detach(), self.critic, device=self.device,
+                                                              lambda_=self.gp_w, rng=self.rng, eps_fn=self.gp_eps_fn)
         loss_critic.backward()
         if overlap:
             self.grad_reducer.finish(self.critic.parameters())
         elif self.grad_reducer is not None:
             self.grad_reducer.reduce(self.critic.parameters())
         if isinstance(self.optimizer_D, FusedAdam):
-            self.optimizer_D.step(clip=self.weight_clip)  # Adam + clamp(+-clip) in one kernel
+            self.optimizer_D.step(clip=self.weight_clip or 0.0)  # Adam + clamp(+-clip) in one kernel
         else:
             self.optimizer_D.step()
-            for p in self.critic.parameters():
-                p.data.clamp_(-self.weight_clip, self.weight_clip)
+            if self.weight_clip is not None:
+                for p in self.critic.parameters():
+                    p.data.clamp_(-self.weight_clip, self.weight_clip)
         if self.lr_scheduler_D is not None:
             self.lr_scheduler_D.step()
         return {"D": loss_critic}

@@ -71,8 +71,10 @@ def generator_layers(n_resnet_blocks=4, n_updownsample_blocks=2, init_channels_o
     return L
 
 
-def critic_layers(channels_in=1, init_channels_out=8, discriminator_depth=3, kernel_size=4, padding=1):
-    """Ordered conv layers of PatchGANDiscriminator (discriminator.py:23-81), BatchNorm variant."""
+def critic_layers(channels_in=1, init_channels_out=8, discriminator_depth=3, kernel_size=4, padding=1, norm="batch"):
+    """Ordered conv layers of PatchGANDiscriminator (discriminator.py:23-81).  norm: "batch" (default, BatchNorm3d),
+    "identity" (WGAN-GP, experiments/gradient_penalty_conf.py:14: conv bias instead of a norm, blocks.py:34) or "layer"
+    (experiments/gp_layernorm.py: LayerNorm over the layer's whole [C, W, H, D] output, elementwise_affine=False)."""
     L = [dict(name="model.first", kind="conv", cin=channels_in, cout=init_channels_out, k=kernel_size,
               stride=2, pad=padding, pad_mode="zeros", out_pad=0, norm=False, act="lrelu", bias=True)]
     out_ = init_channels_out
@@ -80,7 +82,8 @@ def critic_layers(channels_in=1, init_channels_out=8, discriminator_depth=3, ker
         in_ = min(2 ** n, 8) * init_channels_out
         out_ = min(2 ** (n + 1), 8) * init_channels_out
         L.append(dict(name=f"model.middle.{n}", kind="conv", cin=in_, cout=out_, k=kernel_size, stride=2,
-                      pad=padding, pad_mode="zeros", out_pad=0, norm=True, act="lrelu", bias=False))
+                      pad=padding, pad_mode="zeros", out_pad=0, norm={"batch": True, "identity": False, "layer": "layer"}[norm],
+                      act="lrelu", bias=norm == "identity"))
     L.append(dict(name="model.last", kind="conv", cin=out_, cout=1, k=kernel_size, stride=1, pad=padding,
                   pad_mode="zeros", out_pad=0, norm=False, act="none", bias=True, bare=True))
     return L
@@ -132,7 +135,7 @@ def init_params(layers) -> Tuple["OrderedDict[str, Tensor]", "OrderedDict[str, T
         params[pre + ".weight"] = w
         if b is not None:
             params[pre + ".bias"] = b
-        if l["norm"]:
+        if l["norm"] is True:
             n = l["name"] + ".normalization"
             params[n + ".weight"] = torch.ones(l["cout"])
             params[n + ".bias"] = torch.zeros(l["cout"])
@@ -150,7 +153,7 @@ def state_dict_order(layers) -> List[str]:
         keys.append(pre + ".weight")
         if l["bias"]:
             keys.append(pre + ".bias")
-        if l["norm"]:
+        if l["norm"] is True:
             n = l["name"] + ".normalization"
             keys += [n + ".weight", n + ".bias", n + ".running_mean", n + ".running_var",
                      n + ".num_batches_tracked"]
@@ -174,7 +177,9 @@ def _conv_block(x: Tensor, l, params, buffers, train: bool, negative_slope=0.2) 
             y = F.conv3d(x, w, b, stride=l["stride"], padding=0)
         else:
             y = F.conv3d(x, w, b, stride=l["stride"], padding=l["pad"])
-    if l["norm"]:
+    if l["norm"] == "layer":  # nn.LayerNorm(patch_size = [C, W, H, D], elementwise_affine=False), blocks.py:40-45
+        y = F.layer_norm(y, y.shape[1:])
+    elif l["norm"]:
         n = l["name"] + ".normalization"
         if train:
             buffers[n + ".num_batches_tracked"] += 1
@@ -307,9 +312,21 @@ class StepState:
         self.sched_steps_d = 0
 
 
+def gradient_penalty(dp, db, d_layers, real: Tensor, fake: Tensor, eps: Tensor, lambda_=10.0) -> Tensor:
+    """wgan_gradient_penalty (model/utils.py:12-41) for equal batch sizes; eps = the torch.rand((B,1,1,1,1)) draw."""
+    interpolation = eps.expand_as(real) * real + (1 - eps.expand_as(real)) * fake
+    if not interpolation.requires_grad:
+        interpolation.requires_grad_(True)
+    logits = critic_forward(dp, db, interpolation, d_layers)
+    grads, = torch.autograd.grad(logits, interpolation, torch.ones_like(logits), create_graph=True)
+    norm = grads.view(grads.shape[0], -1).norm(2, dim=-1)
+    return lambda_ * (norm - 1).square().mean()
+
+
 def train_step(st: StepState, opt: Tensor, low: Tensor, high: Tensor, mask_low: Tensor, mask_high: Tensor,
                iteration: int, hu_bounds=(0.18666666666666668, 0.35333333333333333), weight_clip=0.01,
-               train_generator_every=1, train_critic_every=1, w_gan=1.0, w_sim=1.0, w_hu=1.0) -> Dict[str, float]:
+               train_generator_every=1, train_critic_every=1, w_gan=1.0, w_sim=1.0, w_hu=1.0, gp_weight=10.0,
+               gp_eps: Optional[Tensor] = None) -> Dict[str, float]:
     """Trainer.train_step (Trainer.py:163-185) + train_critic (:108-142) + train_generator (:144-161)."""
     for p in list(st.gp.values()) + list(st.dp.values()):
         p.requires_grad_(True)
@@ -323,6 +340,9 @@ def train_step(st: StepState, opt: Tensor, low: Tensor, high: Tensor, mask_low: 
         real_logits = critic_forward(st.dp, st.db, opt, st.d_layers)  # :114
         fake_logits = critic_forward(st.dp, st.db, opt_hat.detach(), st.d_layers)  # :116
         loss_d = w_gan * wasserstein_loss(fake_logits, real_logits)  # :119-121
+        if weight_clip is None:  # :122-130 (the penalty's gradient into G is dead: zeroed at :147 before G's backward)
+            eps = gp_eps if gp_eps is not None else torch.rand((opt.shape[0], 1, 1, 1, 1))
+            loss_d = loss_d + gradient_penalty(st.dp, st.db, st.d_layers, opt, opt_hat.detach(), eps, gp_weight)
         names = list(st.dp.keys())
         grads = torch.autograd.grad(loss_d, [st.dp[k] for k in names])
         lr = multistep_lr(st.opt_d.lr, st.milestones, st.gamma, st.sched_steps_d)

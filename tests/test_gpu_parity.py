@@ -340,6 +340,105 @@ def test_train_steps_bf16_against_reference_golden(golden_dir):
     assert np.all(np.abs(losses - ref) <= 2e-2 * np.abs(ref) + atol), f"\n{losses}\n{ref}"
 
 
+def _make_gp_trainer(dtype, norm, patch):
+    from contrast_gan_3d_b200.model import HULoss, PatchGANDiscriminator, ResnetGenerator
+    from contrast_gan_3d_b200.optim import FusedAdam
+    from contrast_gan_3d_b200.trainer.Trainer import NullLogger, Trainer
+    from torch import nn
+
+    cargs = dict(negative_slope=0.2, compute_dtype=dtype)
+    if norm == "identity":
+        cargs.update(norm_layer=nn.Identity)
+    else:
+        cargs.update(norm_layer=nn.LayerNorm, patch_size=(1, *patch), elementwise_affine=False)
+    torch.manual_seed(0)
+    return Trainer(10, 2, None, 1, 1, 1, 0, partial(ResnetGenerator, 4, 2, 16, compute_dtype=dtype),
+                   partial(PatchGANDiscriminator, 1, 8, 3, **cargs),
+                   partial(FusedAdam, lr=1e-4, betas=(0.0, 0.9)), partial(FusedAdam, lr=1e-4, betas=(0.0, 0.9)),
+                   HULoss(0.18666666666666668, 0.35333333333333333), NullLogger(), torch.device(DEV), weight_clip=None,
+                   checkpoint_every=None)
+
+
+def _gp_eps(it):
+    def f(n):
+        torch.manual_seed(9000 + it)  # the recipe of tests/golden/make_golden_gp.py
+        return torch.rand((n, 1, 1, 1, 1))
+    return f
+
+
+@pytest.mark.parametrize("name,norm", [("train_steps_gp_32.npz", "identity"), ("train_steps_gp_layernorm_32.npz", "layer")])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_wgan_gp_train_steps_against_reference_golden(golden_dir, name, norm, dtype):
+    """WGAN-GP mode (weight_clip=None; reference Trainer.py:122-133, model/utils.py:12-41): three full steps against the
+    reference Trainer's logged losses, Identity-norm critic (gradient_penalty_conf.py) and LayerNorm critic
+    (gp_layernorm.py).  The penalty differentiates the critic's input gradient, i.e. runs every conv kernel of the critic
+    in second order (ops.ConvGatherFn / ConvScatterFn / ConvWgradFn)."""
+    g = np.load(golden_dir / name)
+    patch = (32, 32, 32)
+    tr = _make_gp_trainer(dtype, norm, patch)
+    assert list(tr.critic.state_dict().keys()) == list(g["D_keys"])
+    gen = torch.Generator().manual_seed(1)
+    tr.generator.train(); tr.critic.train()
+    rows = []
+    for it in range(3):
+        opt, low, high, ml, mh = _batches(gen, patch)
+        tr.gp_eps_fn = _gp_eps(it)
+        logs = tr.train_step([dict(data=opt, seg=None, name=[]), dict(data=low, seg=ml, name=[]), dict(data=high, seg=mh, name=[])], it)
+        rows.append([float(logs[k].detach()) for k in KEYS])
+    losses, ref = np.array(rows), g["losses"]
+    if dtype == torch.float32:
+        strict = 1e-4 * np.abs(ref) + 1e-5
+        use = np.abs(losses - ref) / strict
+        assert np.all(use[0] <= 1.0) and np.all(use[1:] <= 5.0), f"\n{losses}\n{ref}\n{use}"
+        lr, steps = 1e-4, 3
+        for prefix, mod in (("G/", tr.generator), ("D/", tr.critic)):
+            for k, v in mod.state_dict().items():
+                v = v.double().flatten().cpu()
+                fp = np.array([v.sum().item(), v.abs().sum().item(), (v * v).sum().item(), v[0].item(), v[-1].item()])
+                w, n = g[prefix + k], v.numel()
+                tol = np.array([2 * lr * steps * n ** 0.5, 2 * lr * steps * n ** 0.5, 2e-3 * abs(w[2]) + 1e-6, 2 * lr * steps, 2 * lr * steps])
+                assert np.all(np.abs(fp - w) <= 2e-3 * np.abs(w) + tol), (k, fp, w)
+    else:
+        atol = np.array([2e-2, 2e-3, 2e-3, 1e-3, 1e-3])  # D is dominated by the penalty (~10 = lambda * (|grad| - 1)^2)
+        assert np.all(np.abs(losses - ref) <= 2e-2 * np.abs(ref) + atol), f"\n{losses}\n{ref}"
+
+
+def test_gradient_penalty_second_order_gradients_vs_aten():
+    """d(penalty)/d(weights) of a two-layer bias + LeakyReLU critic: the twice-differentiable conv Functions against ATen's
+    double backward (fp32, CPU) on identical weights and inputs."""
+    from contrast_gan_3d_b200 import ops
+    from contrast_gan_3d_b200.model.utils import wgan_gradient_penalty
+
+    gen = torch.Generator().manual_seed(4)
+    w1 = (torch.randn((8, 1, 4, 4, 4), generator=gen) * 0.2).requires_grad_(True)
+    b1 = (torch.randn(8, generator=gen) * 0.1).requires_grad_(True)
+    w2 = (torch.randn((1, 8, 4, 4, 4), generator=gen) * 0.1).requires_grad_(True)
+    real, fake = torch.randn((3, 1, 12, 10, 8), generator=gen), torch.randn((3, 1, 12, 10, 8), generator=gen)
+    eps = torch.rand((3, 1, 1, 1, 1), generator=gen)
+
+    def critic_ref(x):
+        return F.conv3d(F.leaky_relu(F.conv3d(x, w1, b1, stride=2, padding=1), 0.2), w2, None, stride=1, padding=1)
+
+    pen_ref = wgan_gradient_penalty(real, fake, critic_ref, eps_fn=lambda n: eps)
+    gref = torch.autograd.grad(pen_ref, (w1, b1, w2))
+
+    w1d, b1d, w2d = (t.detach().to(DEV).requires_grad_(True) for t in (w1, b1, w2))
+    s1 = ops.ConvSpec(transposed=False, cin=1, cout=8, k=4, stride=2, pad=1)
+    s2 = ops.ConvSpec(transposed=False, cin=8, cout=1, k=4, stride=1, pad=1)
+
+    def critic_ours(x):  # [B, 1, X, Y, Z] -> channels-last
+        h = x.reshape(x.shape[0], *x.shape[2:], 1)
+        h = F.leaky_relu(ops.conv_differentiable(h, w1d, s1, torch.float32) + b1d, 0.2)
+        h = ops.conv_differentiable(h, w2d, s2, torch.float32)
+        return h.reshape(h.shape[0], 1, *h.shape[1:4])
+
+    pen = wgan_gradient_penalty(real.to(DEV), fake.to(DEV), critic_ours, device=DEV, eps_fn=lambda n: eps)
+    got = torch.autograd.grad(pen, (w1d, b1d, w2d))
+    assert pen.item() == pytest.approx(pen_ref.item(), rel=1e-4)
+    for a, b, nm in zip(got, gref, ("dw1", "db1", "dw2")):
+        assert_close32(a, b, rtol=1e-3, atol=1e-4 * float(b.abs().max()) + 1e-7, msg=nm)
+
+
 def test_train_step_against_oracle_other_shape():
     """Non-cubic patches and unequal low/high batch sizes, fp32, against the CPU oracle step."""
     patch = (32, 48, 32)

@@ -224,3 +224,25 @@ def test_fp32_multi_step_drift_control_against_fp64():
     assert use[1:].max() < 5.0, use            # ... and stays inside the relaxed one (5x) used for steps >= 1
     rel = np.abs(a - b) / np.abs(b)
     assert rel[1:].max() > 20 * rel[0].max(), rel  # the drift is produced by the optimizer steps, not by one forward pass
+
+
+@pytest.mark.parametrize("name,norm", [("train_steps_gp_32.npz", "identity"), ("train_steps_gp_layernorm_32.npz", "layer")])
+def test_wgan_gp_train_steps_against_reference_golden(golden_dir, name, norm):
+    """WGAN-GP mode (weight_clip=None): oracle vs the reference Trainer's logged losses and post-step weights for the
+    Identity-norm critic (gradient_penalty_conf.py) and the LayerNorm critic (gp_layernorm.py)."""
+    g = np.load(golden_dir / name)
+    st = O.StepState(seed=0, lr=1e-4, betas=(0.0, 0.9), d_layers=O.critic_layers(norm=norm))
+    assert O.state_dict_order(st.d_layers) == list(g["D_keys"])
+    gen = torch.Generator().manual_seed(1)
+    rows = []
+    for it in range(3):
+        opt, low, high = (O.synthetic_patches(gen, (n, 1, 32, 32, 32)) for n in (2, 1, 1))
+        ml, mh = (O.synthetic_masks(gen, (1, 1, 32, 32, 32)) for _ in range(2))
+        torch.manual_seed(9000 + it)
+        eps = torch.rand((2, 1, 1, 1, 1))
+        r = O.train_step(st, opt, low, high, ml, mh, it, weight_clip=None, gp_eps=eps)
+        rows.append([r[k] for k in ("D", "G", "G-full", "sim", "HU")])
+    np.testing.assert_allclose(np.array(rows), g["losses"], rtol=2e-5, atol=2e-6)
+    for prefix, d in (("G/", {**st.gp, **st.gb}), ("D/", {**st.dp, **st.db})):
+        for k, v in d.items():
+            np.testing.assert_allclose(_fp(v), g[prefix + k], rtol=1e-4, atol=1e-6, err_msg=k)
