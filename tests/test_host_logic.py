@@ -80,7 +80,13 @@ def test_unsupported_variants_say_so():
     with pytest.raises(NotImplementedError):
         ResnetGenerator(4, 2, 16, is_2D=True)
     with pytest.raises(NotImplementedError):
-        PatchGANDiscriminator(1, 8, 3, norm_layer=nn.LayerNorm, patch_size=(1, 128, 128, 128))
+        PatchGANDiscriminator(1, 8, 3, norm_layer=nn.InstanceNorm3d)
+    # the LayerNorm critic of experiments/gp_layernorm.py: per-layer normalised shapes as in reference discriminator.py:41-54
+    D = PatchGANDiscriminator(1, 8, 3, norm_layer=nn.LayerNorm, patch_size=(1, 128, 128, 32), elementwise_affine=False)
+    assert [tuple(m.normalization.normalized_shape) for m in D.model.middle] == [(16, 32, 32, 8), (32, 16, 16, 4), (64, 8, 8, 2)]
+    assert D.twice_differentiable and list(D.state_dict()) == ["model.first.conv.weight", "model.first.conv.bias",
+                                                               "model.middle.0.conv.weight", "model.middle.1.conv.weight",
+                                                               "model.middle.2.conv.weight", "model.last.weight", "model.last.bias"]
 
 
 def test_conv_geometry_matches_reference_shape_arithmetic(golden_dir):
@@ -152,9 +158,9 @@ def test_trainer_checkpoint_roundtrip_and_reference_layout(tmp_path):
     assert tr2.iteration == 7
     for a, b in zip(tr.critic.parameters(), tr2.critic.parameters()):
         assert torch.equal(a, b)
-    with pytest.raises(NotImplementedError):
-        Trainer(10, 2, None, 1, 1, 1, 0, partial(ResnetGenerator, 1, 1, 4), partial(PatchGANDiscriminator, 1, 4, 1),
-                partial(FusedAdam), partial(FusedAdam), HULoss(0.1, 0.3), NullLogger(), torch.device("cpu"), weight_clip=None)
+    # WGAN-GP mode constructs (weight_clip=None, reference Trainer.py:122-130)
+    Trainer(10, 2, None, 1, 1, 1, 0, partial(ResnetGenerator, 1, 1, 4), partial(PatchGANDiscriminator, 1, 4, 1, norm_layer=torch.nn.Identity),
+            partial(FusedAdam), partial(FusedAdam), HULoss(0.1, 0.3), NullLogger(), torch.device("cpu"), weight_clip=None)
 
 
 def test_optimizer_state_cross_loads_with_torch_adam():
