@@ -67,7 +67,7 @@ struct SegIterW2 {
 __device__ __forceinline__ void bar_sync_builders() { static_assert(kBuildersW2 == 256, "barrier count"); asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(320, 1)
-wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__restrict__ q1, float *__restrict__ dw,
+wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, float *__restrict__ dw,
                  const __grid_constant__ ThinW2Plan p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // nphys S16 plane slots, [rows][16 ch], SWIZZLE_32B (TMA)
@@ -79,7 +79,7 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxRingW2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < kMaxRingW2; ++i) { tc::mbar_init(&s_full[i], 32); tc::mbar_init(&s_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&e_full[i], kBuildWarpsW2); tc::mbar_init(&e_empty[i], 1); }
     tc::mbar_init(done, 1);
     tc::fence_barrier_init();
@@ -103,31 +103,51 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
   const long long ncols = (long long)p.B * p.nyt;
 
   if (warp == 4) {
-    // ------------------------------------------------ S16 plane producer (TMA).  Planes are numbered by the order in which
-    // this CTA loads them (q): slot q % ring, mirrored at ring + slot when that exists.  A segment loads its 6 warm-up
-    // planes and then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
-    if (lane == 0) {
-      tc::tma_prefetch_desc(&tmS);
-      uint32_t q = 0;
-      auto load_plane = [&](int xs, int b, int y0) {
-        const uint32_t slot = q % (uint32_t)p.ring, use = q / (uint32_t)p.ring;
-        if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
-        const bool mirror = (int)slot + p.ring < p.nphys;
-        tc::mbar_expect_tx(&s_full[slot], mirror ? 2 * p.box_bytes : p.box_bytes);
-        tc::tma_load_5d(ring + (size_t)slot * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
-        if (mirror) tc::tma_load_5d(ring + (size_t)(slot + p.ring) * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
-        ++q;
-      };
-      int col, p0, plen;
-      for (SegIterW2 it(ncols, p.npairs); it.next(col, p0, plen);) {
-        const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
-        for (int xs = 2 * p0 - 6; xs < 2 * p0; ++xs) load_plane(xs, b, y0);
-        for (int i = 0; i < plen; ++i) {
-          load_plane(2 * (p0 + i), b, y0);
-          load_plane(2 * (p0 + i) + 1, b, y0);
+    // ------------------------------------------------ S16 plane producer.  Planes are numbered by the order in which this
+    // CTA loads them (q): slot q % ring, mirrored at ring + slot when that exists.  A segment loads its 6 warm-up planes and
+    // then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
+    // The copies are 16-byte cp.async (LDGSTS), NOT TMA: a SWIZZLE_32B tensor map is limited to 32-byte inner rows, and the
+    // TMA engine then issues one 32-byte request per voxel (~3 cycles each: the first version of this kernel could not
+    // load its planes faster than one step per 2000 cycles, whatever the MMAs did).  A warp-wide cp.async covers 512
+    // contiguous bytes = four full 128-byte lines; the SWIZZLE_32B pattern is applied to the destination address, voxels
+    // outside the tensor are zero-filled (src-size 0), and completion is reported to the slot's mbarrier by the hardware.
+    uint32_t q = 0;
+    const uint32_t ring_u32 = tc::smem_u32(ring);
+    const uint8_t *s16b = reinterpret_cast<const uint8_t *>(s16);
+    const uint32_t half = (uint32_t)lane & 1u;
+    auto load_plane = [&](int xs, int b, int y0) {
+      const uint32_t slot = q % (uint32_t)p.ring, use = q / (uint32_t)p.ring;
+      if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
+      const bool mirror = (int)slot + p.ring < p.nphys;
+      const bool plane_ok = (unsigned)xs < (unsigned)p.Xs;
+      const uint32_t dst0 = ring_u32 + slot * p.slot_bytes;
+      const uint32_t moff = (uint32_t)p.ring * p.slot_bytes;
+      for (int yl = 0; yl < p.Yt; ++yl) {
+        const bool line_ok = plane_ok && (y0 + yl) < p.Ys;
+        const uint8_t *src_line = s16b + ((((size_t)b * p.Xs + (plane_ok ? xs : 0)) * p.Ys + (line_ok ? y0 + yl : 0)) * (size_t)p.Zs) * 32u;
+        for (int z = lane >> 1; z < p.Zt; z += 16) {
+          const uint32_t row = (uint32_t)(yl * p.Zt + z);
+          const uint32_t dst = dst0 + row * 32u + ((half ^ ((row >> 2) & 1u)) << 4);
+          const bool ok = line_ok && z < p.Zs;
+          const uint8_t *src = ok ? src_line + (size_t)z * 32u + half * 16u : s16b;
+          const uint32_t nbytes = ok ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+          if (mirror) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + moff), "l"(src), "r"(nbytes) : "memory");
         }
       }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&s_full[slot])) : "memory");
+      ++q;
+    };
+    int col, p0, plen;
+    for (SegIterW2 it(ncols, p.npairs); it.next(col, p0, plen);) {
+      const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
+      for (int xs = 2 * p0 - 6; xs < 2 * p0; ++xs) load_plane(xs, b, y0);
+      for (int i = 0; i < plen; ++i) {
+        load_plane(2 * (p0 + i), b, y0);
+        load_plane(2 * (p0 + i) + 1, b, y0);
+      }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer
     const bool leader = tc::elect_one();
@@ -147,6 +167,7 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
         }
         const uint32_t st = n & 1;
         tc::mbar_wait(&e_full[st], (n >> 1) & 1);
+        tc::fence_proxy_async();  // the planes were written by cp.async (generic proxy); the MMAs read through the async proxy
         tc::tc_fence_after();
         const uint32_t a0 = (e2_u32 + st * p.e2_bytes) >> 4;
         uint32_t j = 0;
@@ -319,12 +340,6 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFnW2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-void *tc_encode_fn_ptr();              // conv_tc.cu
-CUtensorMapL2promotion tc_l2_promo();  // conv_tc.cu
-
 static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
   static int off = -1;
   if (off < 0) off = getenv("CGAN3D_WGRAD7_V1") ? 1 : 0;
@@ -390,18 +405,6 @@ int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, f
     cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)16 * 343 * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "tcgen05 thin wgrad v2 memset");
   }
-  EncodeTiledFnW2 enc = reinterpret_cast<EncodeTiledFnW2>(tc_encode_fn_ptr());
-  if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
-  CUtensorMap tmS;
-  {
-    const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zs, (cuuint64_t)p.Ys, (cuuint64_t)p.Xs, (cuuint64_t)p.B};
-    const cuuint64_t gstr[4] = {32, (cuuint64_t)p.Zs * 32, (cuuint64_t)p.Ys * p.Zs * 32, (cuuint64_t)p.Xs * p.Ys * p.Zs * 32};
-    const cuuint32_t box[5] = {16, (cuuint32_t)p.Zt, (cuuint32_t)p.Yt, 1, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(s16), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, tc_l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (thin wgrad v2) failed with %d", (int)r);
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad7_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitW2 + 1024);
@@ -410,7 +413,7 @@ int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, f
   }
   const long long total = (long long)p.B * p.nyt * p.npairs;
   const int grid = (int)mn<long long>(total, (long long)num_sms());
-  wgrad7_v2_kernel<<<grid, 320, p.smem_bytes + 1024, st>>>(tmS, reinterpret_cast<const uint32_t *>(q1), dw, p);
+  wgrad7_v2_kernel<<<grid, 320, p.smem_bytes + 1024, st>>>(reinterpret_cast<const bf16 *>(s16), reinterpret_cast<const uint32_t *>(q1), dw, p);
   CG_LAUNCH_CHECK("wgrad7_v2_kernel");
   return 0;
 }

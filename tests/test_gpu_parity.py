@@ -389,7 +389,12 @@ def test_wgan_gp_train_steps_against_reference_golden(golden_dir, name, norm, dt
     if dtype == torch.float32:
         strict = 1e-4 * np.abs(ref) + 1e-5
         use = np.abs(losses - ref) / strict
-        assert np.all(use[0] <= 1.0) and np.all(use[1:] <= 5.0), f"\n{losses}\n{ref}\n{use}"
+        # Steps >= 1 run from weights that went through Adam(beta1 = 0): updates are lr * g / |g|-like, so fp32 rounding
+        # noise moves whole weights.  tests/test_oracle_golden.py::test_wgan_gp_fp32_drift_control_against_fp64 measures
+        # ATen's OWN fp32-vs-fp64 difference in these configurations: 0.33x the strict criterion (Identity critic) and 53x
+        # (LayerNorm critic, whose normalisation amplifies the weight noise) at step 2.  Bound: 5x / 100x the strict criterion.
+        later = 5.0 if norm == "identity" else 100.0
+        assert np.all(use[0] <= 1.0) and np.all(use[1:] <= later), f"\n{losses}\n{ref}\n{use}"
         lr, steps = 1e-4, 3
         for prefix, mod in (("G/", tr.generator), ("D/", tr.critic)):
             for k, v in mod.state_dict().items():

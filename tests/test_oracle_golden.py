@@ -246,3 +246,32 @@ def test_wgan_gp_train_steps_against_reference_golden(golden_dir, name, norm):
     for prefix, d in (("G/", {**st.gp, **st.gb}), ("D/", {**st.dp, **st.db})):
         for k, v in d.items():
             np.testing.assert_allclose(_fp(v), g[prefix + k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+def test_wgan_gp_fp32_drift_control_against_fp64():
+    """Control for the multi-step fp32 bound of the WGAN-GP GPU tests: the oracle (ATen CPU) in fp32 vs fp64 from the same
+    seeded state, LayerNorm critic.  With Adam(beta1 = 0) and a LayerNorm critic ATen's own rounding noise grows to tens of
+    times the strict single-step criterion |d| <= 1e-4 |ref| + 1e-5 within three steps (53x on the generator's adversarial
+    loss here), so an independent fp32 implementation is held to 100x that criterion after step 0 in this configuration."""
+    def run(dt):
+        st = O.StepState(seed=0, lr=1e-4, betas=(0.0, 0.9), d_layers=O.critic_layers(norm="layer"))
+        for d in (st.gp, st.gb, st.dp, st.db):
+            for k in d:
+                if d[k].is_floating_point():
+                    d[k] = d[k].to(dt)
+        st.opt_g, st.opt_d = O.AdamState(st.gp, 1e-4, (0.0, 0.9)), O.AdamState(st.dp, 1e-4, (0.0, 0.9))
+        gen = torch.Generator().manual_seed(1)
+        rows = []
+        for it in range(3):
+            opt, low, high = (O.synthetic_patches(gen, (n, 1, 32, 32, 32)).to(dt) for n in (2, 1, 1))
+            ml, mh = (O.synthetic_masks(gen, (1, 1, 32, 32, 32)) for _ in range(2))
+            torch.manual_seed(9000 + it)
+            eps = torch.rand((2, 1, 1, 1, 1)).to(dt)
+            r = O.train_step(st, opt, low, high, ml, mh, it, weight_clip=None, gp_eps=eps)
+            rows.append([r[k] for k in ("D", "G", "G-full", "sim", "HU")])
+        return np.array(rows)
+
+    a, b = run(torch.float32), run(torch.float64)
+    use = np.abs(a - b) / (1e-4 * np.abs(b) + 1e-5)
+    assert use[0].max() < 0.05, use[0]
+    assert 5.0 < use[2].max() < 100.0, use
