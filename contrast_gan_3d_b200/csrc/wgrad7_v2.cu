@@ -16,7 +16,7 @@
 //     (a ring of 10 planes whose first slots are mirrored behind its end, so a window never wraps): ONE M = 128, N = 128
 //     MMA per 16 voxels and per PAIR of E planes, 14 of its 16 (dx_lo, plane) blocks and 49 of 64 rows useful.
 //   * accumulator column = 16 * (plane - first plane of the window): the filter x-offset is dx = 6 - j + dx_lo.
-// Split-K over CTAs (contiguous runs of plane pairs of one (b, y-tile) column), fp32 atomics at the end.
+// Split-K over CTAs (whole (b, y-tile) columns dealt round-robin, see SegIterW2), fp32 atomics at the end.
 #include "common.cuh"
 #include "conv_internal.cuh"
 #include "tc_common.cuh"
@@ -27,10 +27,12 @@ namespace cg {
 using bf16 = __nv_bfloat16;
 constexpr uint32_t kSmemLimitW2 = 232448 - 1024;
 constexpr int kMaxRingW2 = 14;  // logical S16 plane slots: 8 live + 4 or 6 in flight (TMA runs 2 - 3 steps ahead of the MMAs)
-constexpr int kMaxPrefW2 = 22;    // staged 32-bit words per fetch thread and step
-constexpr int kBuildWarpsW2 = 6;  // warps 0-3 (also the epilogue), 6, 7 expand the operand
-constexpr int kFetchersW2 = 64;   // warps 8, 9 fetch and stage the raw Q1 words
-constexpr int kBuildersW2 = 256;  // threads on the named barrier shared by the build and fetch warps (see bar_sync_builders)
+constexpr int kMaxPrefW2 = 11;     // staged 32-bit words per fetch thread and step
+constexpr int kBuildWarpsW2 = 10;  // warps 0-3 (also the epilogue) and 6-11 expand the operand
+constexpr int kFetchWarp0W2 = 12;  // warps 12-15 fetch and stage the raw Q1 words
+constexpr int kFetchersW2 = 128;
+constexpr int kThreadsW2 = 512;
+constexpr int kBuildersW2 = (kBuildWarpsW2 + kFetchersW2 / 32) * 32;  // threads on the named barrier shared by the build and fetch warps (see bar_sync_builders)
 
 struct ThinW2Plan {
   int B, Xs, Ys, Zs;  // S16 extents
@@ -43,31 +45,60 @@ struct ThinW2Plan {
   int ring, nphys, npairs;  // logical ring size; physical slots (>= ring: the first nphys - ring slots are mirrored)
   int nb16, inv_nb16;       // 16-row blocks per line and ceil(65536 / nb16)
   uint32_t slot_bytes, e2_bytes, box_bytes, stage_words, smem_bytes;
-  int debug;  // CGAN3D_W2_DEBUG (profiling aid, results are wrong): 1 = skip the operand build, 2 = skip the MMAs
+  int debug;  // CGAN3D_W2_DEBUG (profiling aid, results are wrong): 1 = skip the operand build, 2 = skip the MMAs, 4 = skip the plane loads
 };
 
+// Work = ncols columns (b, y-tile) x npairs plane pairs.  Columns are dealt to the CTAs ROUND-ROBIN (CTA c takes columns
+// c, c + grid, ... whole), so that at any moment the 148 CTAs stream the same planes of 148 ADJACENT y-tiles, i.e. one
+// contiguous region of the 16-channel tensor: DRAM sees long sequential bursts instead of 148 scattered 8 KB pieces.  The
+// columns of the last, incomplete round are split evenly by plane pairs (a range that crosses a column boundary becomes
+// two segments), so every CTA gets the same number of steps to within one.
 struct SegIterW2 {
-  long long idx, end;
-  int n;
-  __device__ __forceinline__ SegIterW2(long long ncols, int n_) : n(n_) {
-    const long long total = ncols * n;
+  int n, rounds, r;
+  long long rem_col0, idx, end;
+  __device__ __forceinline__ SegIterW2(long long ncols, int n_) : n(n_), r(0) {
+    rounds = (int)(ncols / gridDim.x);
+    rem_col0 = (long long)rounds * gridDim.x;
+    const long long total = (ncols - rem_col0) * n;
     idx = total * blockIdx.x / gridDim.x;
     end = total * (blockIdx.x + 1) / gridDim.x;
   }
+  __device__ __forceinline__ long long steps() const { return (long long)rounds * n + (end - idx); }
+  // step k (0-based, in processing order) of this CTA -> (column, plane pair)
+  __device__ __forceinline__ void locate(long long k, long long idx0, int &col, int &pair) const {
+    if (k < (long long)rounds * n) {
+      const int rr = (int)(k / n);
+      col = rr * (int)gridDim.x + (int)blockIdx.x;
+      pair = (int)(k - (long long)rr * n);
+    } else {
+      const long long flat = idx0 + (k - (long long)rounds * n);
+      const long long c = flat / n;
+      col = (int)(rem_col0 + c);
+      pair = (int)(flat - c * n);
+    }
+  }
   __device__ __forceinline__ bool next(int &col, int &p0, int &plen) {
+    if (r < rounds) {
+      col = r * (int)gridDim.x + (int)blockIdx.x;
+      p0 = 0;
+      plen = n;
+      ++r;
+      return true;
+    }
     if (idx >= end) return false;
-    col = (int)(idx / n);
-    p0 = (int)(idx - (long long)col * n);
+    const long long c = idx / n;
+    col = (int)(rem_col0 + c);
+    p0 = (int)(idx - c * n);
     plen = (int)mn<long long>(n - p0, end - idx);
     idx += plen;
     return true;
   }
 };
 
-__device__ __forceinline__ void bar_sync_builders() { static_assert(kBuildersW2 == 256, "barrier count"); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_builders() { static_assert(kBuildersW2 == 448, "barrier count"); asm volatile("bar.sync 1, 448;" ::: "memory"); }
 
-__global__ void __launch_bounds__(320, 1)
-wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, float *__restrict__ dw,
+__global__ void __launch_bounds__(kThreadsW2, 1)
+wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__restrict__ q1, float *__restrict__ dw,
                  const __grid_constant__ ThinW2Plan p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // nphys S16 plane slots, [rows][16 ch], SWIZZLE_32B (TMA)
@@ -79,7 +110,7 @@ wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxRingW2; ++i) { tc::mbar_init(&s_full[i], 32); tc::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < kMaxRingW2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&e_full[i], kBuildWarpsW2); tc::mbar_init(&e_empty[i], 1); }
     tc::mbar_init(done, 1);
     tc::fence_barrier_init();
@@ -103,51 +134,35 @@ wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, 
   const long long ncols = (long long)p.B * p.nyt;
 
   if (warp == 4) {
-    // ------------------------------------------------ S16 plane producer.  Planes are numbered by the order in which this
-    // CTA loads them (q): slot q % ring, mirrored at ring + slot when that exists.  A segment loads its 6 warm-up planes and
-    // then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
-    // The copies are 16-byte cp.async (LDGSTS), NOT TMA: a SWIZZLE_32B tensor map is limited to 32-byte inner rows, and the
-    // TMA engine then issues one 32-byte request per voxel (~3 cycles each: the first version of this kernel could not
-    // load its planes faster than one step per 2000 cycles, whatever the MMAs did).  A warp-wide cp.async covers 512
-    // contiguous bytes = four full 128-byte lines; the SWIZZLE_32B pattern is applied to the destination address, voxels
-    // outside the tensor are zero-filled (src-size 0), and completion is reported to the slot's mbarrier by the hardware.
-    uint32_t q = 0;
-    const uint32_t ring_u32 = tc::smem_u32(ring);
-    const uint8_t *s16b = reinterpret_cast<const uint8_t *>(s16);
-    const uint32_t half = (uint32_t)lane & 1u;
-    auto load_plane = [&](int xs, int b, int y0) {
-      const uint32_t slot = q % (uint32_t)p.ring, use = q / (uint32_t)p.ring;
-      if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
-      const bool mirror = (int)slot + p.ring < p.nphys;
-      const bool plane_ok = (unsigned)xs < (unsigned)p.Xs;
-      const uint32_t dst0 = ring_u32 + slot * p.slot_bytes;
-      const uint32_t moff = (uint32_t)p.ring * p.slot_bytes;
-      for (int yl = 0; yl < p.Yt; ++yl) {
-        const bool line_ok = plane_ok && (y0 + yl) < p.Ys;
-        const uint8_t *src_line = s16b + ((((size_t)b * p.Xs + (plane_ok ? xs : 0)) * p.Ys + (line_ok ? y0 + yl : 0)) * (size_t)p.Zs) * 32u;
-        for (int z = lane >> 1; z < p.Zt; z += 16) {
-          const uint32_t row = (uint32_t)(yl * p.Zt + z);
-          const uint32_t dst = dst0 + row * 32u + ((half ^ ((row >> 2) & 1u)) << 4);
-          const bool ok = line_ok && z < p.Zs;
-          const uint8_t *src = ok ? src_line + (size_t)z * 32u + half * 16u : s16b;
-          const uint32_t nbytes = ok ? 16u : 0u;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-          if (mirror) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + moff), "l"(src), "r"(nbytes) : "memory");
+    // ------------------------------------------------ S16 plane producer (TMA).  Measured (profiles/README.md, round 2): a
+    // SWIZZLE_32B map is limited to 32-byte inner rows and the TMA engine spends ~3 cycles per row, so the planes of one
+    // step (2 planes + mirrors = 660 rows) cost ~2000 cycles: this, not the MMAs (1350 cycles), is the kernel's floor.  A
+    // 16-byte cp.async producer warp with the swizzle applied by hand was tried and is slower still (5400 cycles / step).  Planes are numbered by the order in which
+    // this CTA loads them (q): slot q % ring, mirrored at ring + slot when that exists.  A segment loads its 6 warm-up
+    // planes and then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmS);
+      uint32_t q = 0;
+      auto load_plane = [&](int xs, int b, int y0) {
+        const uint32_t slot = q % (uint32_t)p.ring, use = q / (uint32_t)p.ring;
+        if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
+        if (p.debug & 4) { tc::mbar_arrive(&s_full[slot]); ++q; return; }  // profiling aid: no plane loads at all
+        const bool mirror = (int)slot + p.ring < p.nphys;
+        tc::mbar_expect_tx(&s_full[slot], mirror ? 2 * p.box_bytes : p.box_bytes);
+        tc::tma_load_5d(ring + (size_t)slot * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
+        if (mirror) tc::tma_load_5d(ring + (size_t)(slot + p.ring) * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
+        ++q;
+      };
+      int col, p0, plen;
+      for (SegIterW2 it(ncols, p.npairs); it.next(col, p0, plen);) {
+        const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
+        for (int xs = 2 * p0 - 6; xs < 2 * p0; ++xs) load_plane(xs, b, y0);
+        for (int i = 0; i < plen; ++i) {
+          load_plane(2 * (p0 + i), b, y0);
+          load_plane(2 * (p0 + i) + 1, b, y0);
         }
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(&s_full[slot])) : "memory");
-      ++q;
-    };
-    int col, p0, plen;
-    for (SegIterW2 it(ncols, p.npairs); it.next(col, p0, plen);) {
-      const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
-      for (int xs = 2 * p0 - 6; xs < 2 * p0; ++xs) load_plane(xs, b, y0);
-      for (int i = 0; i < plen; ++i) {
-        load_plane(2 * (p0 + i), b, y0);
-        load_plane(2 * (p0 + i) + 1, b, y0);
-      }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer
     const bool leader = tc::elect_one();
@@ -167,7 +182,6 @@ wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, 
         }
         const uint32_t st = n & 1;
         tc::mbar_wait(&e_full[st], (n >> 1) & 1);
-        tc::fence_proxy_async();  // the planes were written by cp.async (generic proxy); the MMAs read through the async proxy
         tc::tc_fence_after();
         const uint32_t a0 = (e2_u32 + st * p.e2_bytes) >> 4;
         uint32_t j = 0;
@@ -204,21 +218,21 @@ wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, 
     if (leader) tc::umma_commit(done);
     __syncwarp();
   } else {
-    // ------------------------------------------------ warps 0..3, 6, 7: build the expanded operand (0..3 then run the
-    // epilogue); warps 8, 9: fetch the raw Q1 words two steps ahead and stage them in shared memory.  The roles are split
+    // ------------------------------------------------ warps 0..3, 6..11: build the expanded operand (0..3 then run the
+    // epilogue); warps 12..15: fetch the raw Q1 words two steps ahead and stage them in shared memory.  The roles are split
     // because the generic->async proxy fence that publishes the operand compiles to MEMBAR.ALL.CTA, which waits for every
     // outstanding global load of the executing thread: a warp that prefetches AND builds exposes the full load latency
     // (~1 us under load) in every step.
     const int ZqW = p.Zq >> 1;
     // this CTA's steps are the flat (column, plane pair) indices [idx0, idx0 + total)
-    SegIterW2 range(ncols, p.npairs);
+    const SegIterW2 range(ncols, p.npairs);
     const long long idx0 = range.idx;
-    const uint32_t total = (uint32_t)(range.end - range.idx);
+    const uint32_t total = (uint32_t)range.steps();
     uint32_t n = 0;
-    if (warp >= 8) {
-      const int tid = (warp - 8) * 32 + lane;  // 0..63
+    if (warp >= kFetchWarp0W2) {
+      const int tid = (warp - kFetchWarp0W2) * 32 + lane;  // 0..127
       const int total_words = 2 * p.L * p.LW;
-      // word i of this thread: staging index tid + 64 i = (h, l, w); rel = its offset from the step's base pointer; the
+      // word i of this thread: staging index tid + 128 i = (h, l, w); rel = its offset from the step's base pointer; the
       // z-range check does not depend on the step (meta < 0: never loaded)
       int meta[kMaxPrefW2], rel[kMaxPrefW2];
 #pragma unroll
@@ -232,8 +246,8 @@ wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, 
         }
       }
       auto fetch = [&](uint32_t k, uint32_t (&pref)[kMaxPrefW2]) {  // raw Q1 words of this CTA's step k -> registers
-        const long long flat = idx0 + k;
-        const int col = (int)(flat / p.npairs), pair = (int)(flat - (long long)col * p.npairs);
+        int col, pair;
+        range.locate(k, idx0, col, pair);
         const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
         const int xb = 2 * pair - p.P, yb = y0 - p.P;
         // base may point outside the tensor (halo): it is only dereferenced for in-range (plane, line)
@@ -267,7 +281,7 @@ wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, 
         ++n;
       }
     } else {
-      const int bw = warp < 4 ? warp : warp - 2;  // builder warp 0..5
+      const int bw = warp < 4 ? warp : warp - 2;  // builder warp 0..9
       // E2[l * Zt + r][h][j] = line(h, l)[r + j], j = 0..7.  A warp iteration = 32 rows of one staged line (h, l): 5
       // conflict-free LDS (neighbouring lanes read overlapping words), one funnel shift per output word (odd rows start
       // in the upper half-word), one 16-byte STS (SWIZZLE_32B makes the 8 rows of a quarter-warp hit 8 different 16-byte
@@ -340,6 +354,12 @@ wgrad7_v2_kernel(const bf16 *__restrict__ s16, const uint32_t *__restrict__ q1, 
 }
 
 // ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFnW2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void *tc_encode_fn_ptr();              // conv_tc.cu
+CUtensorMapL2promotion tc_l2_promo();  // conv_tc.cu
+
 static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
   static int off = -1;
   if (off < 0) off = getenv("CGAN3D_WGRAD7_V1") ? 1 : 0;
@@ -375,6 +395,7 @@ static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
     if (nphys < ring + 2 && Yt > 1) continue;
     if (nphys < ring) continue;
     if (nphys > ring + 6) nphys = ring + 6;  // windows start at even slots <= ring - 2: six mirrors make every window contiguous
+    if (const char *e = getenv("CGAN3D_W2_NPHYS")) nphys = mx(ring, mn(nphys, atoi(e)));  // experiment: fewer mirrored slots
     p.Yt = Yt; p.L = L; p.nphys = nphys; p.ring = ring;
     p.slot_bytes = slot; p.e2_bytes = e2b; p.stage_words = stage_words;
     p.smem_bytes = fixed + (uint32_t)nphys * slot;
@@ -405,6 +426,18 @@ int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, f
     cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)16 * 343 * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "tcgen05 thin wgrad v2 memset");
   }
+  EncodeTiledFnW2 enc = reinterpret_cast<EncodeTiledFnW2>(tc_encode_fn_ptr());
+  if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+  CUtensorMap tmS;
+  {
+    const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zs, (cuuint64_t)p.Ys, (cuuint64_t)p.Xs, (cuuint64_t)p.B};
+    const cuuint64_t gstr[4] = {32, (cuuint64_t)p.Zs * 32, (cuuint64_t)p.Ys * p.Zs * 32, (cuuint64_t)p.Xs * p.Ys * p.Zs * 32};
+    const cuuint32_t box[5] = {16, (cuuint32_t)p.Zt, (cuuint32_t)p.Yt, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(s16), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, tc_l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (thin wgrad v2) failed with %d", (int)r);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad7_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitW2 + 1024);
@@ -413,7 +446,7 @@ int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, f
   }
   const long long total = (long long)p.B * p.nyt * p.npairs;
   const int grid = (int)mn<long long>(total, (long long)num_sms());
-  wgrad7_v2_kernel<<<grid, 320, p.smem_bytes + 1024, st>>>(reinterpret_cast<const bf16 *>(s16), reinterpret_cast<const uint32_t *>(q1), dw, p);
+  wgrad7_v2_kernel<<<grid, kThreadsW2, p.smem_bytes + 1024, st>>>(tmS, reinterpret_cast<const uint32_t *>(q1), dw, p);
   CG_LAUNCH_CHECK("wgrad7_v2_kernel");
   return 0;
 }
