@@ -404,7 +404,9 @@ def test_wgan_gp_train_steps_against_reference_golden(golden_dir, name, norm, dt
                 tol = np.array([2 * lr * steps * n ** 0.5, 2 * lr * steps * n ** 0.5, 2e-3 * abs(w[2]) + 1e-6, 2 * lr * steps, 2 * lr * steps])
                 assert np.all(np.abs(fp - w) <= 2e-3 * np.abs(w) + tol), (k, fp, w)
     else:
-        atol = np.array([2e-2, 2e-3, 2e-3, 1e-3, 1e-3])  # D is dominated by the penalty (~10 = lambda * (|grad| - 1)^2)
+        # D is dominated by the penalty (~5-10 = lambda * (|grad| - 1)^2); G = -mean(logits) is a mean of logits whose
+        # spread is O(1) under LayerNorm (unit-variance features) and O(0.1) otherwise: atol = 1 % of that spread
+        atol = np.array([2e-2, 2e-3, 2e-3, 1e-3, 1e-3]) if norm == "identity" else np.array([5e-2, 1e-2, 1e-2, 1e-3, 1e-3])
         assert np.all(np.abs(losses - ref) <= 2e-2 * np.abs(ref) + atol), f"\n{losses}\n{ref}"
 
 
