@@ -9,7 +9,8 @@ accumulation, iteration in which both the critic and the generator are trained, 
 One "pair" = one opt + one subopt patch through that iteration = 363.417 GFLOP of necessary conv work.
 
 Printed keys: see the task contract; `value` = device-timed with inputs resident in HBM, `e2e` = the same step
-through Trainer.train_step from pinned host buffers plus a device->host read of the loss.
+through Trainer.train_step from pinned host buffers (raw int16 HU patches + masks, scaled on the device) plus a
+device->host read of the loss.
 `--impl reference` times the UNMODIFIED reference `Trainer.train_step` on the host cores (the verbatim copy of the
 reference package that `oracle/make_ref.py` puts into the git-ignored `oracle/_ref/`, imported through
 `oracle/ref_shim.py`; the oracle port only when that copy is absent) on a bounded sample of the same workload.
@@ -134,6 +135,61 @@ def synth_batch(gen, n_opt, n_low, n_high, patch, pin=False):
     return [dict(data=opt, seg=None, name=[]), dict(data=low, seg=mm(n_low), name=[]), dict(data=high, seg=mm(n_high), name=[])]
 
 
+def raw_hu_batch(batch, pin=True):
+    """The same synthetic patches as RAW int16 HU (the reference's on-disk dtype, data/CCTADataLoader.py:76-92): what the
+    end-to-end leg uploads; Trainer(hu_scaler=...) applies (hu - 238) / 600 on the device."""
+    import torch
+
+    out = []
+    for b in batch:
+        hu = (b["data"] * 600.0 + 238.0).round().clamp(-1024, 1500).to(torch.int16)
+        out.append(dict(data=hu.pin_memory() if pin else hu, seg=b["seg"], name=[]))
+    return out
+
+
+def bench_c2(generator, dev, pk):
+    """BASELINE config C2: generator-only correction of one synthetic 512 x 512 x 256 int16 CCTA volume tiled into 32 128^3
+    patches, batches of 16 (reference eval/CCTAContrastCorrector.py:60-106), through CCTAContrastCorrector.__call__ (host
+    int16 in, host fp32 HU out).  Reports seconds per volume end to end, the device time of the generator passes alone and
+    their fraction of the bf16 peak (32 x 125.762 GFLOP of fprop per volume)."""
+    import numpy as np
+    import torch
+
+    from contrast_gan_3d_b200.data import FactorZeroCenterScaler
+    from contrast_gan_3d_b200.eval import CCTAContrastCorrector
+
+    rng = np.random.default_rng(7)
+    vol = np.clip(rng.normal(100, 300, size=(512, 512, 256)), -1024, 1500).astype(np.int16)
+    corr = CCTAContrastCorrector(lambda: generator, FactorZeroCenterScaler(-1024, 1500, 600), dev, inference_patch_size=(128, 128, 128))
+    for _ in range(2):
+        corr(vol, batch_size=16)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = corr(vol, batch_size=16)
+        ts.append(time.perf_counter() - t0)
+    assert tuple(out.shape) == vol.shape
+    # generator passes alone, inputs resident
+    x = torch.randn((16, 1, 128, 128, 128), device=dev)
+    with torch.no_grad():
+        for _ in range(2):
+            generator.forward_corrected(x)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            generator.forward_corrected(x)
+        e1.record()
+    torch.cuda.synchronize()
+    g_ms = e0.elapsed_time(e1) / 4 * 2  # two batches of 16 per volume
+    tf = 32 * 125.762e9 / (g_ms * 1e-3) / 1e12
+    t = sorted(ts)[1]
+    return {"workload": "BASELINE config C2: 512x512x256 int16 volume -> 32 tiles of 128^3, batches of 16, train-mode BatchNorm as the reference",
+            "seconds_per_volume_e2e": t, "generator_ms_per_volume": g_ms, "generator_tflops": tf,
+            "generator_frac_of_peak": tf / pk["bf16_sustained"], "host_io_bytes": int(vol.nbytes + vol.size * 4),
+            "non_generator_ms": t * 1e3 - g_ms}
+
+
 def _reference_trainer(patch, n_sub):
     """The UNMODIFIED reference Trainer (from oracle/_ref or /root/reference through oracle/ref_shim.py) on CPU, built the
     way tests/golden/make_golden.py builds it: default G and D, Adam(2e-4, (0.5, 0.999)), weight clip 0.01, generator
@@ -253,6 +309,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick-cpu", action="store_true", help="reference arm: exactly --steps/--warmup steps, no 1-thread line")
     ap.add_argument("--breakdown", default=None, help="write the per-conv-kernel device-time table of the timed region here")
+    ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (default: the step is replayed from a CUDA graph)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c4 (8 pairs per GPU) and c2 (whole-volume inference) objects")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -262,6 +320,7 @@ def main():
     import torch.distributed as dist
 
     from contrast_gan_3d_b200 import _lib, ops
+    from contrast_gan_3d_b200.data import FactorZeroCenterScaler
     from contrast_gan_3d_b200.model import HULoss, PatchGANDiscriminator, ResnetGenerator
     from contrast_gan_3d_b200.optim import FusedAdam
     from contrast_gan_3d_b200.parallel import GradBucketReducer, broadcast_module
@@ -290,14 +349,16 @@ def main():
     tr = Trainer(10 ** 9, 2, None, 1, 1, 0, 0, partial(ResnetGenerator, 4, 2, 16, compute_dtype=dtype),
                  partial(PatchGANDiscriminator, 1, 8, 3, negative_slope=0.2, compute_dtype=dtype),
                  partial(FusedAdam, lr=2e-4, betas=(0.5, 0.999)), partial(FusedAdam, lr=2e-4, betas=(0.5, 0.999)),
-                 HULoss(*HU_BOUNDS), NullLogger(), dev, weight_clip=0.01, checkpoint_every=None, grad_reducer=reducer)
+                 HULoss(*HU_BOUNDS), NullLogger(), dev, weight_clip=0.01, checkpoint_every=None, grad_reducer=reducer,
+                 hu_scaler=FactorZeroCenterScaler(-1024, 1500, 600))
     broadcast_module(tr.generator); broadcast_module(tr.critic)
     tr.generator.train(); tr.critic.train()
 
     gen = torch.Generator().manual_seed(1 + rank)
     host = synth_batch(gen, n_opt, n_low, n_high, patch, pin=True)
     resident = [dict(data=b["data"].to(dev), seg=None if b["seg"] is None else b["seg"].to(dev), name=[]) for b in host]
-    h2d = sum(b["data"].numel() * 4 for b in host) + sum(b["seg"].numel() for b in host if b["seg"] is not None)
+    host = raw_hu_batch(host)  # the end-to-end leg uploads int16 HU + bool masks (2 + 1 bytes per voxel instead of 4 + 1)
+    h2d = sum(b["data"].numel() * b["data"].element_size() for b in host) + sum(b["seg"].numel() for b in host if b["seg"] is not None)
 
     def sync():
         torch.cuda.synchronize()
@@ -362,17 +423,26 @@ def main():
         ms_instr, _ = timed(resident, args.steps, read_loss=False)
         conv_t = ops.conv_timing_summary()
         ops.enable_conv_timing(False)
-        # Pass 2: the headline loop, exactly K steps between two events
+        # Pass 2: the headline loop, exactly K steps between two events.  From here on the step is replayed from a CUDA graph
+        # (Trainer.enable_cuda_graph: 3 eager steps of each input variant, then capture); pass 1 had to run eagerly because
+        # its timing events cannot be recorded into a graph.
+        graph_steps = 0
+        if not args.no_graph:
+            tr.enable_cuda_graph()
+            for _ in range(5):
+                tr.train_step(resident, 0)
+            sync()
+            graph_steps = tr.graph_launches_per_step()
         n0 = _lib.launch_count
         ms, logs = timed(resident, args.steps, read_loss=False)
-        launches = _lib.launch_count - n0
+        launches = (_lib.launch_count - n0) + graph_steps * args.steps
         value_retry = None
         if ms > 1.15 * ms_instr:  # the same kernels ran faster WITH instrumentation: this loop was disturbed; measure again
             value_retry = ms
             n0 = _lib.launch_count
             ms, logs = timed(resident, args.steps, read_loss=False)
-            launches = _lib.launch_count - n0
-    for _ in range(max(args.warmup, 5)):  # warm the end-to-end path too (side-stream upload pool, pinned-memory registration)
+            launches = (_lib.launch_count - n0) + graph_steps * args.steps
+    for _ in range(max(args.warmup, 5)):  # warm the end-to-end path too (side-stream upload pool, pinned-memory registration, its graph)
         tr.train_step(host, 0)
     ms_e2e, logs = timed(host, args.steps, read_loss=True)
     if os.environ.get("BENCH_E2E_ABLATE"):  # where does the end-to-end overhead come from?
@@ -396,6 +466,25 @@ def main():
     value = pairs_per_step / (ms / 1e3)
     e2e = pairs_per_step / (ms_e2e / 1e3)
     h2d_gbps = measure_h2d_gbps(dev)
+
+    # BASELINE config C4 (8 pairs per GPU: the scaling configuration whose step is short enough to expose host overhead):
+    # same measurement, device-timed with resident inputs and end to end from pinned int16 host buffers.
+    c4 = None
+    if not args.no_extras and args.pairs_per_gpu != 8:
+        g4 = torch.Generator().manual_seed(101 + rank)
+        host4f = synth_batch(g4, 8, 4, 4, patch, pin=False)
+        res4 = [dict(data=b["data"].to(dev), seg=None if b["seg"] is None else b["seg"].to(dev), name=[]) for b in host4f]
+        host4 = raw_hu_batch(host4f)
+        for _ in range(6):
+            tr.train_step(res4, 0)
+        ms4, _ = timed(res4, args.steps, read_loss=False)
+        for _ in range(6):
+            tr.train_step(host4, 0)
+        ms4e, _ = timed(host4, args.steps, read_loss=True)
+        c4 = {"workload": f"BASELINE config C4: per GPU 8 opt + 4 low + 4 high 1x{args.patch}^3 patches", "pairs_per_gpu": 8,
+              "value": 8 * world / (ms4 / 1e3), "ms_per_step": ms4, "e2e_value": 8 * world / (ms4e / 1e3), "e2e_ms_per_step": ms4e,
+              "unit": "pairs/s", "step_frac_of_peak": 8 * PAIR_GFLOP_128 * (args.patch / 128) ** 3 / (ms4 * 1e-3) / 1e3 / peaks()["bf16_sustained"]}
+        del res4, host4, host4f
 
     if rank != 0:
         if world > 1:
@@ -452,6 +541,10 @@ def main():
         except Exception:
             cpu = {"error": (r.stderr or r.stdout)[-300:]}
 
+    c2 = None
+    if not args.no_extras and args.patch == 128:
+        c2 = bench_c2(tr.generator, dev, pk)
+
     out = {
         "metric": "patch_pairs_per_sec_gd_train_step", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -464,8 +557,9 @@ def main():
         "e2e": {"value": e2e, "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "pinned_h2d_gbps": round(h2d_gbps, 1), "first_try_ms_per_step": e2e_retry},
         "value_first_try_ms_per_step": value_retry,  # set when the resident loop ran host-bound (busy host) and was re-measured
-        "gpu_launches": launches, "gpu_launches_note": "libcgan3d entry-point calls in the timed region; each enqueues >= 1 kernel",
-        "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": launches, "gpu_launches_note": "libcgan3d entry-point calls in the timed region (those recorded in the replayed CUDA graph counted once per replay); each enqueues >= 1 kernel",
+        "roofline": roof, "cpu_baseline": cpu, "c4": c4, "c2": c2,
+        "cuda_graph": not args.no_graph,
         "losses_last_step": {k: float(v.detach()) for k, v in logs.items()},
     }
     print(json.dumps(out))

@@ -191,6 +191,46 @@ adam_multi_kernel(const __grid_constant__ AdamBatch t, float lr, float b1, float
   }
 }
 
+// Capturable variant (CUDA graphs): the learning rate and the step count live in DEVICE memory (hyper[0] = lr, hyper[1] =
+// step as a float, exact up to 2^24), so a captured optimizer step stays valid when the scheduler changes the rate and as
+// the bias corrections evolve.  adam_tick_kernel advances the step count once per optimizer.step().
+__global__ void adam_tick_kernel(float *hyper) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) hyper[1] += 1.f;
+}
+__global__ void __launch_bounds__(256)
+adam_multi_dev_kernel(const __grid_constant__ AdamBatch t, const float *__restrict__ hyper, float b1, float b2, float eps, float clip) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double lr = (double)hyper[0], step = (double)hyper[1];
+    const double bc1 = 1.0 - pow((double)b1, step);
+    const double bc2 = 1.0 - pow((double)b2, step);
+    s_step_size = (float)(lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = 1.f - b1, w2 = 1.f - b2;
+  const int k = blockIdx.y;
+  float *__restrict__ p = t.p[k];
+  const float *__restrict__ g = t.g[k];
+  float *__restrict__ m = t.m[k];
+  float *__restrict__ v = t.v[k];
+  const int64_t n = t.n[k];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float mi = m[i];
+    mi = (w1 < 0.5f) ? mi + w1 * (gi - mi) : gi - (gi - mi) * (1.f - w1);  // torch lerp_
+    float vi = v[i] * b2;
+    vi = vi + (w2 * gi) * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    float pi = p[i] + (-step_size) * (mi / denom);
+    if (clip > 0.f) pi = fminf(fmaxf(pi, -clip), clip);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+  }
+}
+
 // ---------------------------------------------------------------- sampler / tiler
 __global__ void __launch_bounds__(256)
 crop_scale_kernel(const int16_t *__restrict__ vol, int X, int Y, int Z, int lbx, int lby, int lbz, int PX, int PY, int PZ,
@@ -359,6 +399,37 @@ int cgan3d_adam_step_multi(int count, float *const *params, const float *const *
     const int bx = (int)((nmax + 255) / 256 < 64 ? (nmax + 255) / 256 : 64);
     adam_multi_kernel<<<dim3(bx, nb), 256, 0, as_stream(stream)>>>(t, lr, beta1, beta2, eps, step, clip);
     CG_LAUNCH_CHECK("adam_step_multi");
+  }
+  return 0;
+}
+
+int cgan3d_adam_tick(float *hyper, void *stream) {
+  CG_CHECK_ARG(hyper, "adam_tick: NULL pointer");
+  adam_tick_kernel<<<1, 32, 0, as_stream(stream)>>>(hyper);
+  CG_LAUNCH_CHECK("adam_tick");
+  return 0;
+}
+
+int cgan3d_adam_step_multi_dev(int count, float *const *params, const float *const *grads, float *const *exp_avgs,
+                               float *const *exp_avg_sqs, const int64_t *numels, const float *hyper, float beta1, float beta2,
+                               float eps, float clip, void *stream) {
+  CG_CHECK_ARG(count >= 0 && (count == 0 || (params && grads && exp_avgs && exp_avg_sqs && numels)), "adam_step_multi_dev: NULL table");
+  CG_CHECK_ARG(hyper, "adam_step_multi_dev: NULL hyper-parameter pointer");
+  for (int i0 = 0; i0 < count; i0 += kAdamBatch) {
+    AdamBatch t{};
+    const int nb = count - i0 < kAdamBatch ? count - i0 : kAdamBatch;
+    int64_t nmax = 0;
+    for (int i = 0; i < nb; ++i) {
+      CG_CHECK_ARG(params[i0 + i] && grads[i0 + i] && exp_avgs[i0 + i] && exp_avg_sqs[i0 + i] && numels[i0 + i] >= 0,
+                   "adam_step_multi_dev: NULL tensor %d", i0 + i);
+      t.p[i] = params[i0 + i]; t.g[i] = grads[i0 + i]; t.m[i] = exp_avgs[i0 + i]; t.v[i] = exp_avg_sqs[i0 + i];
+      t.n[i] = numels[i0 + i];
+      nmax = nmax > t.n[i] ? nmax : t.n[i];
+    }
+    if (nmax == 0) continue;
+    const int bx = (int)((nmax + 255) / 256 < 64 ? (nmax + 255) / 256 : 64);
+    adam_multi_dev_kernel<<<dim3(bx, nb), 256, 0, as_stream(stream)>>>(t, hyper, beta1, beta2, eps, clip);
+    CG_LAUNCH_CHECK("adam_step_multi_dev");
   }
   return 0;
 }

@@ -163,13 +163,17 @@ def conv_bnstats(g: ConvGeom, x, wp, transposed: bool):
     return out, sums
 
 
-def conv_wgrad(g: ConvGeom, big, small, impl=None, out=None):
-    """dW (fp32, torch layout [Cs, Cb, k, k, k]); with `out` the kernel ACCUMULATES into it (beta = 1)."""
+def conv_wgrad(g: ConvGeom, big, small, impl=None, out=None, ws=None):
+    """dW (fp32, torch layout [Cs, Cb, k, k, k]); with `out` the kernel ACCUMULATES into it (beta = 1).  `ws`: a workspace
+    the caller allocated (on the stream that owns the memory pool), else one is allocated on the current stream."""
     dt = _dt(big.dtype)
     dw = out if out is not None else torch.empty((g.Cs, g.Cb, g.k, g.k, g.k), dtype=torch.float32, device=big.device)
     if out is not None and (out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != g.Cs * g.Cb * g.k ** 3):
         raise ValueError("conv_wgrad: `out` must be a contiguous fp32 tensor of the weight's size")
-    ws, n = _workspace(g, dt, _lib.OP_WGRAD, big.device)
+    if ws is None:
+        ws, n = _workspace(g, dt, _lib.OP_WGRAD, big.device)
+    else:
+        n = ws.numel()
     with _timed("wgrad", g, dt):
         call("cgan3d_conv_wgrad", C.byref(g), dt, _p(big), _p(small), _p(dw), 0.0 if out is None else 1.0, _p(ws), n,
              _CONV_IMPL if impl is None else impl, _st())
@@ -210,11 +214,15 @@ def _weight_grad(weight, g: ConvGeom, big, small):
         return conv_wgrad(g, big, small)
     main = torch.cuda.current_stream(big.device)
     side = sink.side_stream(big.device)
+    # the workspace comes from the COMPUTE stream's pool: under CUDA-graph capture only that stream's allocations belong to
+    # the graph's private pool, and memory handed out to the side stream could be given to someone else between replays
+    ws, _ = _workspace(g, _dt(big.dtype), _lib.OP_WGRAD, big.device)
     side.wait_stream(main)  # `big` / `small` were produced on the compute stream
     with torch.cuda.stream(side):
-        conv_wgrad(g, big, small, out=weight.grad)
-    big.record_stream(side)
-    small.record_stream(side)
+        conv_wgrad(g, big, small, out=weight.grad, ws=ws)
+    for t in (big, small, ws):
+        if t is not None:
+            t.record_stream(side)
     left = _FWD_USES.get(id(weight), 1) - 1
     _FWD_USES[id(weight)] = max(left, 0)
     if left <= 0:

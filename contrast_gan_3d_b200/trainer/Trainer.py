@@ -91,6 +91,7 @@ class Trainer:
         checkpoint_every: Optional[int] = 1000,
         rng: Optional[np.random.Generator] = None,
         grad_reducer=None,
+        hu_scaler=None,
     ):
         self.rng = rng
         self.device = torch.device(device)
@@ -111,6 +112,12 @@ class Trainer:
         self.sim_loss_w = sim_loss_weight
         self.gan_loss_w = gan_loss_weight
         self.gp_w = gp_weight
+        # Optional (ours): batches may carry RAW int16 HU patches in "data" (the reference's on-disk format,
+        # data/CCTADataLoader.py:76-92) instead of scaled fp32; they cross PCIe at 2 bytes per voxel and are scaled on the
+        # device with `hu_scaler` ((hu - shift) / factor, bit-identical to data/Scaler.py:41-42 in fp32).
+        self.hu_scaler = hu_scaler
+        self._defer_schedulers = False
+        self._graphs = None  # enable_cuda_graph()
         self.weight_clip = weight_clip
         self.gp_eps_fn = None  # optional source of the WGAN-GP interpolation coefficients (tests); default torch.rand
 
@@ -172,7 +179,7 @@ class Trainer:
             if self.weight_clip is not None:
                 for p in self.critic.parameters():
                     p.data.clamp_(-self.weight_clip, self.weight_clip)
-        if self.lr_scheduler_D is not None:
+        if self.lr_scheduler_D is not None and not self._defer_schedulers:
             self.lr_scheduler_D.step()
         return {"D": loss_critic}
 
@@ -204,7 +211,7 @@ class Trainer:
         elif self.grad_reducer is not None:
             self.grad_reducer.reduce(self.generator.parameters())
         self.optimizer_G.step()
-        if self.lr_scheduler_G is not None:
+        if self.lr_scheduler_G is not None and not self._defer_schedulers:
             self.lr_scheduler_G.step()
         return {"G": loss_G, "G-full": full_loss_G, "sim": loss_sim, "HU": loss_hu}
 
@@ -291,11 +298,44 @@ class Trainer:
         self._staging_used.add(pf[3])
         return pf[1]
 
+    def _scaled(self, t: Optional[Tensor], out: Optional[Tensor] = None) -> Optional[Tensor]:
+        """fp32 network input from a device batch: int16 raw HU -> (hu - shift) / factor on the device, fp32 passes through
+        (copied when a destination is given)."""
+        if t is None:
+            return t
+        if t.dtype != torch.int16:
+            if out is not None:
+                out.copy_(t, non_blocking=True)
+                return out
+            return t
+        if self.hu_scaler is None:
+            raise ValueError("int16 (raw HU) batches need Trainer(hu_scaler=FactorZeroCenterScaler(...))")
+        t = t.contiguous()
+        if out is None:
+            out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+        n = t.numel()
+        inner = t.shape[-1]
+        # the tile kernel of the whole-volume corrector, applied to the batch seen as one [n / inner, 1, inner] volume
+        ops.call("cgan3d_tile_extract", t.data_ptr(), n // inner, 1, inner, 0, 0, 0, n // inner, 1, inner,
+                 float(self.hu_scaler.shift), float(getattr(self.hu_scaler, "factor", 1)), out.data_ptr(), ops._st())
+        return out
+
     def _generate(self, subopt: Tensor):
         if hasattr(self.generator, "forward_corrected"):
             return self.generator.forward_corrected(subopt)
         attenuation = self.generator(subopt)
         return attenuation, subopt - attenuation
+
+    def _step_core(self, subopt: Tensor, opt_t: Optional[Tensor], mask_t: Optional[Tensor], do_train_critic: bool,
+                   do_train_generator: bool):
+        """The device part of reference Trainer.train_step (Trainer.py:168-185) on device-resident fp32 inputs."""
+        attenuation, opt_hat = self._generate(subopt)
+        log_dict: Dict[str, Tensor] = {}
+        if do_train_critic:
+            log_dict = self.train_critic(opt_t, opt_hat, do_train_generator)
+        if do_train_generator:
+            log_dict |= self.train_generator(subopt, opt_hat, mask_t)
+        return log_dict, attenuation, opt_hat
 
     def train_step(self, patches: List[dict], iteration: int) -> Dict[str, Tensor]:
         opt, low, high = patches
@@ -308,17 +348,16 @@ class Trainer:
             subopt = self._upload_cat(low["data"], high["data"])  # needed first: on the compute stream
         opt_t, opt_ev = self._side_upload("opt", [opt["data"]]) if do_train_critic else (None, None)
         mask_t, mask_ev = self._side_upload("mask", [low["seg"], high["seg"]]) if do_train_generator else (None, None)
-        attenuation, opt_hat = self._generate(subopt)
 
-        log_dict: Dict[str, Tensor] = {}
-        if do_train_critic:
+        if self._graphs is not None:
+            log_dict, attenuation, opt_hat = self._graphed_step(subopt, opt_t, opt_ev, mask_t, mask_ev, do_train_critic, do_train_generator)
+        else:
+            subopt = self._scaled(subopt)
             if opt_ev is not None:
                 main.wait_event(opt_ev)
-            log_dict = self.train_critic(opt_t, opt_hat, do_train_generator)
-        if do_train_generator:
             if mask_ev is not None:
                 main.wait_event(mask_ev)
-            log_dict |= self.train_generator(subopt, opt_hat, mask_t)
+            log_dict, attenuation, opt_hat = self._step_core(subopt, self._scaled(opt_t), mask_t, do_train_critic, do_train_generator)
         self._release_staging()
 
         if self.log_every and iteration % self.log_every == 0:
@@ -329,6 +368,79 @@ class Trainer:
             self.logger_interface(patches, [None, opt_hat[:cut], opt_hat[cut:]], [None, attenuation[:cut], attenuation[cut:]],
                                   list(SCAN_TYPE_ORDER), iteration, "train", self.train_log_sample_size)
         return log_dict
+
+    # ---------------------------------------------------------------- CUDA graph of the step
+    def enable_cuda_graph(self, warmup: int = 3) -> None:
+        """Replay the device part of train_step from a CUDA graph (ours; the reference has no counterpart).  The ~300
+        kernels of a step are enqueued by ONE launch, which takes the Python / ctypes / autograd host cost (~8 ms per step)
+        off the critical path: a small-batch step (BASELINE config C4, 8 pairs per GPU) is otherwise host-bound.
+        One graph per (critic?, generator?, input shapes) variant, captured after `warmup` eager steps of that variant;
+        inputs are copied (or scaled from int16) into static tensors before each replay; learning rate and Adam step
+        count live on the device (FusedAdam), LR schedulers keep running on the host after each replay.
+        The loss tensors returned by train_step are the graph's static outputs: read them before the next step."""
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device")
+        for o in (self.optimizer_G, self.optimizer_D):
+            if not isinstance(o, FusedAdam):
+                raise NotImplementedError("the captured step needs FusedAdam (device-resident lr / step count)")
+        self._graphs = {"warmup": int(warmup), "entries": {}}
+        self._defer_schedulers = True
+
+    def _graphed_step(self, subopt_in, opt_in, opt_ev, mask_in, mask_ev, do_c: bool, do_g: bool):
+        main = torch.cuda.current_stream(self.device)
+        key = (do_c, do_g, tuple(subopt_in.shape), subopt_in.dtype, None if opt_in is None else (tuple(opt_in.shape), opt_in.dtype),
+               None if mask_in is None else (tuple(mask_in.shape), mask_in.dtype))
+        ent = self._graphs["entries"].get(key)
+        if ent is None:
+            f32 = dict(dtype=torch.float32, device=self.device)
+            ent = dict(sub=torch.empty(tuple(subopt_in.shape), **f32), opt=None if opt_in is None else torch.empty(tuple(opt_in.shape), **f32),
+                       mask=None if mask_in is None else torch.empty_like(mask_in, device=self.device), graph=None, out=None, seen=0,
+                       launches=0)
+            self._graphs["entries"][key] = ent
+        # inputs -> the graph's static tensors (on the compute stream, after everything the previous replay enqueued)
+        self._scaled(subopt_in, out=ent["sub"])
+        if opt_in is not None:
+            if opt_ev is not None:
+                main.wait_event(opt_ev)
+            self._scaled(opt_in, out=ent["opt"])
+        if mask_in is not None:
+            if mask_ev is not None:
+                main.wait_event(mask_ev)
+            ent["mask"].copy_(mask_in, non_blocking=True)
+        if ent["graph"] is not None:
+            ent["graph"].replay()
+            self.optimizer_G.note_graph_replay() if do_g else None
+            self.optimizer_D.note_graph_replay() if do_c else None
+            out = ent["out"]
+        elif ent["seen"] < self._graphs["warmup"]:
+            ent["seen"] += 1
+            out = self._step_core(ent["sub"], ent["opt"], ent["mask"], do_c, do_g)
+        else:
+            from .. import _lib
+
+            self.optimizer_G.sync_device_hyper(); self.optimizer_D.sync_device_hyper()
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = self._step_core(ent["sub"], ent["opt"], ent["mask"], do_c, do_g)
+            ent["launches"] = _lib.launch_count - n0
+            ent["graph"], ent["out"] = g, out
+            g.replay()  # the capture only recorded this step; run it (its optimizer host counters were advanced while recording)
+        # host-side schedule bookkeeping (reference Trainer.py:139-140,158-159), then mirror a changed rate to the device
+        if do_c and self.lr_scheduler_D is not None:
+            self.lr_scheduler_D.step()
+            self.optimizer_D.sync_device_hyper()
+        if do_g and self.lr_scheduler_G is not None:
+            self.lr_scheduler_G.step()
+            self.optimizer_G.sync_device_hyper()
+        return out
+
+    def graph_launches_per_step(self) -> int:
+        """libcgan3d entry-point calls recorded in the captured graphs (bench.py: gpu_launches)."""
+        if self._graphs is None:
+            return 0
+        return max([e["launches"] for e in self._graphs["entries"].values()] + [0])
 
     # ---------------------------------------------------------------- loop
     def fit(self, train_loaders: Dict[int, object], val_loaders: Dict[int, object], profiler=None):

@@ -193,6 +193,15 @@ int cgan3d_adam_step_multi(int count, float *const *params, const float *const *
                            float *const *exp_avg_sqs, const int64_t *numels, float lr, float beta1, float beta2,
                            float eps, int step, float clip, void *stream);
 
+/* Capturable form of the same update (CUDA graphs): lr and the step count are read from DEVICE memory, hyper[0] = lr,
+ * hyper[1] = step (float, exact to 2^24), so a captured optimizer.step() stays valid across scheduler changes
+ * (torch.optim.Adam(capturable=True) semantics; reference trainer/Trainer.py:134-140,157-159).  cgan3d_adam_tick adds 1
+ * to hyper[1]; call it once per optimizer step before the update launches.                                        */
+int cgan3d_adam_tick(float *hyper, void *stream);
+int cgan3d_adam_step_multi_dev(int count, float *const *params, const float *const *grads, float *const *exp_avgs,
+                               float *const *exp_avg_sqs, const int64_t *numels, const float *hyper, float beta1,
+                               float beta2, float eps, float clip, void *stream);
+
 /* ---- patch sampler (reference data/CCTADataLoader.py:76-95, data/Scaler.py:41-42) ----------
  * vol: int16 [X][Y][Z][2] (HU, centerline mask) on device.  Pads symmetrically with 0 up to the
  * patch size (below = d//2), crops at lower bounds lb (computed on the host by the index law),

@@ -543,6 +543,27 @@ def test_fit_prefetches_next_batch_with_identical_results():
     assert float(d) < 2e-4, float(d)
 
 
+def test_raw_int16_hu_batches_scaled_on_device():
+    """Batches may carry raw int16 HU (2 bytes per voxel across PCIe); Trainer(hu_scaler=...) applies the reference's
+    FactorZeroCenterScaler on the device (data/Scaler.py:41-42): same losses as feeding the host-scaled fp32 patches."""
+    from contrast_gan_3d_b200.data import FactorZeroCenterScaler
+
+    sc = FactorZeroCenterScaler(-1024, 1500, 600)
+    gen = torch.Generator().manual_seed(8)
+    patch = (32, 32, 32)
+    hu = [torch.randint(-1024, 1500, (n, 1, *patch), generator=gen, dtype=torch.int16) for n in (2, 1, 1)]
+    ml, mh = O.synthetic_masks(gen, (1, 1, *patch)), O.synthetic_masks(gen, (1, 1, *patch))
+    scaled = [torch.from_numpy(sc(h.numpy().astype(np.float32)).astype(np.float32)) for h in hu]
+    a, b = _make_trainer(torch.float32), _make_trainer(torch.float32)
+    b.hu_scaler = sc
+    la = a.train_step([dict(data=scaled[0], seg=None), dict(data=scaled[1], seg=ml), dict(data=scaled[2], seg=mh)], 0)
+    lb = b.train_step([dict(data=hu[0].pin_memory(), seg=None), dict(data=hu[1].pin_memory(), seg=ml), dict(data=hu[2].pin_memory(), seg=mh)], 0)
+    for k in KEYS:
+        assert float(lb[k]) == pytest.approx(float(la[k]), rel=1e-5, abs=1e-7), k
+    with pytest.raises(ValueError, match="hu_scaler"):
+        a.train_step([dict(data=hu[0], seg=None), dict(data=hu[1], seg=ml), dict(data=hu[2], seg=mh)], 0)
+
+
 def test_generator_only_iterations_and_cadence():
     tr = _make_trainer(torch.float32)
     tr.train_generator_every = 2
