@@ -564,6 +564,57 @@ def test_raw_int16_hu_batches_scaled_on_device():
         a.train_step([dict(data=hu[0], seg=None), dict(data=hu[1], seg=ml), dict(data=hu[2], seg=mh)], 0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_cuda_graphed_step_equals_eager_step(dtype):
+    """Trainer.enable_cuda_graph: the captured + replayed step (3 eager warm-ups, capture at the 4th step, replays after it)
+    against the eager Trainer on the same batches, with an LR schedule that changes the rate while the graph is live
+    (learning rate and Adam step count are device-resident in FusedAdam) and a generator trained every second iteration
+    (two graph variants)."""
+    from torch.optim.lr_scheduler import MultiStepLR
+
+    def make():
+        tr = _make_trainer(dtype)
+        tr.lr_scheduler_G = MultiStepLR(tr.optimizer_G, milestones=[2, 4], gamma=0.5)
+        tr.lr_scheduler_D = MultiStepLR(tr.optimizer_D, milestones=[5, 8], gamma=0.5)
+        tr.train_generator_every = 2
+        return tr
+
+    a, b = make(), make()
+    b.enable_cuda_graph(warmup=2)
+    gen = torch.Generator().manual_seed(17)
+    patch = (32, 32, 32)
+    steps = 12
+    la, lb = [], []
+    for it in range(steps):
+        opt, low, high, ml, mh = _batches(gen, patch)
+        p = [dict(data=opt, seg=None, name=[]), dict(data=low, seg=ml, name=[]), dict(data=high, seg=mh, name=[])]
+        ra = a.train_step(p, it)
+        la.append({k: float(v) for k, v in ra.items()})
+        rb = b.train_step(p, it)
+        lb.append({k: float(v) for k, v in rb.items()})  # read before the next replay overwrites the static outputs
+    ents = b._graphs["entries"]
+    assert len(ents) == 2 and all(e["graph"] is not None for e in ents.values()), "both variants (critic only / critic + generator) captured"
+    assert b.optimizer_G.param_groups[0]["lr"] == a.optimizer_G.param_groups[0]["lr"] == 2e-4 * 0.25
+    assert b.optimizer_D.param_groups[0]["lr"] == a.optimizer_D.param_groups[0]["lr"] == 2e-4 * 0.25
+    for o_a, o_b in ((a.optimizer_G, b.optimizer_G), (a.optimizer_D, b.optimizer_D)):
+        sa = [o_a.state[p]["step"] for p in o_a.param_groups[0]["params"]]
+        sb = [o_b.state[p]["step"] for p in o_b.param_groups[0]["params"]]
+        assert sa == sb, "host-side Adam step counts follow the replays"
+        hyper = o_b._dev[id(o_b.param_groups[0])]["hyper"].cpu()
+        assert float(hyper[1]) == sa[0] and float(hyper[0]) == pytest.approx(o_b.param_groups[0]["lr"])
+    rt, at = (2e-3, 1e-4) if dtype == torch.float32 else (2e-2, 2e-3)  # same kernels; fp atomics order differs between runs
+    for it in range(steps):
+        assert set(la[it]) == set(lb[it])
+        for k in la[it]:
+            assert abs(la[it][k] - lb[it][k]) <= rt * abs(la[it][k]) + at, (it, k, la[it][k], lb[it][k])
+    for (k, va), vb in zip(a.generator.state_dict().items(), b.generator.state_dict().values()):
+        if "num_batches" in k:
+            assert int(va) == int(vb), k
+        elif "running_" not in k:
+            assert_close32(va, vb, rtol=0, atol=2 * 2e-4 * steps, msg=k)
+            assert float((va.float() - vb.float()).abs().mean()) < 1e-4, k
+
+
 def test_generator_only_iterations_and_cadence():
     tr = _make_trainer(torch.float32)
     tr.train_generator_every = 2
