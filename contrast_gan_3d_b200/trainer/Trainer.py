@@ -407,6 +407,11 @@ class Trainer:
             if mask_ev is not None:
                 main.wait_event(mask_ev)
             ent["mask"].copy_(mask_in, non_blocking=True)
+        # Everything the graphed path hands back is DETACHED: a loss tensor that still referenced the step's autograd graph
+        # would keep its AccumulateGrad nodes (bound to the stream of that step) alive into the capture, where autograd
+        # would synchronise the capturing stream with the default stream and invalidate the capture.
+        core = lambda: tuple(({k: v.detach() for k, v in o.items()} if isinstance(o, dict) else o.detach())
+                             for o in self._step_core(ent["sub"], ent["opt"], ent["mask"], do_c, do_g))
         if ent["graph"] is not None:
             ent["graph"].replay()
             self.optimizer_G.note_graph_replay() if do_g else None
@@ -414,7 +419,7 @@ class Trainer:
             out = ent["out"]
         elif ent["seen"] < self._graphs["warmup"]:
             ent["seen"] += 1
-            out = self._step_core(ent["sub"], ent["opt"], ent["mask"], do_c, do_g)
+            out = core()
         else:
             from .. import _lib
 
@@ -423,7 +428,7 @@ class Trainer:
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                out = self._step_core(ent["sub"], ent["opt"], ent["mask"], do_c, do_g)
+                out = core()
             ent["launches"] = _lib.launch_count - n0
             ent["graph"], ent["out"] = g, out
             g.replay()  # the capture only recorded this step; run it (its optimizer host counters were advanced while recording)
