@@ -274,29 +274,36 @@ class Trainer:
         self._staging_used = set()
 
     def prefetch(self, patches: List[dict]) -> None:
-        """Start the host->device copy of the NEXT step's generator input (the [low; high] batch, the one upload that
-        `train_step` needs before it can launch anything) on the side stream while the current step is still running.
-        `fit` calls this with the batch it has just drawn for the following iteration; `train_step` recognises the batch by
-        the identity of its host tensors and only waits on the copy's event.  Two alternating staging tensors: the step in
-        flight still reads the other one (the similarity loss uses the input until the end of the step)."""
-        _, low, high = patches
-        parts = [low["data"], high["data"]]
-        if all(self._on_device(t) for t in parts):
+        """Start the host->device copies of the NEXT step's batch (generator input [low; high], the real batch and the
+        masks) on the side stream while the current step is still running.  `fit` calls this with the batch it has just
+        drawn for the following iteration; `train_step` recognises the batch by the identity of its host tensors and only
+        waits on the copies' events.  Two alternating sets of staging tensors: the step in flight still reads the other
+        set (the similarity loss uses the generator input until the end of the step)."""
+        opt, low, high = patches
+        groups = {"subopt": [low["data"], high["data"]], "opt": [opt["data"]]}
+        if low.get("seg") is not None and high.get("seg") is not None:
+            groups["mask"] = [low["seg"], high["seg"]]
+        if all(self._on_device(t) for parts in groups.values() for t in parts):
             return
         flip = 1 - getattr(self, "_prefetch_flip", 1)
         self._prefetch_flip = flip
-        key = f"subopt{flip}"
-        buf, ev = self._side_upload(key, parts, consumed_now=False)
-        self._prefetched = (tuple(id(t) for t in parts), buf, ev, key)
+        got = {}
+        for name, parts in groups.items():
+            key = f"{name}{flip}"
+            buf, ev = self._side_upload(key, parts, consumed_now=False)
+            got[name] = (tuple(id(t) for t in parts), buf, ev, key)
+        self._prefetched = got
 
-    def _take_prefetched(self, low: dict, high: dict):
+    def _take_prefetched(self, name: str, parts: List[Tensor]):
+        """(device tensor, event) of a part uploaded by `prefetch` for exactly these host tensors, else None."""
         pf = getattr(self, "_prefetched", None)
-        self._prefetched = None
-        if pf is None or pf[0] != (id(low["data"]), id(high["data"])):
+        if not pf or name not in pf:
             return None
-        torch.cuda.current_stream(self.device).wait_event(pf[2])
-        self._staging_used.add(pf[3])
-        return pf[1]
+        ids, buf, ev, key = pf.pop(name)
+        if ids != tuple(id(t) for t in parts):
+            return None
+        self._staging_used.add(key)
+        return buf, ev
 
     def _scaled(self, t: Optional[Tensor], out: Optional[Tensor] = None) -> Optional[Tensor]:
         """fp32 network input from a device batch: int16 raw HU -> (hu - shift) / factor on the device, fp32 passes through
@@ -343,11 +350,21 @@ class Trainer:
         do_train_generator = iteration % self.train_generator_every == 0
         do_train_critic = iteration % self.train_critic_every == 0
         main = torch.cuda.current_stream(self.device)
-        subopt = self._take_prefetched(low, high)  # copied during the previous step when `prefetch` was called with this batch
-        if subopt is None:
+        # parts copied during the previous step (when `prefetch` was called with this batch) only need their events waited on
+        pf = self._take_prefetched("subopt", [low["data"], high["data"]])
+        if pf is not None:
+            subopt = pf[0]
+            if pf[1] is not None:
+                main.wait_event(pf[1])
+        else:
             subopt = self._upload_cat(low["data"], high["data"])  # needed first: on the compute stream
-        opt_t, opt_ev = self._side_upload("opt", [opt["data"]]) if do_train_critic else (None, None)
-        mask_t, mask_ev = self._side_upload("mask", [low["seg"], high["seg"]]) if do_train_generator else (None, None)
+        opt_t = opt_ev = mask_t = mask_ev = None
+        if do_train_critic:
+            opt_t, opt_ev = self._take_prefetched("opt", [opt["data"]]) or self._side_upload("opt", [opt["data"]])
+        if do_train_generator:
+            mask_t, mask_ev = (self._take_prefetched("mask", [low["seg"], high["seg"]])
+                               or self._side_upload("mask", [low["seg"], high["seg"]]))
+        self._prefetched = None
 
         if self._graphs is not None:
             log_dict, attenuation, opt_hat = self._graphed_step(subopt, opt_t, opt_ev, mask_t, mask_ev, do_train_critic, do_train_generator)
