@@ -296,6 +296,27 @@ def run_reference(args):
     }), file=real_stdout)
 
 
+def shutdown(tr=None, dist=None, world=1):
+    """Leave without hanging: CUDA graphs that recorded NCCL kernels must be gone before the communicator is torn down
+    (destroying the process group under a live graph blocked the NCCL watchdog for minutes), and the teardown itself runs
+    in a helper thread with a deadline; the process then exits with status 0 whatever NCCL does."""
+    import gc
+
+    import torch
+
+    sys.stdout.flush(); sys.stderr.flush()
+    if tr is not None:
+        tr.release_cuda_graphs()
+    gc.collect()
+    torch.cuda.synchronize()
+    if world > 1 and dist is not None and dist.is_initialized():
+        t = threading.Thread(target=lambda: dist.destroy_process_group(), daemon=True)
+        t.start()
+        t.join(timeout=20)
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -486,10 +507,10 @@ def main():
               "unit": "pairs/s", "step_frac_of_peak": 8 * PAIR_GFLOP_128 * (args.patch / 128) ** 3 / (ms4 * 1e-3) / 1e3 / peaks()["bf16_sustained"]}
         del res4, host4, host4f
 
+    if world > 1:
+        dist.barrier()  # every rank has finished its timed loops
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        shutdown(tr, dist, world)
 
     pk = peaks()
     # dominant conv kernel of the step (by summed device time) and its tensor-pipe roofline
@@ -526,7 +547,7 @@ def main():
             f.write(f"conv total ms/step {sum(r[4] for r in rows):.3f} of step {ms:.3f}\n")
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the reference's CPU step is timed at N = 1 only (rank 0 is the only rank)
         # The reference's CPU step, timed in a child process that hides the GPUs (see run_reference) and may use every core
         # of this box: 2 warm-ups + 5 timed steps of 2 pairs at this patch size, median.
         env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE")}
@@ -562,9 +583,8 @@ def main():
         "cuda_graph": not args.no_graph,
         "losses_last_step": {k: float(v.detach()) for k, v in logs.items()},
     }
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    shutdown(tr, dist, world)
 
 
 if __name__ == "__main__":

@@ -458,6 +458,15 @@ class Trainer:
             self.optimizer_G.sync_device_hyper()
         return out
 
+    def release_cuda_graphs(self) -> None:
+        """Drop the captured graphs (and their static tensors / private memory pool) and return to eager steps.  Call this
+        before tearing down a process group whose collectives were recorded in the graphs."""
+        if self._graphs is not None:
+            torch.cuda.synchronize(self.device)
+            self._graphs["entries"].clear()
+            self._graphs = None
+            self._defer_schedulers = False
+
     def graph_launches_per_step(self) -> int:
         """libcgan3d entry-point calls recorded in the captured graphs (bench.py: gpu_launches)."""
         if self._graphs is None:
