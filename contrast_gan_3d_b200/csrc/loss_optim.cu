@@ -231,6 +231,27 @@ adam_multi_dev_kernel(const __grid_constant__ AdamBatch t, const float *__restri
   }
 }
 
+// RMSprop (torch.optim.RMSprop defaults: no momentum, not centered; reference experiments/rmsprop_conf.py:8-9):
+// v = alpha v + (1 - alpha) g^2;  p -= lr g / (sqrt(v) + eps)  [+ weight clip].  The AdamBatch table is reused: m is unused.
+__global__ void __launch_bounds__(256)
+rmsprop_multi_kernel(const __grid_constant__ AdamBatch t, float lr, float alpha, float eps, float clip) {
+  const int k = blockIdx.y;
+  float *__restrict__ p = t.p[k];
+  const float *__restrict__ g = t.g[k];
+  float *__restrict__ v = t.v[k];
+  const int64_t n = t.n[k];
+  const float w = 1.f - alpha;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float vi = v[i] * alpha;
+    vi = vi + (w * gi) * gi;  // torch: square_avg.mul_(alpha).addcmul_(grad, grad, value = 1 - alpha)
+    float pi = p[i] + (-lr) * (gi / (sqrtf(vi) + eps));
+    if (clip > 0.f) pi = fminf(fmaxf(pi, -clip), clip);
+    v[i] = vi;
+    p[i] = pi;
+  }
+}
+
 // ---------------------------------------------------------------- sampler / tiler
 __global__ void __launch_bounds__(256)
 crop_scale_kernel(const int16_t *__restrict__ vol, int X, int Y, int Z, int lbx, int lby, int lbz, int PX, int PY, int PZ,
@@ -430,6 +451,27 @@ int cgan3d_adam_step_multi_dev(int count, float *const *params, const float *con
     const int bx = (int)((nmax + 255) / 256 < 64 ? (nmax + 255) / 256 : 64);
     adam_multi_dev_kernel<<<dim3(bx, nb), 256, 0, as_stream(stream)>>>(t, hyper, beta1, beta2, eps, clip);
     CG_LAUNCH_CHECK("adam_step_multi_dev");
+  }
+  return 0;
+}
+
+int cgan3d_rmsprop_step_multi(int count, float *const *params, const float *const *grads, float *const *square_avgs,
+                              const int64_t *numels, float lr, float alpha, float eps, float clip, void *stream) {
+  CG_CHECK_ARG(count >= 0 && (count == 0 || (params && grads && square_avgs && numels)), "rmsprop_step_multi: NULL table");
+  for (int i0 = 0; i0 < count; i0 += kAdamBatch) {
+    AdamBatch t{};
+    const int nb = count - i0 < kAdamBatch ? count - i0 : kAdamBatch;
+    int64_t nmax = 0;
+    for (int i = 0; i < nb; ++i) {
+      CG_CHECK_ARG(params[i0 + i] && grads[i0 + i] && square_avgs[i0 + i] && numels[i0 + i] >= 0, "rmsprop_step_multi: NULL tensor %d", i0 + i);
+      t.p[i] = params[i0 + i]; t.g[i] = grads[i0 + i]; t.m[i] = nullptr; t.v[i] = square_avgs[i0 + i];
+      t.n[i] = numels[i0 + i];
+      nmax = nmax > t.n[i] ? nmax : t.n[i];
+    }
+    if (nmax == 0) continue;
+    const int bx = (int)((nmax + 255) / 256 < 64 ? (nmax + 255) / 256 : 64);
+    rmsprop_multi_kernel<<<dim3(bx, nb), 256, 0, as_stream(stream)>>>(t, lr, alpha, eps, clip);
+    CG_LAUNCH_CHECK("rmsprop_step_multi");
   }
   return 0;
 }

@@ -120,3 +120,54 @@ class FusedAdam(Optimizer):
                     call("cgan3d_adam_step_multi", n, tabs[0], tabs[1], tabs[2], tabs[3], numels, float(group["lr"]), float(b1),
                          float(b2), float(group["eps"]), int(step), float(c or 0.0), ops._st())
         return loss
+
+
+class FusedRMSprop(Optimizer):
+    """torch.optim.RMSprop with its default settings (alpha 0.99, eps 1e-8, no momentum, not centered, no weight decay:
+    what reference experiments/rmsprop_conf.py:8-9 constructs) as one libcgan3d launch per 48 tensors, with the critic
+    weight clip fused in like FusedAdam."""
+
+    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, clip: float = 0.0):
+        defaults = dict(lr=lr, alpha=alpha, eps=eps, clip=clip, weight_decay=0, momentum=0, centered=False, capturable=False,
+                        foreach=None, maximize=False, differentiable=False)
+        super().__init__(params, defaults)
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for group in self.param_groups:
+            group.setdefault("clip", 0.0)
+            if group.get("momentum", 0) or group.get("centered", False) or group.get("weight_decay", 0):
+                raise NotImplementedError("FusedRMSprop implements plain RMSprop (the reference's settings)")
+        for st in self.state.values():
+            if torch.is_tensor(st.get("step")):
+                st["step"] = int(st["step"].item())
+
+    @torch.no_grad()
+    def step(self, closure=None, clip: float | None = None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            c = group.get("clip", 0.0) if clip is None else clip
+            items = []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["square_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.float().contiguous()
+                ops._need_cuda(p, g)
+                items.append((p.data, g, st["square_avg"]))
+            if items:
+                n = len(items)
+                tabs = [(C.c_void_p * n)(*[t[k].data_ptr() for t in items]) for k in range(3)]
+                numels = (C.c_int64 * n)(*[t[0].numel() for t in items])
+                call("cgan3d_rmsprop_step_multi", n, tabs[0], tabs[1], tabs[2], numels, float(group["lr"]), float(group["alpha"]),
+                     float(group["eps"]), float(c or 0.0), ops._st())
+        return loss

@@ -24,7 +24,7 @@ from torch import Tensor, nn
 from .. import ops
 from ..model.loss import HULoss, WassersteinLoss, ZNCCLoss, fused_similarity_and_hu
 from ..model.utils import wgan_gradient_penalty
-from ..optim import FusedAdam
+from ..optim import FusedAdam, FusedRMSprop
 
 logger = logging.getLogger(__name__)
 
@@ -172,8 +172,8 @@ class Trainer:
             self.grad_reducer.finish(self.critic.parameters())
         elif self.grad_reducer is not None:
             self.grad_reducer.reduce(self.critic.parameters())
-        if isinstance(self.optimizer_D, FusedAdam):
-            self.optimizer_D.step(clip=self.weight_clip or 0.0)  # Adam + clamp(+-clip) in one kernel
+        if isinstance(self.optimizer_D, (FusedAdam, FusedRMSprop)):
+            self.optimizer_D.step(clip=self.weight_clip or 0.0)  # update + clamp(+-clip) in one kernel
         else:
             self.optimizer_D.step()
             if self.weight_clip is not None:

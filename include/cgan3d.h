@@ -202,6 +202,11 @@ int cgan3d_adam_step_multi_dev(int count, float *const *params, const float *con
                                float *const *exp_avg_sqs, const int64_t *numels, const float *hyper, float beta1,
                                float beta2, float eps, float clip, void *stream);
 
+/* torch.optim.RMSprop (defaults: alpha 0.99, eps 1e-8, no momentum, not centered; reference
+ * experiments/rmsprop_conf.py:8-9) for `count` tensors per launch, with the optional critic weight clip.             */
+int cgan3d_rmsprop_step_multi(int count, float *const *params, const float *const *grads, float *const *square_avgs,
+                              const int64_t *numels, float lr, float alpha, float eps, float clip, void *stream);
+
 /* ---- patch sampler (reference data/CCTADataLoader.py:76-95, data/Scaler.py:41-42) ----------
  * vol: int16 [X][Y][Z][2] (HU, centerline mask) on device.  Pads symmetrically with 0 up to the
  * patch size (below = d//2), crops at lower bounds lb (computed on the host by the index law),

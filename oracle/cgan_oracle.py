@@ -287,6 +287,24 @@ class AdamState:
             p.data.addcdiv_(self.m[k], denom, value=-step_size)
 
 
+class RMSpropState:
+    """torch.optim.RMSprop single-tensor algorithm at its defaults (alpha 0.99, eps 1e-8, no momentum, not centered), the
+    optimizer of experiments/rmsprop_conf.py:8-9; same interface as AdamState."""
+
+    def __init__(self, params, lr=2e-4, alpha=0.99, eps=1e-8):
+        self.lr, self.alpha, self.eps = lr, alpha, eps
+        self.v = {k: torch.zeros_like(v) for k, v in params.items()}
+
+    def apply(self, params, grads, lr: Optional[float] = None):
+        lr = self.lr if lr is None else lr
+        for k, p in params.items():
+            g = grads.get(k)
+            if g is None:
+                continue
+            self.v[k].mul_(self.alpha).addcmul_(g, g, value=1 - self.alpha)
+            p.data.addcdiv_(g, self.v[k].sqrt().add_(self.eps), value=-lr)
+
+
 def multistep_lr(base_lr: float, milestones: Sequence[int], gamma: float, n_steps_done: int) -> float:
     """MultiStepLR value after `n_steps_done` scheduler steps (basic_conf.py:35-36,56-58)."""
     return base_lr * gamma ** sum(1 for m in milestones if n_steps_done >= m)

@@ -615,6 +615,43 @@ def test_cuda_graphed_step_equals_eager_step(dtype):
             assert float((va.float() - vb.float()).abs().mean()) < 1e-4, k
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_rmsprop_small_patch_configuration_against_oracle(dtype):
+    """The reference's rmsprop_conf.py (RMSprop for both networks, which star-imports small_patch_size.py: non-cubic
+    128 x 128 x 32 patches): two steps with FusedRMSprop (+ fused weight clip) against the oracle stepping with the
+    torch.optim.RMSprop algorithm."""
+    from contrast_gan_3d_b200.model import HULoss, PatchGANDiscriminator, ResnetGenerator
+    from contrast_gan_3d_b200.optim import FusedRMSprop
+    from contrast_gan_3d_b200.trainer.Trainer import NullLogger, Trainer
+
+    patch = (128, 128, 32)
+    st = O.StepState(seed=0)
+    st.opt_g, st.opt_d = O.RMSpropState(st.gp, 2e-4), O.RMSpropState(st.dp, 2e-4)
+    torch.manual_seed(0)
+    tr = Trainer(10, 2, None, 1, 1, 1, 0, partial(ResnetGenerator, 4, 2, 16, compute_dtype=dtype),
+                 partial(PatchGANDiscriminator, 1, 8, 3, negative_slope=0.2, compute_dtype=dtype),
+                 partial(FusedRMSprop, lr=2e-4), partial(FusedRMSprop, lr=2e-4),
+                 HULoss(0.18666666666666668, 0.35333333333333333), NullLogger(), torch.device(DEV), weight_clip=0.01,
+                 checkpoint_every=None)
+    gen = torch.Generator().manual_seed(23)
+    for it in range(2):
+        opt, low, high, ml, mh = _batches(gen, patch)
+        ref = O.train_step(st, opt, low, high, ml, mh, it)
+        logs = tr.train_step([dict(data=opt, seg=None, name=[]), dict(data=low, seg=ml, name=[]), dict(data=high, seg=mh, name=[])], it)
+        for k in KEYS:
+            got = float(logs[k].detach())
+            if dtype == torch.float32:
+                rt, at = (1e-4, 1e-5) if it == 0 else (5e-4, 5e-5)
+            else:
+                rt, at = 2e-2, (2e-3 if k in ("D", "G", "G-full") else 1e-3)
+            assert abs(got - ref[k]) <= rt * abs(ref[k]) + at, (it, k, got, ref[k])
+    if dtype == torch.float32:
+        for k, v in tr.critic.state_dict().items():
+            if "running_" in k or "num_batches" in k:
+                continue
+            assert float(v.abs().max()) <= 0.01 + 1e-7, k  # the clip is fused into the RMSprop kernel
+
+
 def test_generator_only_iterations_and_cadence():
     tr = _make_trainer(torch.float32)
     tr.train_generator_every = 2

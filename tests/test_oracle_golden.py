@@ -275,3 +275,18 @@ def test_wgan_gp_fp32_drift_control_against_fp64():
     use = np.abs(a - b) / (1e-4 * np.abs(b) + 1e-5)
     assert use[0].max() < 0.05, use[0]
     assert 5.0 < use[2].max() < 100.0, use
+
+
+def test_oracle_rmsprop_matches_torch_rmsprop():
+    """The oracle's RMSprop (experiments/rmsprop_conf.py:8-9 constructs torch.optim.RMSprop(lr=lr)) against torch itself."""
+    torch.manual_seed(0)
+    p = {"a": torch.randn(50)}
+    q = p["a"].clone().requires_grad_(True)
+    opt = torch.optim.RMSprop([q], lr=2e-4)
+    st = O.RMSpropState(p, 2e-4)
+    for i in range(4):
+        g = torch.randn(50) * 10.0 ** (i - 2)
+        q.grad = g.clone()
+        opt.step()
+        st.apply(p, {"a": g})
+    assert torch.equal(p["a"], q.detach())
