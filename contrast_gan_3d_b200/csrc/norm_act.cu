@@ -414,9 +414,15 @@ template <typename T, int ACT>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_apply8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t total8, int C, double inv_n,
                      const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
-                     float slope, const double *__restrict__ sums) {
+                     float slope, const double *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta, float acc) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0) {  // the parameter gradients are the reduction's totals: dbeta = sum g, dgamma = sum g * xhat
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (acc != 0.f ? dbeta[c] : 0.f) + (float)sums[c];
+      if (dgamma) dgamma[c] = (acc != 0.f ? dgamma[c] : 0.f) + (float)sums[C + c];
+    }
+  }
   const int c0 = (int)((i * 8) % C);
   BnC8 k8;
   k8.load(mi, gamma, beta, C, c0);
@@ -541,7 +547,14 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t total, int C,
                     double inv_n, const float *__restrict__ mi, const float *__restrict__ gamma,
-                    const float *__restrict__ beta, int act, float slope, const double *__restrict__ sums) {
+                    const float *__restrict__ beta, int act, float slope, const double *__restrict__ sums,
+                    float *__restrict__ dgamma, float *__restrict__ dbeta, float acc) {
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (acc != 0.f ? dbeta[c] : 0.f) + (float)sums[c];
+      if (dgamma) dgamma[c] = (acc != 0.f ? dgamma[c] : 0.f) + (float)sums[C + c];
+    }
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const float invstd = mi[C + c];
@@ -784,8 +797,9 @@ int cgan3d_bn_backward_reduce(const void *dz, const void *y, int dtype, int64_t 
 
 int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype, int64_t n_rows, int C,
                              const float *mean_invstd, const float *gamma, const float *beta, int act, float slope,
-                             const double *sums, float *dgamma, float *dbeta, void *stream) {
+                             const double *sums, float *dgamma, float *dbeta, float grad_beta, void *stream) {
   CG_CHECK_ARG(dz && y && dy && mean_invstd && gamma && beta && sums, "bn_backward_apply: NULL pointer");
+  CG_CHECK_ARG(grad_beta == 0.f || grad_beta == 1.f, "bn_backward_apply: grad_beta must be 0 (overwrite) or 1 (accumulate)");
   CG_DTYPE_OK(dtype, "bn_backward_apply");
   CG_CHECK_SHAPE(n_rows > 0 && C > 0, "bn_backward_apply: bad sizes");
   cudaStream_t st = as_stream(stream);
@@ -797,11 +811,11 @@ int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype,
       constexpr int A = decltype(act_tag)::value;
       if (dtype == CGAN3D_F32)
         bn_bwd_apply8_kernel<float, A><<<ew_blocks(t8), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, t8, C, inv_n,
-                                                                      mean_invstd, gamma, beta, act, slope, sums);
+                                                                      mean_invstd, gamma, beta, act, slope, sums, dgamma, dbeta, grad_beta);
       else
         bn_bwd_apply8_kernel<__nv_bfloat16, A><<<ew_blocks(t8), 256, 0, st>>>((const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y,
                                                                               (__nv_bfloat16 *)dy, t8, C, inv_n, mean_invstd, gamma,
-                                                                              beta, act, slope, sums);
+                                                                              beta, act, slope, sums, dgamma, dbeta, grad_beta);
     };
     if (act == CGAN3D_ACT_RELU) go(std::integral_constant<int, CGAN3D_ACT_RELU>{});
     else if (act == CGAN3D_ACT_LRELU) go(std::integral_constant<int, CGAN3D_ACT_LRELU>{});
@@ -810,20 +824,12 @@ int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype,
     CG_LAUNCH_CHECK("bn_backward_apply(vec8)");
   } else if (dtype == CGAN3D_F32)
     bn_bwd_apply_kernel<float><<<ew_blocks(total), 256, 0, st>>>((const float *)dz, (const float *)y, (float *)dy, total, C,
-                                                                 inv_n, mean_invstd, gamma, beta, act, slope, sums);
+                                                                 inv_n, mean_invstd, gamma, beta, act, slope, sums, dgamma, dbeta, grad_beta);
   else
     bn_bwd_apply_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, st>>>(
         (const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)dy, total, C, inv_n, mean_invstd, gamma, beta,
-        act, slope, sums);
+        act, slope, sums, dgamma, dbeta, grad_beta);
   CG_LAUNCH_CHECK("bn_backward_apply");
-  if (dbeta) {
-    sums_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dbeta, C, 1.f, 0.f);
-    CG_LAUNCH_CHECK("bn_backward dbeta");
-  }
-  if (dgamma) {
-    sums_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums + C, dgamma, C, 1.f, 0.f);
-    CG_LAUNCH_CHECK("bn_backward dgamma");
-  }
   return 0;
 }
 

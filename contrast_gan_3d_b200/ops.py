@@ -201,6 +201,24 @@ def forget_forward_uses(params) -> None:
         _FWD_USES.pop(id(p), None)
 
 
+def _direct_target(param):
+    """`param.grad` when the active sink wants this parameter's gradient accumulated in place by our kernel, else None."""
+    sink = _GRAD_SINK
+    if sink is not None and param is not None and sink.accepts(param):
+        return param.grad
+    return None
+
+
+def _grad_handled(param, direct: bool) -> None:
+    """One pending application of `param` has produced its gradient (in place when `direct`)."""
+    if param is None:
+        return
+    left = _FWD_USES.get(id(param), 1) - 1
+    _FWD_USES[id(param)] = max(left, 0)
+    if direct and left <= 0:
+        _GRAD_SINK.direct_done(param)
+
+
 def _weight_grad(weight, g: ConvGeom, big, small):
     """The weight gradient of one conv application: returned to autograd, or (sink active) accumulated in place on the
     sink's side stream, in which case None is returned and the sink is told when the parameter's last pending
@@ -353,8 +371,11 @@ class ConvBlockFn(torch.autograd.Function):
             z = cast(z, torch.float32)
         ctx.cfg, ctx.g = cfg, g
         ctx.wparam = weight if ctx.needs_input_grad[1] else None  # the parameter itself: its .grad may be the wgrad sink
-        if ctx.wparam is not None:
-            _note_forward_use(weight)
+        ctx.small_params = tuple(p if (p is not None and ctx.needs_input_grad[i]) else None
+                                 for i, p in ((2, bias), (3, gamma), (4, beta)))
+        for p in (ctx.wparam,) + ctx.small_params:
+            if p is not None:
+                _note_forward_use(p)
         ctx.x_dtype = x.dtype
         ctx.has_res = residual is not None
         ctx.res_dtype = None if residual is None else residual.dtype
@@ -381,18 +402,32 @@ class ConvBlockFn(torch.autograd.Function):
             call("cgan3d_bn_backward_reduce", _p(dz), _p(y), dt, n_rows, Co, _p(mi), _p(gamma), _p(beta), cfg.act,
                  cfg.slope, _p(sums), _st())
             dy = torch.empty_like(y)
-            dgamma = torch.empty(Co, dtype=torch.float32, device=y.device)
-            dbeta = torch.empty(Co, dtype=torch.float32, device=y.device)
+            pbias, pgamma, pbeta = ctx.small_params
+            # parameter gradients: accumulated into the gradient bucket by the same launch when a sink is active
+            tg, tb = _direct_target(pgamma), _direct_target(pbeta)
+            direct = tg is not None and tb is not None
+            if not direct:
+                tg = torch.empty(Co, dtype=torch.float32, device=y.device)
+                tb = torch.empty(Co, dtype=torch.float32, device=y.device)
             call("cgan3d_bn_backward_apply", _p(dz), _p(y), _p(dy), dt, n_rows, Co, _p(mi), _p(gamma), _p(beta),
-                 cfg.act, cfg.slope, _p(sums), _p(dgamma), _p(dbeta), _st())
+                 cfg.act, cfg.slope, _p(sums), _p(tg), _p(tb), 1.0 if direct else 0.0, _st())
+            _grad_handled(pgamma, direct)
+            _grad_handled(pbeta, direct)
+            dgamma, dbeta = (None, None) if direct else (tg, tb)
         elif bias is not None or cfg.act != _lib.ACT_NONE:
             sums = torch.empty(Co, dtype=torch.float64, device=y.device)
             dy = torch.empty_like(y)
             call("cgan3d_bias_act_backward", _p(dz), _p(y), _p(dy), dt, n_rows, Co, _p(bias), cfg.act, cfg.slope,
                  _p(sums), _st())
             if bias is not None:
-                dbias = torch.empty(Co, dtype=torch.float32, device=y.device)
-                call("cgan3d_sums_to_f32", _p(sums), _p(dbias), Co, 1.0, 0.0, _st())
+                pbias = ctx.small_params[0]
+                tb = _direct_target(pbias)
+                direct = tb is not None
+                dbias = tb if direct else torch.empty(Co, dtype=torch.float32, device=y.device)
+                call("cgan3d_sums_to_f32", _p(sums), _p(dbias), Co, 1.0, 1.0 if direct else 0.0, _st())
+                _grad_handled(pbias, direct)
+                if direct:
+                    dbias = None
         else:
             dy = dz
         dres = cast(dz, ctx.res_dtype) if ctx.has_res else None
@@ -440,8 +475,10 @@ class GenTailFn(torch.autograd.Function):
         call("cgan3d_tanh_residual", _p(y), _p(bias.detach()), _p(sub), _p(att), _p(opt_hat), _dt(cfg.dtype), n, _st())
         ctx.cfg, ctx.g, ctx.x_dtype = cfg, g, x.dtype
         ctx.wparam = weight if ctx.needs_input_grad[1] else None
-        if ctx.wparam is not None:
-            _note_forward_use(weight)
+        ctx.bparam = bias if ctx.needs_input_grad[2] else None
+        for p in (ctx.wparam, ctx.bparam):
+            if p is not None:
+                _note_forward_use(p)
         ctx.save_for_backward(xin, wp, att)
         if opt_hat is None:
             return att, att.new_empty(0)
@@ -462,8 +499,13 @@ class GenTailFn(torch.autograd.Function):
         dy = torch.empty((g.B, g.Xs, g.Ys, g.Zs, 1), dtype=cfg.dtype, device=att.device)
         sums = torch.empty(1, dtype=torch.float64, device=att.device)
         call("cgan3d_tanh_residual_backward", _p(do), _p(da), _p(att), _p(dy), _dt(cfg.dtype), n, _p(sums), _st())
-        dbias = torch.empty(1, dtype=torch.float32, device=att.device)
-        call("cgan3d_sums_to_f32", _p(sums), _p(dbias), 1, 1.0, 0.0, _st())
+        tb = _direct_target(ctx.bparam)
+        direct = tb is not None
+        dbias = tb if direct else torch.empty(1, dtype=torch.float32, device=att.device)
+        call("cgan3d_sums_to_f32", _p(sums), _p(dbias), 1, 1.0, 1.0 if direct else 0.0, _st())
+        _grad_handled(ctx.bparam, direct)
+        if direct:
+            dbias = None
         dx = None
         if ctx.needs_input_grad[0]:
             dx = conv_scatter(g, dy, wp)

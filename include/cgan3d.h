@@ -137,10 +137,13 @@ int cgan3d_bn_apply_pad(const void *y, void *z_padded, int dtype, int B, int X, 
 int cgan3d_bn_backward_reduce(const void *dz, const void *y, int dtype, int64_t n_rows, int C,
                               const float *mean_invstd, const float *gamma, const float *beta, int act,
                               float slope, double *sums, void *stream);
-/* Pass 2: dy = gamma*invstd*(g - sum_g/n - xhat*sum_gx/n); dgamma/dbeta (fp32 [C], beta_acc 0/1). */
+/* Pass 2: dy = gamma*invstd*(g - sum_g/n - xhat*sum_gx/n); the same launch writes the parameter gradients dgamma = sum
+ * g*xhat, dbeta = sum g (fp32 [C], may be NULL): grad_beta = 0 overwrites them, 1 accumulates into them (the caller's
+ * gradient buffer: a layer applied twice per backward, reference trainer/Trainer.py:114-116).                          */
 int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype, int64_t n_rows, int C,
                              const float *mean_invstd, const float *gamma, const float *beta, int act,
-                             float slope, const double *sums, float *dgamma, float *dbeta, void *stream);
+                             float slope, const double *sums, float *dgamma, float *dbeta, float grad_beta,
+                             void *stream);
 /* bias + activation without norm (critic first layer, blocks.py:34 bias=True under Identity norm):
  * z = act(y + bias); backward: dy = dz * act'(y + bias), dbias = sum dy                     */
 int cgan3d_bias_act(const void *y, void *z, int dtype, int64_t n_rows, int C, const float *bias, int act,

@@ -35,7 +35,7 @@ def main():
             "bn_apply": (lambda: call("cgan3d_bn_apply", _p(y), _p(z), dt, rows, C, _p(mi), _p(gamma), _p(beta), _lib.ACT_RELU, 0.0, None, _st()), 2),
             "bn_apply+res": (lambda: call("cgan3d_bn_apply", _p(y), _p(z), dt, rows, C, _p(mi), _p(gamma), _p(beta), _lib.ACT_RELU, 0.0, _p(dz), _st()), 3),
             "bn_bwd_reduce": (lambda: call("cgan3d_bn_backward_reduce", _p(dz), _p(y), dt, rows, C, _p(mi), _p(gamma), _p(beta), _lib.ACT_RELU, 0.0, _p(sums), _st()), 2),
-            "bn_bwd_apply": (lambda: call("cgan3d_bn_backward_apply", _p(dz), _p(y), _p(z), dt, rows, C, _p(mi), _p(gamma), _p(beta), _lib.ACT_RELU, 0.0, _p(sums), _p(dg), _p(db), _st()), 3),
+            "bn_bwd_apply": (lambda: call("cgan3d_bn_backward_apply", _p(dz), _p(y), _p(z), dt, rows, C, _p(mi), _p(gamma), _p(beta), _lib.ACT_RELU, 0.0, _p(sums), _p(dg), _p(db), 0.0, _st()), 3),
             "torch_copy": (lambda: z.copy_(y), 2),
         }
         for name, (fn, passes) in cases.items():
