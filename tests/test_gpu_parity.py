@@ -486,6 +486,50 @@ def test_bn_apply_fused_with_reflect_pad(C, dtype, act):
     assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_conv_block_with_padded_output_backward_vs_aten(dtype):
+    """ConvBlock whose output carries its consumer's reflection padding (pad_out = 3, the generator's last up-sampling
+    block): forward and all gradients against ATen's conv_transpose3d -> batch_norm -> relu -> reflection_pad3d.  The
+    padding's adjoint is folded into the BatchNorm-backward kernels (cgan3d_bn_backward_*_pad)."""
+    from contrast_gan_3d_b200.model.blocks import ConvBlock
+    from torch import nn
+
+    torch.manual_seed(6)
+    blk = ConvBlock(False, 32, 16, 3, upsample=True, output_padding=1, padding=1, stride=2, compute_dtype=dtype)
+    with torch.no_grad():
+        blk.normalization.weight.uniform_(0.5, 1.5)
+        blk.normalization.bias.uniform_(-0.5, 0.5)
+    ref_conv = nn.ConvTranspose3d(32, 16, 3, stride=2, padding=1, output_padding=1, bias=False)
+    ref_bn = nn.BatchNorm3d(16)
+    ref_conv.load_state_dict(blk.conv.state_dict()); ref_bn.load_state_dict(blk.normalization.state_dict())
+    x = torch.randn(2, 32, 5, 6, 4)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+        with torch.no_grad():
+            ref_conv.weight.copy_(ref_conv.weight.bfloat16().float())
+            blk.conv.weight.copy_(ref_conv.weight)
+    x.requires_grad_(True)
+    yr = F.pad(F.relu(ref_bn(ref_conv(x))), (3,) * 6, mode="reflect")
+    gy = torch.randn_like(yr)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    gx_r, gw_r, gg_r, gb_r = torch.autograd.grad(yr, [x, ref_conv.weight, ref_bn.weight, ref_bn.bias], gy)
+    blk = blk.to(DEV)
+    xd = cl(x.detach()).to(DEV).requires_grad_(True)
+    yd = blk.forward_cl(xd, pad_out=3)
+    gx, gw, gg, gb = torch.autograd.grad(yd, [xd, blk.conv.weight, blk.normalization.weight, blk.normalization.bias], cl(gy).to(DEV, yd.dtype))
+    if dtype == torch.float32:
+        assert_close32(ncl(yd), yr, msg="fwd")
+        assert_close32(ncl(gx), gx_r, rtol=1e-4, atol=2e-5, msg="dx")
+        for a_, b_, n in ((gw, gw_r, "dw"), (gg, gg_r, "dgamma"), (gb, gb_r, "dbeta")):
+            assert_close32(a_, b_, rtol=1e-4, atol=1e-4, msg=n)
+    else:
+        assert_close16(ncl(yd), yr, msg="fwd")
+        assert_close16(ncl(gx), gx_r, msg="dx")
+        for a_, b_, n in ((gw, gw_r, "dw"), (gg, gg_r, "dgamma"), (gb, gb_r, "dbeta")):
+            assert_close16(a_, b_, msg=n)
+
+
 def test_fit_prefetches_next_batch_with_identical_results():
     """`fit` draws the next batch one iteration early and copies it under the running step (Trainer.prefetch).  The staged
     generator input must be exactly the host batch both when the step starts and when it ends (the next prefetch must not
