@@ -304,57 +304,11 @@ struct BnC8 {
   }
 };
 
-// Gradient w.r.t. the UNPADDED activation read straight from the gradient of its reflection-padded copy (the adjoint of
-// aten::reflection_pad3d folded into the consumer): 8 channels of row r = (b, x, y, z) are the sum of the padded positions
-// that mirror onto (x, y, z) — one position for interior voxels, up to 8 near the faces.  Sum in fp32 in the order of
-// reflect_pad_backward (x sources outer, z inner), rounded to the storage type once, exactly as the stand-alone pass does.
-struct PadGeom {
-  int X, Y, Z, p;
-};
-__device__ __forceinline__ int pad_sources(int i, int n, int p, int src[3]) {
-  int cnt = 0;
-  src[cnt++] = i + p;
-  if (i >= 1 && i <= p) src[cnt++] = p - i;
-  if (i <= n - 2 && i >= n - 1 - p) src[cnt++] = p + 2 * (n - 1) - i;
-  return cnt;
-}
-template <typename T>
-__device__ __forceinline__ void load_folded8(const T *__restrict__ gp, int64_t r, int C, int c0, const PadGeom &pg, float (&out)[8]) {
-  unsigned t = (unsigned)r;  // n_rows < 2^31 (checked on the host)
-  const int z = (int)(t % (unsigned)pg.Z); t /= (unsigned)pg.Z;
-  const int y = (int)(t % (unsigned)pg.Y); t /= (unsigned)pg.Y;
-  const int x = (int)(t % (unsigned)pg.X);
-  const int64_t b = (int64_t)(t / (unsigned)pg.X);
-  const int p = pg.p, Xp = pg.X + 2 * p, Yp = pg.Y + 2 * p, Zp = pg.Z + 2 * p;
-  auto edge = [p](int i, int n) { return (i >= 1 && i <= p) || (i <= n - 2 && i >= n - 1 - p); };
-  V8<T> v;
-  if (!(edge(x, pg.X) || edge(y, pg.Y) || edge(z, pg.Z))) {
-    v.load(gp + ((((b * Xp + x + p) * Yp + y + p) * Zp + z + p) * (int64_t)C + c0));
-#pragma unroll
-    for (int k = 0; k < 8; ++k) out[k] = v.v[k];
-    return;
-  }
-  int sx[3], sy[3], sz[3];
-  const int nx = pad_sources(x, pg.X, p, sx), ny = pad_sources(y, pg.Y, p, sy), nz = pad_sources(z, pg.Z, p, sz);
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  for (int a = 0; a < nx; ++a)
-    for (int bb = 0; bb < ny; ++bb)
-      for (int cc = 0; cc < nz; ++cc) {
-        v.load(gp + ((((b * Xp + sx[a]) * Yp + sy[bb]) * Zp + sz[cc]) * (int64_t)C + c0));
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
-      }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) out[k] = to_f(from_f<T>(acc[k]));
-}
-
-template <typename T, int ACT, bool PAD = false>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t n_rows, int C, int rpb,
                       const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
-                      float slope, double *sums, const PadGeom pg = PadGeom{}) {
+                      float slope, double *sums) {
   const int c0 = (threadIdx.x % (C >> 3)) * 8;
   struct { float a[8], b[8], invstd[8], nm[8]; } k8;  // only what the streaming loop needs (register budget: 2 blocks/SM)
 #pragma unroll
@@ -368,15 +322,11 @@ bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t
   constexpr int NV = (int)sizeof(T) / 2;
   col_reduce8_body<2, 4, 2 * NV>(
       n_rows, C, sums,
-      [&](int64_t r, uint4 *raw) {
-        load8raw(y + r * C + c0, raw);
-        if constexpr (!PAD) load8raw(dz + r * C + c0, raw + NV);
-      },
-      [&](int64_t r, const uint4 *raw, float (&v)[2][8]) {
+      [&](int64_t r, uint4 *raw) { load8raw(y + r * C + c0, raw); load8raw(dz + r * C + c0, raw + NV); },
+      [&](int64_t, const uint4 *raw, float (&v)[2][8]) {
         float yy[8], dd[8];
         unpack8<T>(raw, yy);
-        if constexpr (PAD) load_folded8<T>(dz, r, C, c0, pg, dd);  // dz = gradient of the reflection-padded tensor
-        else unpack8<T>(raw + NV, dd);
+        unpack8<T>(raw + NV, dd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // streams sum g and sum g*y; sum g*xhat = invstd * sum g*y - mean*invstd * sum g is applied to the totals
@@ -460,12 +410,11 @@ bn_apply_pad8_kernel(const T *__restrict__ y, T *__restrict__ zp, int X, int Y, 
   }
 }
 
-template <typename T, int ACT, bool PAD = false>
+template <typename T, int ACT>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_apply8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__restrict__ dy, int64_t total8, int C, double inv_n,
                      const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
-                     float slope, const double *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta, float acc,
-                     const PadGeom pg = PadGeom{}) {
+                     float slope, const double *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta, float acc) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (blockIdx.x == 0) {  // the parameter gradients are the reduction's totals: dbeta = sum g, dgamma = sum g * xhat
@@ -485,14 +434,8 @@ bn_bwd_apply8_kernel(const T *__restrict__ dz, const T *__restrict__ y, T *__res
     const bool two = i + stride < total8;
     V8<T> y0, d0, y1, d1;
     y0.load(y + e0);
-    if (two) y1.load(y + e1);
-    if constexpr (PAD) {  // dz = gradient of the reflection-padded tensor: fold the mirrored positions while reading
-      load_folded8<T>(dz, (int64_t)((unsigned)e0 / (unsigned)C), C, c0, pg, d0.v);  // < 2^31 elements (checked on the host)
-      if (two) load_folded8<T>(dz, (int64_t)((unsigned)e1 / (unsigned)C), C, c0, pg, d1.v);
-    } else {
-      d0.load(dz + e0);
-      if (two) d1.load(dz + e1);
-    }
+    d0.load(dz + e0);
+    if (two) { y1.load(y + e1); d1.load(dz + e1); }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float xh0 = fmaf(y0.v[k], k8.invstd[k], k8.nm[k]), xh1 = fmaf(y1.v[k], k8.invstd[k], k8.nm[k]);
@@ -887,69 +830,6 @@ int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype,
         (const __nv_bfloat16 *)dz, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)dy, total, C, inv_n, mean_invstd, gamma, beta,
         act, slope, sums, dgamma, dbeta, grad_beta);
   CG_LAUNCH_CHECK("bn_backward_apply");
-  return 0;
-}
-
-static int check_pad_geom(const char *who, int B, int X, int Y, int Z, int C, int pad, const void *a, const void *b, const void *c) {
-  if (!(B > 0 && X > 0 && Y > 0 && Z > 0 && C > 0 && pad >= 0 && pad < X && pad < Y && pad < Z)) return fail(CGAN3D_E_SHAPE, "%s: bad sizes", who);
-  if (!vec8_ok(C, a, b, c)) return fail(CGAN3D_E_UNSUPPORTED, "%s: needs C %% 8 == 0 and 16-byte aligned tensors", who);
-  if ((int64_t)B * X * Y * Z * C >= ((int64_t)1 << 31)) return fail(CGAN3D_E_UNSUPPORTED, "%s: tensor has 2^31 or more elements", who);
-  return 0;
-}
-
-int cgan3d_bn_backward_reduce_pad(const void *dz_padded, const void *y, int dtype, int B, int X, int Y, int Z, int C, int pad,
-                                  const float *mean_invstd, const float *gamma, const float *beta, int act, float slope, double *sums,
-                                  void *stream) {
-  CG_CHECK_ARG(dz_padded && y && mean_invstd && gamma && beta && sums, "bn_backward_reduce_pad: NULL pointer");
-  CG_DTYPE_OK(dtype, "bn_backward_reduce_pad");
-  int r = check_pad_geom("bn_backward_reduce_pad", B, X, Y, Z, C, pad, dz_padded, y, nullptr);
-  if (r) return r;
-  cudaStream_t st = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st);
-  if (e != cudaSuccess) return cuda_fail(e, "bn_backward_reduce_pad memset");
-  const int64_t n_rows = (int64_t)B * X * Y * Z;
-  const PadGeom pg{X, Y, Z, pad};
-  ColGrid g8 = col_grid8(n_rows, C, 2);
-  auto go = [&](auto act_tag) {
-    constexpr int A = decltype(act_tag)::value;
-    if (dtype == CGAN3D_F32)
-      bn_bwd_reduce8_kernel<float, A, true><<<g8.blocks, 256, g8.smem, st>>>((const float *)dz_padded, (const float *)y, n_rows, C,
-                                                                             g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums, pg);
-    else
-      bn_bwd_reduce8_kernel<__nv_bfloat16, A, true><<<g8.blocks, 256, g8.smem, st>>>(
-          (const __nv_bfloat16 *)dz_padded, (const __nv_bfloat16 *)y, n_rows, C, g8.rows_per_block, mean_invstd, gamma, beta, act, slope, sums, pg);
-  };
-  if (act == CGAN3D_ACT_RELU) go(std::integral_constant<int, CGAN3D_ACT_RELU>{});
-  else go(std::integral_constant<int, -1>{});
-  CG_LAUNCH_CHECK("bn_backward_reduce_pad");
-  return 0;
-}
-
-int cgan3d_bn_backward_apply_pad(const void *dz_padded, const void *y, void *dy, int dtype, int B, int X, int Y, int Z, int C, int pad,
-                                 const float *mean_invstd, const float *gamma, const float *beta, int act, float slope,
-                                 const double *sums, float *dgamma, float *dbeta, float grad_beta, void *stream) {
-  CG_CHECK_ARG(dz_padded && y && dy && mean_invstd && gamma && beta && sums, "bn_backward_apply_pad: NULL pointer");
-  CG_CHECK_ARG(grad_beta == 0.f || grad_beta == 1.f, "bn_backward_apply_pad: grad_beta must be 0 or 1");
-  CG_DTYPE_OK(dtype, "bn_backward_apply_pad");
-  int r = check_pad_geom("bn_backward_apply_pad", B, X, Y, Z, C, pad, dz_padded, y, dy);
-  if (r) return r;
-  cudaStream_t st = as_stream(stream);
-  const int64_t n_rows = (int64_t)B * X * Y * Z, t8 = n_rows * C / 8;
-  const double inv_n = 1.0 / (double)n_rows;
-  const PadGeom pg{X, Y, Z, pad};
-  auto go = [&](auto act_tag) {
-    constexpr int A = decltype(act_tag)::value;
-    if (dtype == CGAN3D_F32)
-      bn_bwd_apply8_kernel<float, A, true><<<ew_blocks(t8), 256, 0, st>>>((const float *)dz_padded, (const float *)y, (float *)dy, t8, C, inv_n,
-                                                                          mean_invstd, gamma, beta, act, slope, sums, dgamma, dbeta, grad_beta, pg);
-    else
-      bn_bwd_apply8_kernel<__nv_bfloat16, A, true><<<ew_blocks(t8), 256, 0, st>>>((const __nv_bfloat16 *)dz_padded, (const __nv_bfloat16 *)y,
-                                                                                  (__nv_bfloat16 *)dy, t8, C, inv_n, mean_invstd, gamma, beta,
-                                                                                  act, slope, sums, dgamma, dbeta, grad_beta, pg);
-  };
-  if (act == CGAN3D_ACT_RELU) go(std::integral_constant<int, CGAN3D_ACT_RELU>{});
-  else go(std::integral_constant<int, -1>{});
-  CG_LAUNCH_CHECK("bn_backward_apply_pad");
   return 0;
 }
 

@@ -390,25 +390,17 @@ class ConvBlockFn(torch.autograd.Function):
         xin, wp, y, mi, gamma, beta, bias = ctx.saved_tensors
         dt = _dt(cfg.dtype)
         dz = cast(dz.contiguous(), cfg.dtype)
+        if cfg.pad_out:
+            dz = reflect_pad_backward(dz, cfg.pad_out)  # adjoint of the consumer's padding
         Co = spec.cout
         n_rows = y.numel() // Co
-        # adjoint of the consumer's reflection padding: folded into the BatchNorm-backward reads when possible
-        fold_pad = (bool(cfg.pad_out) and gamma is not None and cfg.training and Co % 8 == 0 and y.numel() < 2 ** 31
-                    and not ctx.has_res)
-        if cfg.pad_out and not fold_pad:
-            dz = reflect_pad_backward(dz, cfg.pad_out)
         dgamma = dbeta = dbias = None
         if gamma is not None:
             if not cfg.training:
                 raise NotImplementedError("backward through eval-mode BatchNorm is not part of the hot path")
             sums = torch.empty(2 * Co, dtype=torch.float64, device=y.device)
-            pgeo = (y.shape[0], y.shape[1], y.shape[2], y.shape[3], Co, cfg.pad_out)
-            if fold_pad:
-                call("cgan3d_bn_backward_reduce_pad", _p(dz), _p(y), dt, *pgeo, _p(mi), _p(gamma), _p(beta), cfg.act, cfg.slope,
-                     _p(sums), _st())
-            else:
-                call("cgan3d_bn_backward_reduce", _p(dz), _p(y), dt, n_rows, Co, _p(mi), _p(gamma), _p(beta), cfg.act,
-                     cfg.slope, _p(sums), _st())
+            call("cgan3d_bn_backward_reduce", _p(dz), _p(y), dt, n_rows, Co, _p(mi), _p(gamma), _p(beta), cfg.act,
+                 cfg.slope, _p(sums), _st())
             dy = torch.empty_like(y)
             pbias, pgamma, pbeta = ctx.small_params
             # parameter gradients: accumulated into the gradient bucket by the same launch when a sink is active
@@ -417,12 +409,8 @@ class ConvBlockFn(torch.autograd.Function):
             if not direct:
                 tg = torch.empty(Co, dtype=torch.float32, device=y.device)
                 tb = torch.empty(Co, dtype=torch.float32, device=y.device)
-            if fold_pad:
-                call("cgan3d_bn_backward_apply_pad", _p(dz), _p(y), _p(dy), dt, *pgeo, _p(mi), _p(gamma), _p(beta), cfg.act,
-                     cfg.slope, _p(sums), _p(tg), _p(tb), 1.0 if direct else 0.0, _st())
-            else:
-                call("cgan3d_bn_backward_apply", _p(dz), _p(y), _p(dy), dt, n_rows, Co, _p(mi), _p(gamma), _p(beta),
-                     cfg.act, cfg.slope, _p(sums), _p(tg), _p(tb), 1.0 if direct else 0.0, _st())
+            call("cgan3d_bn_backward_apply", _p(dz), _p(y), _p(dy), dt, n_rows, Co, _p(mi), _p(gamma), _p(beta),
+                 cfg.act, cfg.slope, _p(sums), _p(tg), _p(tb), 1.0 if direct else 0.0, _st())
             _grad_handled(pgamma, direct)
             _grad_handled(pbeta, direct)
             dgamma, dbeta = (None, None) if direct else (tg, tb)

@@ -144,17 +144,6 @@ int cgan3d_bn_backward_apply(const void *dz, const void *y, void *dy, int dtype,
                              const float *mean_invstd, const float *gamma, const float *beta, int act,
                              float slope, const double *sums, float *dgamma, float *dbeta, float grad_beta,
                              void *stream);
-/* The two passes with the adjoint of the CONSUMER's reflection padding folded in: `dz_padded` is the gradient w.r.t.
- * reflect_pad(z, pad), [B][X+2p][Y+2p][Z+2p][C] (what the dgrad of a Conv3d(padding_mode="reflect") consumer produces,
- * reference model/generator.py:77-83); the mirrored positions are summed while reading, so aten::reflection_pad3d_backward
- * never runs as a pass of its own.  y / dy are the un-padded [B][X][Y][Z][C].  C % 8 == 0, < 2^31 elements.             */
-int cgan3d_bn_backward_reduce_pad(const void *dz_padded, const void *y, int dtype, int B, int X, int Y, int Z, int C,
-                                  int pad, const float *mean_invstd, const float *gamma, const float *beta, int act,
-                                  float slope, double *sums, void *stream);
-int cgan3d_bn_backward_apply_pad(const void *dz_padded, const void *y, void *dy, int dtype, int B, int X, int Y, int Z,
-                                 int C, int pad, const float *mean_invstd, const float *gamma, const float *beta, int act,
-                                 float slope, const double *sums, float *dgamma, float *dbeta, float grad_beta,
-                                 void *stream);
 /* bias + activation without norm (critic first layer, blocks.py:34 bias=True under Identity norm):
  * z = act(y + bias); backward: dy = dz * act'(y + bias), dbias = sum dy                     */
 int cgan3d_bias_act(const void *y, void *z, int dtype, int64_t n_rows, int C, const float *bias, int act,

@@ -489,8 +489,7 @@ def test_bn_apply_fused_with_reflect_pad(C, dtype, act):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_conv_block_with_padded_output_backward_vs_aten(dtype):
     """ConvBlock whose output carries its consumer's reflection padding (pad_out = 3, the generator's last up-sampling
-    block): forward and all gradients against ATen's conv_transpose3d -> batch_norm -> relu -> reflection_pad3d.  The
-    padding's adjoint is folded into the BatchNorm-backward kernels (cgan3d_bn_backward_*_pad)."""
+    block): forward and all gradients against ATen's conv_transpose3d -> batch_norm -> relu -> reflection_pad3d."""
     from contrast_gan_3d_b200.model.blocks import ConvBlock
     from torch import nn
 
