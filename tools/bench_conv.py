@@ -1,6 +1,7 @@
 """Micro-benchmark of the convolution kernels (BASELINE config C5 style): per-op device time with CUDA events.
 
-    python tools/bench_conv.py [--cases res,down,...] [--impls tc,generic,cudnn] [--iters 20]
+    python tools/bench_conv.py [--cases res,down,...] [--impls tc,generic,cudnn,cpu] [--iters 20]
+    python tools/bench_conv.py --sweep --impls tc,cudnn,cpu --ops gather,scatter,wgrad     # BASELINE config C5
 Prints one JSON line per (case, op, impl): TFLOP/s of algorithmic 2*MAC work and the fraction of the measured bf16 peak.
 `cudnn` is the comparison line of SURVEY §8d: aten::convolution / convolution_backward in bf16 channels_last_3d with
 cudnn.benchmark = True on the same shapes (library code, never on the product path; non-transposed cases only).
@@ -47,7 +48,23 @@ def main():
     ap.add_argument("--impls", default="tc,generic")
     ap.add_argument("--ops", default="gather,scatter,wgrad")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config C5: channels 16-256 x spatial 32^3-128^3 x stride 1/2, k = 3")
+    ap.add_argument("--cpu-gflop-cap", type=float, default=120.0, help="`cpu` line only for cases up to this many GFLOP per op (B = 1)")
     args = ap.parse_args()
+    if args.sweep:
+        # x [B, C, S, S, S], C in {16..256}, S in {32, 64, 128}, k = 3, stride in {1, 2}, C -> C channels, B = the largest
+        # power of two <= 16 that keeps the bf16 tensor <= 2 GiB
+        names = []
+        for C in (16, 32, 64, 128, 256):
+            for S in (32, 64, 128):
+                for st in (1, 2):
+                    B = 16
+                    while B > 1 and B * C * S ** 3 * 2 > 2 << 30:
+                        B //= 2
+                    name = f"c5_C{C}_S{S}_s{st}"
+                    CASES[name] = (False, C, C, 3, st, 1, 0, B, (S, S, S))
+                    names.append(name)
+        args.cases = ",".join(names)
     peak = 1396.9
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
@@ -95,8 +112,33 @@ def main():
                     print(json.dumps({"case": name, "op": opn, "impl": impl, "ms": round(ms, 4), "tflops": round(tf, 2),
                                       "frac_of_bf16_burst_peak": round(tf / peak, 4), "gflop": round(flops / 1e9, 2)}), flush=True)
                     continue
+                if impl == "cpu":
+                    # the reference's path: aten::convolution / convolution_backward on the host cores, fp32, B = 1
+                    f1 = flops / g.B
+                    if f1 / 1e9 > args.cpu_gflop_cap:
+                        print(json.dumps({"case": name, "op": opn, "impl": impl, "skipped": f"{f1 / 1e9:.0f} GFLOP at B = 1 exceeds --cpu-gflop-cap"}), flush=True)
+                        continue
+                    import time
+                    xc = big[:1].float().cpu().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+                    wc = w.float().cpu().requires_grad_(True)
+                    if tr:
+                        continue
+                    yc = torch.nn.functional.conv3d(xc, wc, stride=s, padding=p)
+                    gyc = torch.randn_like(yc)
+                    fn = {"gather": lambda: torch.nn.functional.conv3d(xc, wc, stride=s, padding=p),
+                          "scatter": lambda: torch.autograd.grad(yc, xc, gyc, retain_graph=True),
+                          "wgrad": lambda: torch.autograd.grad(yc, wc, gyc, retain_graph=True)}[opn]
+                    fn()
+                    t0 = time.perf_counter()
+                    for _ in range(2):
+                        fn()
+                    ms = (time.perf_counter() - t0) / 2 * 1e3
+                    print(json.dumps({"case": name, "op": opn, "impl": impl, "ms": round(ms, 2), "tflops": round(f1 / (ms * 1e-3) / 1e12, 4),
+                                      "gflop": round(f1 / 1e9, 2), "batch": 1, "threads": torch.get_num_threads()}), flush=True)
+                    continue
                 ii = {"tc": _lib.IMPL_TC, "generic": _lib.IMPL_GENERIC}[impl]
                 if impl == "tc" and _lib.lib().cgan3d_conv_select(ctypes.byref(g), _lib.BF16, opi) != 2:
+                    print(json.dumps({"case": name, "op": opn, "impl": impl, "unsupported": "no tcgen05 plan for this shape (CUDA-core kernel would run)"}), flush=True)
                     continue
                 fn = {"gather": lambda: ops.conv_gather(g, big, wp, impl=ii), "scatter": lambda: ops.conv_scatter(g, small, wp, impl=ii),
                       "wgrad": lambda: ops.conv_wgrad(g, big, small, impl=ii)}[opn]
@@ -113,7 +155,7 @@ def main():
                 ms = e0.elapsed_time(e1) / iters
                 tf = flops / (ms * 1e-3) / 1e12
                 print(json.dumps({"case": name, "op": opn, "impl": impl, "ms": round(ms, 4), "tflops": round(tf, 2),
-                                  "frac_of_bf16_burst_peak": round(tf / peak, 4), "gflop": round(flops / 1e9, 2)}), flush=True)
+                                  "frac_of_bf16_burst_peak": round(tf / peak, 4), "gflop": round(flops / 1e9, 2), "batch": g.B}), flush=True)
 
 
 if __name__ == "__main__":
