@@ -231,16 +231,19 @@ def _weight_grad(weight, g: ConvGeom, big, small):
                 _FWD_USES[id(weight)] = n - 1
         return conv_wgrad(g, big, small)
     main = torch.cuda.current_stream(big.device)
-    side = sink.side_stream(big.device)
+    # per-kernel timing (bench.py's instrumented pass) needs exclusive durations: keep the kernel on the compute stream then
+    side = main if _CONV_TIMING is not None else sink.side_stream(big.device)
     # the workspace comes from the COMPUTE stream's pool: under CUDA-graph capture only that stream's allocations belong to
     # the graph's private pool, and memory handed out to the side stream could be given to someone else between replays
     ws, _ = _workspace(g, _dt(big.dtype), _lib.OP_WGRAD, big.device)
-    side.wait_stream(main)  # `big` / `small` were produced on the compute stream
+    if side is not main:
+        side.wait_stream(main)  # `big` / `small` were produced on the compute stream
     with torch.cuda.stream(side):
         conv_wgrad(g, big, small, out=weight.grad, ws=ws)
-    for t in (big, small, ws):
-        if t is not None:
-            t.record_stream(side)
+    if side is not main:
+        for t in (big, small, ws):
+            if t is not None:
+                t.record_stream(side)
     left = _FWD_USES.get(id(weight), 1) - 1
     _FWD_USES[id(weight)] = max(left, 0)
     if left <= 0:
