@@ -76,6 +76,7 @@ SIGNATURES = {
     "cgan3d_adam_step_multi_dev": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     "cgan3d_rmsprop_step_multi": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp]),
     "cgan3d_crop_scale": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "cgan3d_scale_i16": (_i, [_vp, _vp, _i64, _f, _f, _vp]),
     "cgan3d_tile_extract": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "cgan3d_tile_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cgan3d_tile_finalize": (_i, [_vp, _vp, _vp, _i64, _f, _f, _vp]),

@@ -323,6 +323,27 @@ sub_resized_kernel(const float *__restrict__ x, const float *__restrict__ att, f
   }
 }
 
+// out = (hu - shift) / factor for a contiguous int16 tensor, 8 elements per thread (one 16-byte load, two 16-byte stores):
+// the device side of FactorZeroCenterScaler.__call__ (reference data/Scaler.py:41-42) for batches uploaded as raw HU
+__global__ void __launch_bounds__(256)
+scale_i16_kernel(const int16_t *__restrict__ hu, float *__restrict__ out, int64_t n, float shift, float factor) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4 *>(hu)[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] = ((float)(int16_t)(w[k] & 0xFFFFu) - shift) / factor;
+      f[2 * k + 1] = ((float)(int16_t)(w[k] >> 16) - shift) / factor;
+    }
+    reinterpret_cast<float4 *>(out)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4 *>(out)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) out[i] = ((float)hu[i] - shift) / factor;
+}
+
 static inline int ew_blocks2(int64_t n) { return (int)mx<int64_t>(1, mn<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16)); }
 
 }  // namespace cg
@@ -523,6 +544,16 @@ int cgan3d_sub_resized(const float *x, const float *att, float *out, int B, int 
   if (total == 0) return 0;
   sub_resized_kernel<<<ew_blocks2(total), 256, 0, as_stream(stream)>>>(x, att, out, B, X, Y, Z, Xa, Ya, Za);
   CG_LAUNCH_CHECK("sub_resized");
+  return 0;
+}
+
+int cgan3d_scale_i16(const int16_t *hu, float *out, int64_t n, float shift, float factor, void *stream) {
+  CG_CHECK_ARG(hu && out, "scale_i16: NULL pointer");
+  CG_CHECK_SHAPE(n >= 0 && factor != 0.f, "scale_i16: bad size / zero factor");
+  CG_CHECK_ARG(!(reinterpret_cast<uintptr_t>(hu) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15), "scale_i16: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  scale_i16_kernel<<<ew_blocks2(n >> 3 ? n >> 3 : 1), 256, 0, as_stream(stream)>>>(hu, out, n, shift, factor);
+  CG_LAUNCH_CHECK("scale_i16");
   return 0;
 }
 

@@ -77,7 +77,9 @@ class CCTAContrastCorrector:
         return out
 
     def _accumulate(self, ccta, batch_size: int):
-        if isinstance(ccta, np.ndarray):
+        if isinstance(ccta, Tensor) and not ccta.is_cuda and ccta.dtype == torch.int16 and ccta.is_pinned():
+            vol = ccta.to(self.device, non_blocking=True)  # already page-locked: no staging copy
+        elif isinstance(ccta, np.ndarray):
             if ccta.dtype != np.int16:
                 ccta = np.rint(ccta).astype(np.int16) if np.issubdtype(ccta.dtype, np.floating) else ccta.astype(np.int16)
             # stage through a cached pinned buffer: the pageable->device path of a 134 MB volume costs several times the
@@ -134,10 +136,13 @@ class CCTAContrastCorrector:
         out = torch.empty_like(acc)
         call("cgan3d_tile_finalize", acc.data_ptr(), cnt.data_ptr(), out.data_ptr(), acc.numel(), float(self.scaler.shift),
              float(self.scaler.factor), ops._st())
-        host = self._pinned("out", out.shape, out.dtype)
+        # a FRESH page-locked tensor per call (like the reference's `.cpu()` result, the caller owns it): torch's caching host
+        # allocator hands the block of an earlier, released result back without a new cudaHostAlloc, so there is no
+        # 268 MB host-side clone on the path
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
         host.copy_(out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return host.clone()
+        return host
 
     @classmethod
     def from_checkpoint(cls, inference_patch_size, device, checkpoint_path, generator_class=None, scaler=None):

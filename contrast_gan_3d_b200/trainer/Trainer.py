@@ -320,11 +320,8 @@ class Trainer:
         t = t.contiguous()
         if out is None:
             out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
-        n = t.numel()
-        inner = t.shape[-1]
-        # the tile kernel of the whole-volume corrector, applied to the batch seen as one [n / inner, 1, inner] volume
-        ops.call("cgan3d_tile_extract", t.data_ptr(), n // inner, 1, inner, 0, 0, 0, n // inner, 1, inner,
-                 float(self.hu_scaler.shift), float(getattr(self.hu_scaler, "factor", 1)), out.data_ptr(), ops._st())
+        ops.call("cgan3d_scale_i16", t.data_ptr(), out.data_ptr(), t.numel(), float(self.hu_scaler.shift),
+                 float(getattr(self.hu_scaler, "factor", 1)), ops._st())
         return out
 
     def _generate(self, subopt: Tensor):

@@ -216,6 +216,9 @@ int cgan3d_rmsprop_step_multi(int count, float *const *params, const float *cons
  * writes data = (HU - shift)/factor fp32 and mask uint8 for one patch [PX][PY][PZ].             */
 int cgan3d_crop_scale(const int16_t *vol, int X, int Y, int Z, int lbx, int lby, int lbz, int PX, int PY, int PZ,
                       float shift, float factor, float *data, uint8_t *mask, void *stream);
+/* out[i] = (hu[i] - shift) / factor for a contiguous int16 tensor (batches uploaded as raw HU and scaled on the device;
+ * FactorZeroCenterScaler.__call__, reference data/Scaler.py:41-42, bit-identical in fp32).  16-byte aligned pointers. */
+int cgan3d_scale_i16(const int16_t *hu, float *out, int64_t n, float shift, float factor, void *stream);
 /* tile extraction / stitching for whole-volume inference (eval/CCTAContrastCorrector.py:60-81) */
 int cgan3d_tile_extract(const int16_t *vol, int X, int Y, int Z, int x0, int y0, int z0, int PX, int PY, int PZ,
                         float shift, float factor, float *tile, void *stream);
