@@ -27,11 +27,14 @@ def _nvcc() -> str:
 
 
 def _digest(paths) -> str:
+    """Digest of the sources and of the flags that shape the binary.  Location-independent: the repository is checked out
+    under different roots (authoring container, GPU box), and a digest that contained the absolute -I paths made every
+    process on the GPU box rebuild the shipped library — eight ranks at once, racing on the same output file."""
     h = hashlib.sha256()
     for p in sorted(paths):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith(str(ROOT))).encode())
     return h.hexdigest()
 
 
@@ -59,6 +62,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
         return LIB
     OBJ.mkdir(exist_ok=True)
+    # one builder at a time (ranks of one job share the tree): the others wait, then find the stamp up to date
+    import fcntl
+
+    with open(OBJ / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
+            return LIB
+        return _build_locked(dig, stamp, verbose)
+
+
+def _build_locked(dig: str, stamp: Path, verbose: bool) -> Path:
     nvcc = _nvcc()
 
     def compile_one(src: str):
@@ -75,9 +89,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart"], capture_output=True, text=True)
+    tmp = LIB.with_suffix(".so.tmp")
+    r = subprocess.run([nvcc, "-shared", "-o", str(tmp), *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new library, never a partial one
     stamp.write_text(dig)
     return LIB
 
