@@ -17,6 +17,13 @@
 //     MMA per 16 voxels and per PAIR of E planes, 14 of its 16 (dx_lo, plane) blocks and 49 of 64 rows useful.
 //   * accumulator column = 16 * (plane - first plane of the window): the filter x-offset is dx = 6 - j + dx_lo.
 // Split-K over CTAs (whole (b, y-tile) columns dealt round-robin, see SegIterW2), fp32 atomics at the end.
+//
+// Z-PAIR variant (template ZP = true, the default): a K row is a PAIR of z-adjacent voxels.  The S16 box is loaded as 64-byte
+// rows (z parity, 16 channels) = 32 N elements per plane under SWIZZLE_64B, so the TMA engine handles half as many rows
+// (its cost is per row, see the producer below) and N = 8 planes x 32 = 256; the E rows are the EVEN shifts only,
+// E[l, rp][h][j] = line(h, l)[2 rp + j] — word-aligned windows of the staged line, half as many rows to build, no funnel
+// shifts.  Accumulator column = 32 * plane + 16 * parity + c holds the partial sum over one z parity of the tap
+// dz = j - parity; the epilogue adds lane (.., j) of the parity-0 columns to lane (.., j + 1) of the parity-1 columns.
 #include "common.cuh"
 #include "conv_internal.cuh"
 #include "tc_common.cuh"
@@ -32,6 +39,7 @@ constexpr int kBuildWarpsW2 = 10;  // warps 0-3 (also the epilogue) and 6-11 exp
 constexpr int kFetchWarp0W2 = 12;  // warps 12-15 fetch and stage the raw Q1 words
 constexpr int kFetchersW2 = 128;
 constexpr int kThreadsW2 = 512;
+constexpr int kMaxStagesW2 = 4;
 constexpr int kBuildersW2 = (kBuildWarpsW2 + kFetchersW2 / 32) * 32;  // threads on the named barrier shared by the build and fetch warps (see bar_sync_builders)
 
 struct ThinW2Plan {
@@ -41,11 +49,15 @@ struct ThinW2Plan {
   int P, flip;
   int Zt, Yt, nyt, L; // z rows per line (multiple of 16, >= Zs), S16 lines per step, y tiles, E lines per step (Yt + 7)
   int LW;             // staged words per Q1 line segment
-  int rows, kblocks;  // rows per S16 slot (Yt * Zt), K blocks per step
+  int rows, kblocks;  // rows per S16 slot (Yt * zr), K blocks per step
   int ring, nphys, npairs;  // logical ring size; physical slots (>= ring: the first nphys - ring slots are mirrored)
   int nb16, inv_nb16;       // 16-row blocks per line and ceil(65536 / nb16)
   uint32_t slot_bytes, e2_bytes, box_bytes, stage_words, smem_bytes;
-  int debug;  // CGAN3D_W2_DEBUG (profiling aid, results are wrong): 1 = skip the operand build, 2 = skip the MMAs, 4 = skip the plane loads
+  int zp;     // z-pair variant: K rows are pairs of voxels (zr = Zt / 2 rows per line), else single voxels (zr = Zt)
+  int zr;
+  int nst;     // stages of the expanded operand (2..4)
+  int cfence;  // 1: the MMA-issuing thread runs the generic->async proxy fence after its wait (DESIGN fact 12), 0: every builder before its arrive
+  int debug;  // CGAN3D_W2_DEBUG (profiling aid, results are wrong): 1 = skip the operand build, 2 = skip the MMAs, 4 = skip the plane loads, 8 = skip the Q1 loads
 };
 
 // Work = ncols columns (b, y-tile) x npairs plane pairs.  Columns are dealt to the CTAs ROUND-ROBIN (CTA c takes columns
@@ -95,28 +107,72 @@ struct SegIterW2 {
   }
 };
 
-__device__ __forceinline__ void bar_sync_builders() { static_assert(kBuildersW2 == 448, "barrier count"); asm volatile("bar.sync 1, 448;" ::: "memory"); }
+// Hand-off of the two staging buffers between the fetch warps (producers) and the build warps (consumers): named barriers
+// 1 + buf ("full": 128 fetch threads arrive, 320 builders wait) and 3 + buf ("empty": the builders arrive, the fetchers wait).
+__device__ __forceinline__ void bar_sync_id(uint32_t id) { static_assert(kBuildersW2 == 448, "barrier count"); asm volatile("bar.sync %0, 448;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive_id(uint32_t id) { asm volatile("bar.arrive %0, 448;" ::"r"(id) : "memory"); }
 
+// The fetch warps walk this CTA's steps in order: (column, plane pair) advanced incrementally (SegIterW2::locate divides).
+struct StepWalkW2 {
+  int n, rounds, r, pair, col;
+  long long rem_col0;
+  __device__ __forceinline__ StepWalkW2(const SegIterW2 &it) : n(it.n), rounds(it.rounds), r(0), pair(0), rem_col0(it.rem_col0) {
+    if (rounds > 0) {
+      col = (int)blockIdx.x;
+    } else {
+      const long long c = it.idx / n;
+      col = (int)(rem_col0 + c);
+      pair = (int)(it.idx - c * n);
+    }
+    first_flat_col = (int)(rem_col0 + it.idx / n);
+    first_flat_pair = (int)(it.idx % n);
+  }
+  int first_flat_col, first_flat_pair;
+  __device__ __forceinline__ void advance() {
+    if (++pair < n) return;
+    pair = 0;
+    if (r < rounds) {
+      ++r;
+      if (r < rounds) { col += (int)gridDim.x; return; }
+      col = first_flat_col;
+      pair = first_flat_pair;
+      return;
+    }
+    ++col;
+  }
+};
+
+// CGAN3D_W2_DEBUG bit 16: CTA 0 prints where each role's leading thread spends its cycles (waits vs work).
+struct ProfW2 {
+  long long t0, acc[6];
+  bool on;
+  __device__ __forceinline__ ProfW2(bool on_) : on(on_) { for (int i = 0; i < 6; ++i) acc[i] = 0; t0 = on ? clock64() : 0; }
+  __device__ __forceinline__ void lap(int i) { if (on) { const long long t = clock64(); acc[i] += t - t0; t0 = t; } }
+};
+
+template <bool ZP>
 __global__ void __launch_bounds__(kThreadsW2, 1)
 wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__restrict__ q1, float *__restrict__ dw,
                  const __grid_constant__ ThinW2Plan p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // nphys S16 plane slots, [rows][16 ch], SWIZZLE_32B (TMA)
   uint8_t *e2 = ring + (size_t)p.nphys * p.slot_bytes;          // 2 stages of the expanded operand, [L * Zt rows][2][8], SWIZZLE_32B
-  uint32_t *stage = reinterpret_cast<uint32_t *>(e2 + 2 * (size_t)p.e2_bytes);  // raw Q1 line segments [2][L][LW]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stage + p.stage_words);
-  uint64_t *s_full = bars, *s_empty = bars + kMaxRingW2, *e_full = s_empty + kMaxRingW2, *e_empty = e_full + 2, *done = e_empty + 2;
+  uint32_t *stage = reinterpret_cast<uint32_t *>(e2 + (size_t)p.nst * p.e2_bytes);  // 2 buffers of raw Q1 line segments [2][L][LW]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 2 * p.stage_words);
+  uint64_t *s_full = bars, *s_empty = bars + kMaxRingW2, *e_full = s_empty + kMaxRingW2, *e_empty = e_full + kMaxStagesW2, *done = e_empty + kMaxStagesW2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = ZP ? 256 : 128;  // accumulator columns: 8 planes x (32 | 16)
+  constexpr uint32_t kNper = ZP ? 32 : 16;    // N elements per plane
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxRingW2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&e_full[i], kBuildWarpsW2); tc::mbar_init(&e_empty[i], 1); }
+    for (int i = 0; i < kMaxStagesW2; ++i) { tc::mbar_init(&e_full[i], kBuildWarpsW2); tc::mbar_init(&e_empty[i], 1); }
     tc::mbar_init(done, 1);
     tc::fence_barrier_init();
   }
   if (warp == 5) {
-    tc::tmem_alloc(tmem_ptr, 128);
+    tc::tmem_alloc(tmem_ptr, kCols);
     tc::tmem_relinquish();
   }
   tc::tc_fence_before();
@@ -124,7 +180,7 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (warp < 4) {  // every MMA accumulates: start from zero
-    for (int c0 = 0; c0 < 128; c0 += 16) tc::tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0);
+    for (int c0 = 0; c0 < (int)kCols; c0 += 16) tc::tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0);
     tc::tmem_st_wait();
   }
   tc::tc_fence_before();
@@ -142,16 +198,26 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
     // planes and then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmS);
-      uint32_t q = 0;
+      // plane q of this CTA goes to slot q % ring on its (q / ring)-th use: both kept incrementally (a runtime division costs
+      // this single thread ~100 cycles, and there were four per step)
+      uint32_t slot = 0, use = 0;
+      const uint32_t mirrored = (uint32_t)(p.nphys - p.ring);
+      uint8_t *slot_ptr = ring;
+      ProfW2 prof((p.debug & 16) && blockIdx.x == 0);
       auto load_plane = [&](int xs, int b, int y0) {
-        const uint32_t slot = q % (uint32_t)p.ring, use = q / (uint32_t)p.ring;
+        prof.lap(0);
         if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
-        if (p.debug & 4) { tc::mbar_arrive(&s_full[slot]); ++q; return; }  // profiling aid: no plane loads at all
-        const bool mirror = (int)slot + p.ring < p.nphys;
-        tc::mbar_expect_tx(&s_full[slot], mirror ? 2 * p.box_bytes : p.box_bytes);
-        tc::tma_load_5d(ring + (size_t)slot * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
-        if (mirror) tc::tma_load_5d(ring + (size_t)(slot + p.ring) * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
-        ++q;
+        prof.lap(1);
+        if (p.debug & 4) {  // profiling aid: no plane loads at all
+          tc::mbar_arrive(&s_full[slot]);
+        } else {
+          const bool mirror = slot < mirrored;
+          tc::mbar_expect_tx(&s_full[slot], mirror ? 2 * p.box_bytes : p.box_bytes);
+          tc::tma_load_5d(slot_ptr, &tmS, &s_full[slot], 0, 0, y0, xs, b);
+          if (mirror) tc::tma_load_5d(slot_ptr + (size_t)p.ring * p.slot_bytes, &tmS, &s_full[slot], 0, 0, y0, xs, b);
+        }
+        slot_ptr += p.slot_bytes;
+        if (++slot == (uint32_t)p.ring) { slot = 0; ++use; slot_ptr = ring; }
       };
       int col, p0, plen;
       for (SegIterW2 it(ncols, p.npairs); it.next(col, p0, plen);) {
@@ -162,71 +228,92 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
           load_plane(2 * (p0 + i) + 1, b, y0);
         }
       }
+      prof.lap(0);
+      if (prof.on) printf("w2 prof TMA : work %lld  wait s_empty %lld\n", prof.acc[0], prof.acc[1]);
     }
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer
     const bool leader = tc::elect_one();
     // A: MN-major SWIZZLE_32B, 16 M elements per 32-byte row, further M blocks one slab line later (LBO), 8-row K groups 256 B
-    const uint64_t a_hi = tc::make_desc_sw_mn(0, (uint32_t)p.Zt * 32u, 256, 32);
-    // B: MN-major SWIZZLE_32B, one 16-channel N block per ring slot (LBO = slot stride)
-    const uint64_t b_hi = tc::make_desc_sw_mn(0, p.slot_bytes, 256, 32);
+    const uint64_t a_hi = tc::make_desc_sw_mn(0, (uint32_t)p.zr * 32u, 256, 32);
+    // B: MN-major, one N block per ring slot (LBO = slot stride): SWIZZLE_32B rows of 16 channels, or SWIZZLE_64B rows of
+    // (z parity, 16 channels)
+    const uint64_t b_hi = ZP ? tc::make_desc_sw_mn(0, p.slot_bytes, 512, 64) : tc::make_desc_sw_mn(0, p.slot_bytes, 256, 32);
     const uint32_t ring_u32 = tc::smem_u32(ring), e2_u32 = tc::smem_u32(e2);
-    uint32_t waited = 0, n = 0, w0 = 0;  // planes waited for / steps issued / sequence number of the window's first plane
+    // planes waited for / steps issued / sequence number of the window's first plane; ws, wph = waited % ring and the parity
+    // of waited / ring, w0s = w0 % ring (all incremental: no runtime divisions on this warp's critical path)
+    uint32_t waited = 0, w0 = 0, ws = 0, wph = 0, w0s = 0, st = 0, eph = 0;  // st, eph: operand stage of the step and its parity
+    const uint32_t ringn = (uint32_t)p.ring;
+    ProfW2 prof((p.debug & 16) && blockIdx.x == 0 && lane == 0);
     int col, p0, plen;
     for (SegIterW2 it(ncols, p.npairs); it.next(col, p0, plen);) {
       w0 = waited;  // the segment's first window starts at its first warm-up plane
-      for (int i = 0; i < plen; ++i, ++n, w0 += 2) {
+      w0s = ws;
+      prof.lap(0);
+      for (int i = 0; i < plen; ++i, w0 += 2) {
         while (waited < w0 + 8) {
-          tc::mbar_wait(&s_full[waited % (uint32_t)p.ring], (waited / (uint32_t)p.ring) & 1);
+          tc::mbar_wait(&s_full[ws], wph);
           ++waited;
+          if (++ws == ringn) { ws = 0; wph ^= 1u; }
         }
-        const uint32_t st = n & 1;
-        tc::mbar_wait(&e_full[st], (n >> 1) & 1);
+        prof.lap(1);
+        tc::mbar_wait(&e_full[st], eph);
+        prof.lap(2);
+        if (p.cfence) tc::fence_proxy_async();  // the builders' plain stores -> visible to the MMAs issued below
         tc::tc_fence_after();
         const uint32_t a0 = (e2_u32 + st * p.e2_bytes) >> 4;
         uint32_t j = 0;
         while (j < 8) {  // runs of window planes that are contiguous in the (mirrored) ring
-          const uint32_t slot = (w0 + j) % (uint32_t)p.ring;
+          uint32_t slot = w0s + j;
+          if (slot >= ringn) slot -= ringn;
           const uint32_t run = mn<uint32_t>(8 - j, (uint32_t)p.nphys - slot);
-          const uint32_t idesc = tc::make_idesc_bf16(128, (int)(16 * run), 1, 1);
+          const uint32_t idesc = tc::make_idesc_bf16(128, (int)(kNper * run), 1, 1);
           const uint32_t b0 = (ring_u32 + slot * p.slot_bytes) >> 4;
-          const uint32_t d = tmem_base + 16 * j;
+          const uint32_t d = tmem_base + kNper * j;
           if (leader && !(p.debug & 2)) {
             uint64_t a_desc = a_hi | (uint64_t)(a0 & 0x3FFF), b_desc = b_hi | (uint64_t)(b0 & 0x3FFF);
 #pragma unroll 4
             for (int kb = 0; kb < p.kblocks; ++kb) {
               tc::umma_bf16(d, a_desc, b_desc, idesc, 1u);
               a_desc += 32;  // 16 rows of 32 B
-              b_desc += 32;
+              b_desc += ZP ? 64 : 32;
             }
           }
           __syncwarp();
           j += run;
         }
+        prof.lap(3);
         if (leader) {
           tc::umma_commit(&e_empty[st]);
-          tc::umma_commit(&s_empty[w0 % (uint32_t)p.ring]);        // the two oldest planes leave the window
-          tc::umma_commit(&s_empty[(w0 + 1) % (uint32_t)p.ring]);
+          tc::umma_commit(&s_empty[w0s]);  // the two oldest planes leave the window (w0s is even, so is the ring)
+          tc::umma_commit(&s_empty[w0s + 1]);
         }
         __syncwarp();
+        w0s += 2;
+        if (w0s >= ringn) w0s -= ringn;
+        if (++st == (uint32_t)p.nst) { st = 0; eph ^= 1u; }
+        prof.lap(4);
       }
       // the six planes still resident belong to this segment only
       if (leader)
-        for (uint32_t k = 0; k < 6; ++k) tc::umma_commit(&s_empty[(w0 + k) % (uint32_t)p.ring]);
+        for (uint32_t k = 0; k < 6; ++k) tc::umma_commit(&s_empty[w0s + k >= ringn ? w0s + k - ringn : w0s + k]);
       __syncwarp();
     }
     if (leader) tc::umma_commit(done);
     __syncwarp();
+    if (prof.on)
+      printf("w2 prof MMA : other %lld  wait s_full %lld  wait e_full %lld  issue %lld  commit %lld (leader %d)\n", prof.acc[0], prof.acc[1],
+             prof.acc[2], prof.acc[3], prof.acc[4], (int)leader);
   } else {
     // ------------------------------------------------ warps 0..3, 6..11: build the expanded operand (0..3 then run the
     // epilogue); warps 12..15: fetch the raw Q1 words two steps ahead and stage them in shared memory.  The roles are split
     // because the generic->async proxy fence that publishes the operand compiles to MEMBAR.ALL.CTA, which waits for every
     // outstanding global load of the executing thread: a warp that prefetches AND builds exposes the full load latency
-    // (~1 us under load) in every step.
+    // (~1 us under load) in every step.  The staging area is double-buffered and handed over with arrive / wait named
+    // barriers, so the fetch warps' instruction chain (~150 dependent instructions per step) runs beside the build instead
+    // of in series with it (measured with everything else disabled: 0.36 ms of the first form's 0.55 ms was this chain).
     const int ZqW = p.Zq >> 1;
-    // this CTA's steps are the flat (column, plane pair) indices [idx0, idx0 + total)
     const SegIterW2 range(ncols, p.npairs);
-    const long long idx0 = range.idx;
     const uint32_t total = (uint32_t)range.steps();
     uint32_t n = 0;
     if (warp >= kFetchWarp0W2) {
@@ -245,89 +332,122 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
           if ((unsigned)wq < (unsigned)ZqW) { meta[i] = l | (h << 8); rel[i] = (h * p.Yq + l) * ZqW + w; }
         }
       }
-      auto fetch = [&](uint32_t k, uint32_t (&pref)[kMaxPrefW2]) {  // raw Q1 words of this CTA's step k -> registers
-        int col, pair;
-        range.locate(k, idx0, col, pair);
-        const int b = col / p.nyt, y0 = (col - b * p.nyt) * p.Yt;
-        const int xb = 2 * pair - p.P, yb = y0 - p.P;
+      ProfW2 prof((p.debug & 16) && blockIdx.x == 0 && tid == 0);
+      StepWalkW2 walk(range);
+      int cur_col = -1, yb = 0;
+      const uint32_t *col_base = q1;  // Q1 word (b, x = 0, y = yb, z = -P) of the current column
+      const long long plane_words = (long long)p.Yq * ZqW;
+      auto fetch = [&](uint32_t (&pref)[kMaxPrefW2]) {  // raw Q1 words of this CTA's next step -> registers
+        if (walk.col != cur_col) {
+          cur_col = walk.col;
+          const int b = cur_col / p.nyt, y0 = (cur_col - b * p.nyt) * p.Yt;
+          yb = y0 - p.P;
+          col_base = q1 + ((long long)b * p.Xq * p.Yq + yb) * ZqW - p.P / 2;
+        }
+        const int xb = 2 * walk.pair - p.P;
+        walk.advance();
         // base may point outside the tensor (halo): it is only dereferenced for in-range (plane, line)
-        const uint32_t *base = q1 + ((long long)b * p.Xq * p.Yq + (long long)xb * p.Yq + yb) * ZqW - p.P / 2;
+        const uint32_t *base = col_base + (long long)xb * plane_words;
         const bool hv0 = (unsigned)xb < (unsigned)p.Xq, hv1 = (unsigned)(xb + 1) < (unsigned)p.Xq;
 #pragma unroll
         for (int i = 0; i < kMaxPrefW2; ++i) {
           uint32_t v = 0;
           if (meta[i] >= 0) {
             const bool hv = (meta[i] >> 8) ? hv1 : hv0;
-            if (hv && (unsigned)(yb + (meta[i] & 0xFF)) < (unsigned)p.Yq) v = __ldg(base + rel[i]);
+            if (hv && (unsigned)(yb + (meta[i] & 0xFF)) < (unsigned)p.Yq && !(p.debug & 8)) v = __ldg(base + rel[i]);
           }
           pref[i] = v;
         }
       };
       auto put = [&](uint32_t k, uint32_t (&pref)[kMaxPrefW2]) {
-        bar_sync_builders();  // the builders have finished reading the previous step's staging area
+        const uint32_t sb = k & 1;
+        prof.lap(0);
+        if (k >= 2) bar_sync_id(3 + sb);  // the builders have finished reading step k - 2 from this buffer
+        prof.lap(1);
+        uint32_t *dst = stage + sb * p.stage_words;
 #pragma unroll
         for (int i = 0; i < kMaxPrefW2; ++i)
-          if (tid + kFetchersW2 * i < total_words) stage[tid + kFetchersW2 * i] = pref[i];
-        bar_sync_builders();
-        if (k + 2 < total) fetch(k + 2, pref);
+          if (tid + kFetchersW2 * i < total_words) dst[tid + kFetchersW2 * i] = pref[i];
+        prof.lap(2);
+        bar_arrive_id(1 + sb);
+        if (k + 2 < total) fetch(pref);
       };
       uint32_t prefA[kMaxPrefW2], prefB[kMaxPrefW2];
-      if (total > 0) fetch(0, prefA);
-      if (total > 1) fetch(1, prefB);
+      if (total > 0) fetch(prefA);
+      if (total > 1) fetch(prefB);
       while (n < total) {
         put(n, prefA);
         if (++n >= total) break;
         put(n, prefB);
         ++n;
       }
+      prof.lap(0);
+      if (prof.on) printf("w2 prof FETCH: fetch+issue %lld  wait empty %lld  sts(+load latency) %lld  steps %u\n", prof.acc[0], prof.acc[1], prof.acc[2], total);
     } else {
       const int bw = warp < 4 ? warp : warp - 2;  // builder warp 0..9
       // E2[l * Zt + r][h][j] = line(h, l)[r + j], j = 0..7.  A warp iteration = 32 rows of one staged line (h, l): 5
       // conflict-free LDS (neighbouring lanes read overlapping words), one funnel shift per output word (odd rows start
       // in the upper half-word), one 16-byte STS (SWIZZLE_32B makes the 8 rows of a quarter-warp hit 8 different 16-byte
       // bank groups).  The 2 L ipl iterations of a step are dealt to the 6 builder warps as contiguous ranges.
-      const int ipl = (p.Zt + 31) >> 5, iters = 2 * p.L * ipl, per = (iters + kBuildWarpsW2 - 1) / kBuildWarpsW2;
+      // Z-pair variant: E2[l * zr + rp][h][j] = line(h, l)[2 rp + j] = staged words rp .. rp + 3: four conflict-free LDS,
+      // no shifts, 32 rows of a line per warp iteration cover 32 words.
+      const int ipl = (p.zr + 31) >> 5, iters = 2 * p.L * ipl, per = (iters + kBuildWarpsW2 - 1) / kBuildWarpsW2;
       const int it0 = bw * per, it1 = mn(iters, it0 + per);
       const int hl0 = it0 / ipl, rb0 = it0 - hl0 * ipl;
-      const uint32_t stage_u32 = tc::smem_u32(stage) + (uint32_t)(lane >> 1) * 4u;
+      const uint32_t stage_u32 = tc::smem_u32(stage) + (uint32_t)(ZP ? lane : (lane >> 1)) * 4u, stage_stride = p.stage_words * 4u;
       const uint32_t lane_dst = (uint32_t)lane * 32u;
       const uint32_t swz = (uint32_t)((lane >> 2) & 1);  // rows advance by 32 per iteration: the swizzle phase is the lane's
       const uint32_t sh = (uint32_t)(lane & 1) << 4;
+      uint32_t st = 0, use = 0;  // operand stage of step n and how often it has been used before
+      ProfW2 prof((p.debug & 16) && blockIdx.x == 0 && threadIdx.x == 0);
       for (; n < total; ++n) {
-        bar_sync_builders();
-        bar_sync_builders();  // the fetch warps have written this step's staging area
-        const uint32_t st = n & 1;
-        if (n >= 2) tc::mbar_wait(&e_empty[st], ((n >> 1) - 1) & 1);
+        const uint32_t sb = n & 1;
+        prof.lap(0);
+        bar_sync_id(1 + sb);  // the fetch warps have written this step's staging buffer
+        prof.lap(1);
+        if (use > 0) tc::mbar_wait(&e_empty[st], (use - 1) & 1);
+        prof.lap(2);
         if (!(p.debug & 1)) {
           const uint32_t dst_u32 = tc::smem_u32(e2) + st * p.e2_bytes + lane_dst;
           int it = it0, hl = hl0, rb = rb0;
           while (it < it1) {
             const int h = hl >= p.L ? 1 : 0, l = hl - h * p.L;
-            uint32_t src = stage_u32 + (uint32_t)(hl * p.LW + rb * 16) * 4u;
-            uint32_t d = dst_u32 + (uint32_t)(l * p.Zt + rb * 32) * 32u + (((uint32_t)h ^ swz) << 4);
+            uint32_t src = stage_u32 + sb * stage_stride + (uint32_t)(hl * p.LW + rb * (ZP ? 32 : 16)) * 4u;
+            uint32_t d = dst_u32 + (uint32_t)(l * p.zr + rb * 32) * 32u + (((uint32_t)h ^ swz) << 4);
             int r = rb * 32 + lane;
 #pragma unroll 2
-            for (; rb < ipl && it < it1; ++rb, ++it, src += 64, d += 1024, r += 32) {
-              if (r < p.Zt) {
+            for (; rb < ipl && it < it1; ++rb, ++it, src += (ZP ? 128 : 64), d += 1024, r += 32) {
+              if (r < p.zr) {
                 uint32_t a0, a1, a2, a3, a4;
                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a0) : "r"(src));
                 asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(a1) : "r"(src));
                 asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(a2) : "r"(src));
                 asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(a3) : "r"(src));
-                asm volatile("ld.shared.b32 %0, [%1+16];" : "=r"(a4) : "r"(src));
-                const uint32_t o0 = __funnelshift_r(a0, a1, sh), o1 = __funnelshift_r(a1, a2, sh), o2 = __funnelshift_r(a2, a3, sh),
-                               o3 = __funnelshift_r(a3, a4, sh);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                if (ZP) {
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+                } else {
+                  asm volatile("ld.shared.b32 %0, [%1+16];" : "=r"(a4) : "r"(src));
+                  const uint32_t o0 = __funnelshift_r(a0, a1, sh), o1 = __funnelshift_r(a1, a2, sh), o2 = __funnelshift_r(a2, a3, sh),
+                                 o3 = __funnelshift_r(a3, a4, sh);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                }
               }
             }
             rb = 0;
             ++hl;
           }
         }
-        tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        prof.lap(3);
+        if (n + 2 < total) bar_arrive_id(3 + sb);  // this warp has read the staging buffer: the fetch warps may refill it
+        if (!p.cfence) tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&e_full[st]);
+        if (++st == (uint32_t)p.nst) { st = 0; ++use; }
+        prof.lap(4);
       }
+      if (prof.on)
+        printf("w2 prof BUILD: other %lld  wait full %lld  wait e_empty %lld  build %lld  fence+arrive %lld\n", prof.acc[0], prof.acc[1],
+               prof.acc[2], prof.acc[3], prof.acc[4]);
     }
     // epilogue: TMEM lane m = (dy = m >> 4, dx_lo = (m >> 3) & 1, dz = m & 7); column = 16 * j + c, dx = 6 - j + dx_lo
     if (n > 0 && warp < 4) {
@@ -336,8 +456,18 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
       const int m = warp * 32 + lane, dy = m >> 4, dxl = (m >> 3) & 1, dz = m & 7;
       for (int j = 0; j < 8; ++j) {
         uint32_t v[16];
-        tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(16 * j), v);
-        tc::tmem_ld_wait();
+        tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + kNper * (uint32_t)j, v);
+        if (ZP) {
+          // columns 16..31 of the plane: the odd-z partial sums, tap dz = (lane's j) - 1: take them from lane + 1
+          uint32_t v1[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + kNper * (uint32_t)j + 16u, v1);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            v[c] = __float_as_uint(__uint_as_float(v[c]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1));
+        } else {
+          tc::tmem_ld_wait();
+        }
         const int dx = 6 - j + dxl;
         if (dy < 7 && dz < 7 && dx >= 0 && dx < 7) {
           int tap = dx * 49 + dy * 7 + dz;
@@ -350,7 +480,7 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, 128);
+  if (warp == 5) tc::tmem_dealloc(tmem_base, kCols);
 }
 
 // ---------------------------------------------------------------- host side
@@ -379,13 +509,24 @@ static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
   p.LW = (p.Zt + 8) / 2 + 1;
   p.nb16 = p.Zt / 16;
   p.inv_nb16 = (65536 + p.nb16 - 1) / p.nb16;
+  static int v2_single = -1;  // CGAN3D_WGRAD7_V2_SINGLE: one voxel per K row (the first form of this kernel), for A/B timing
+  if (v2_single < 0) v2_single = getenv("CGAN3D_WGRAD7_V2_SINGLE") ? 1 : 0;
+  p.zp = (v2_single || (p.Zs & 1)) ? 0 : 1;
+  p.zr = p.zp ? p.Zt / 2 : p.Zt;
+  p.nst = 2;
+  if (const char *e = getenv("CGAN3D_W2_STAGES")) p.nst = mx(2, mn(kMaxStagesW2, atoi(e)));
+  p.cfence = 0;
+  if (const char *e = getenv("CGAN3D_W2_CFENCE")) p.cfence = atoi(e) ? 1 : 0;
+  // pass 0 only takes a tile whose ring is the deep one (14 logical slots, >= 4 mirrored); pass 1 takes what fits
+  for (int pass = p.zp ? 0 : 1; pass < 2 && p.Yt == 0; ++pass)
   for (int Yt = mn(p.Ys, 8); Yt >= 1; --Yt) {
     const int L = Yt + 7;
     if (2 * L * p.LW > kFetchersW2 * kMaxPrefW2) continue;
+    if ((Yt * p.zr) % 16) continue;  // whole K blocks of 16 rows
     const uint32_t slot = (uint32_t)Yt * p.Zt * 32u;
-    const uint32_t e2b = ((uint32_t)L * p.Zt * 32u + 1023u) / 1024u * 1024u;
+    const uint32_t e2b = ((uint32_t)L * p.zr * 32u + 1023u) / 1024u * 1024u;
     const uint32_t stage_words = ((uint32_t)(2 * L * p.LW) + 3u) & ~3u;
-    const uint32_t fixed = 2 * e2b + stage_words * 4 + 512;
+    const uint32_t fixed = (uint32_t)p.nst * e2b + 2 * stage_words * 4 + 512;
     if (slot % 1024) continue;
     int nphys = (int)((kSmemLimitW2 - mn(kSmemLimitW2, fixed)) / slot);
     if (nphys > kMaxRingW2 + 6) nphys = kMaxRingW2 + 6;
@@ -394,6 +535,7 @@ static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
     const int ring = nphys >= kMaxRingW2 + 4 ? kMaxRingW2 : 12;
     if (nphys < ring + 2 && Yt > 1) continue;
     if (nphys < ring) continue;
+    if (pass == 0 && ring != kMaxRingW2) continue;
     if (nphys > ring + 6) nphys = ring + 6;  // windows start at even slots <= ring - 2: six mirrors make every window contiguous
     if (const char *e = getenv("CGAN3D_W2_NPHYS")) nphys = mx(ring, mn(nphys, atoi(e)));  // experiment: fewer mirrored slots
     p.Yt = Yt; p.L = L; p.nphys = nphys; p.ring = ring;
@@ -403,7 +545,7 @@ static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
   }
   if (p.Yt == 0) return false;
   p.nyt = (p.Ys + p.Yt - 1) / p.Yt;
-  p.rows = p.Yt * p.Zt;
+  p.rows = p.Yt * p.zr;
   p.kblocks = p.rows / 16;
   p.box_bytes = p.slot_bytes;
   return true;
@@ -430,23 +572,31 @@ int thin_w2_run(const cgan3d_conv_geom &g, const void *big, const void *small, f
   if (!enc) return fail(CGAN3D_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
   CUtensorMap tmS;
   {
-    const cuuint64_t gdim[5] = {16, (cuuint64_t)p.Zs, (cuuint64_t)p.Ys, (cuuint64_t)p.Xs, (cuuint64_t)p.B};
-    const cuuint64_t gstr[4] = {32, (cuuint64_t)p.Zs * 32, (cuuint64_t)p.Ys * p.Zs * 32, (cuuint64_t)p.Xs * p.Ys * p.Zs * 32};
-    const cuuint32_t box[5] = {16, (cuuint32_t)p.Zt, (cuuint32_t)p.Yt, 1, 1};
+    // rows of one voxel (16 channels, 32 B) or of a z-adjacent voxel pair (64 B)
+    const cuuint64_t vox = p.zp ? 2 : 1;
+    const cuuint64_t gdim[5] = {16 * vox, (cuuint64_t)p.Zs / vox, (cuuint64_t)p.Ys, (cuuint64_t)p.Xs, (cuuint64_t)p.B};
+    const cuuint64_t gstr[4] = {32 * vox, (cuuint64_t)p.Zs * 32, (cuuint64_t)p.Ys * p.Zs * 32, (cuuint64_t)p.Xs * p.Ys * p.Zs * 32};
+    const cuuint32_t box[5] = {(cuuint32_t)(16 * vox), (cuuint32_t)p.zr, (cuuint32_t)p.Yt, 1, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(s16), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, tc_l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, p.zp ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, tc_l2_promo(),
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CGAN3D_E_SHAPE, "cuTensorMapEncodeTiled (thin wgrad v2) failed with %d", (int)r);
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad7_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitW2 + 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad7_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitW2 + 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad7_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitW2 + 1024);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(wgrad7_v2_kernel)");
     attr_set = true;
   }
   const long long total = (long long)p.B * p.nyt * p.npairs;
   const int grid = (int)mn<long long>(total, (long long)num_sms());
-  wgrad7_v2_kernel<<<grid, kThreadsW2, p.smem_bytes + 1024, st>>>(tmS, reinterpret_cast<const uint32_t *>(q1), dw, p);
+  if (p.zp)
+    wgrad7_v2_kernel<true><<<grid, kThreadsW2, p.smem_bytes + 1024, st>>>(tmS, reinterpret_cast<const uint32_t *>(q1), dw, p);
+  else
+    wgrad7_v2_kernel<false><<<grid, kThreadsW2, p.smem_bytes + 1024, st>>>(tmS, reinterpret_cast<const uint32_t *>(q1), dw, p);
   CG_LAUNCH_CHECK("wgrad7_v2_kernel");
   return 0;
 }
