@@ -33,13 +33,15 @@ namespace cg {
 
 using bf16 = __nv_bfloat16;
 constexpr uint32_t kSmemLimitW2 = 232448 - 1024;
-constexpr int kMaxRingW2 = 14;  // logical S16 plane slots: 8 live + 4 or 6 in flight (TMA runs 2 - 3 steps ahead of the MMAs)
+constexpr int kMaxRingW2 = 14;  // default logical S16 plane slots: 8 live + 4 or 6 in flight (TMA runs 2 - 3 steps ahead of the MMAs)
+constexpr int kRingCapW2 = 20;  // barrier slots (CGAN3D_W2_RING experiments: deeper ring, fewer mirrors)
 constexpr int kMaxPrefW2 = 11;     // staged 32-bit words per fetch thread and step
 constexpr int kBuildWarpsW2 = 10;  // warps 0-3 (also the epilogue) and 6-11 expand the operand
 constexpr int kFetchWarp0W2 = 12;  // warps 12-15 fetch and stage the raw Q1 words
 constexpr int kFetchersW2 = 128;
 constexpr int kThreadsW2 = 512;
 constexpr int kMaxStagesW2 = 4;
+constexpr int kMaxStageBufsW2 = 4;  // raw-line staging buffers (named barriers 1.. = full, 1 + kMaxStageBufsW2.. = empty)
 constexpr int kBuildersW2 = (kBuildWarpsW2 + kFetchersW2 / 32) * 32;  // threads on the named barrier shared by the build and fetch warps (see bar_sync_builders)
 
 struct ThinW2Plan {
@@ -56,6 +58,7 @@ struct ThinW2Plan {
   int zp;     // z-pair variant: K rows are pairs of voxels (zr = Zt / 2 rows per line), else single voxels (zr = Zt)
   int zr;
   int nst;     // stages of the expanded operand (2..4)
+  int nsb;     // raw-line staging buffers (2..4): the fetch warps run nsb - 1 steps ahead of the builders
   int cfence;  // 1: the MMA-issuing thread runs the generic->async proxy fence after its wait (DESIGN fact 12), 0: every builder before its arrive
   int debug;  // CGAN3D_W2_DEBUG (profiling aid, results are wrong): 1 = skip the operand build, 2 = skip the MMAs, 4 = skip the plane loads, 8 = skip the Q1 loads
 };
@@ -142,13 +145,26 @@ struct StepWalkW2 {
   }
 };
 
-// CGAN3D_W2_DEBUG bit 16: CTA 0 prints where each role's leading thread spends its cycles (waits vs work).
+// Built with -DCGAN3D_W2_PROF: CGAN3D_W2_DEBUG bit 16 makes CTA 0 print where each role's leading thread spends its cycles
+// (waits vs work; a named-barrier wait is charged to the NEXT lap because BAR.SYNC blocks at its first dependent
+// instruction).  Compiled out by default (the printf costs registers and stack).
+#ifdef CGAN3D_W2_PROF
 struct ProfW2 {
   long long t0, acc[6];
   bool on;
   __device__ __forceinline__ ProfW2(bool on_) : on(on_) { for (int i = 0; i < 6; ++i) acc[i] = 0; t0 = on ? clock64() : 0; }
   __device__ __forceinline__ void lap(int i) { if (on) { const long long t = clock64(); acc[i] += t - t0; t0 = t; } }
 };
+#define W2_PROF_PRINT(...) printf(__VA_ARGS__)
+#else
+struct ProfW2 {
+  static constexpr bool on = false;
+  long long acc[6];
+  __device__ __forceinline__ ProfW2(bool) {}
+  __device__ __forceinline__ void lap(int) {}
+};
+#define W2_PROF_PRINT(...) ((void)0)
+#endif
 
 template <bool ZP>
 __global__ void __launch_bounds__(kThreadsW2, 1)
@@ -157,16 +173,16 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
   extern __shared__ uint8_t smem_raw[];
   uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // nphys S16 plane slots, [rows][16 ch], SWIZZLE_32B (TMA)
   uint8_t *e2 = ring + (size_t)p.nphys * p.slot_bytes;          // 2 stages of the expanded operand, [L * Zt rows][2][8], SWIZZLE_32B
-  uint32_t *stage = reinterpret_cast<uint32_t *>(e2 + (size_t)p.nst * p.e2_bytes);  // 2 buffers of raw Q1 line segments [2][L][LW]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stage + 2 * p.stage_words);
-  uint64_t *s_full = bars, *s_empty = bars + kMaxRingW2, *e_full = s_empty + kMaxRingW2, *e_empty = e_full + kMaxStagesW2, *done = e_empty + kMaxStagesW2;
+  uint32_t *stage = reinterpret_cast<uint32_t *>(e2 + (size_t)p.nst * p.e2_bytes);  // nsb buffers of raw Q1 line segments [2][L][LW]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stage + (size_t)p.nsb * p.stage_words);
+  uint64_t *s_full = bars, *s_empty = bars + kRingCapW2, *e_full = s_empty + kRingCapW2, *e_empty = e_full + kMaxStagesW2, *done = e_empty + kMaxStagesW2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kCols = ZP ? 256 : 128;  // accumulator columns: 8 planes x (32 | 16)
   constexpr uint32_t kNper = ZP ? 32 : 16;    // N elements per plane
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxRingW2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < kRingCapW2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 1); }
     for (int i = 0; i < kMaxStagesW2; ++i) { tc::mbar_init(&e_full[i], kBuildWarpsW2); tc::mbar_init(&e_empty[i], 1); }
     tc::mbar_init(done, 1);
     tc::fence_barrier_init();
@@ -229,7 +245,7 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
         }
       }
       prof.lap(0);
-      if (prof.on) printf("w2 prof TMA : work %lld  wait s_empty %lld\n", prof.acc[0], prof.acc[1]);
+      if (prof.on) W2_PROF_PRINT("w2 prof TMA : work %lld  wait s_empty %lld\n", prof.acc[0], prof.acc[1]);
     }
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer
@@ -301,17 +317,20 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
     }
     if (leader) tc::umma_commit(done);
     __syncwarp();
-    if (prof.on)
-      printf("w2 prof MMA : other %lld  wait s_full %lld  wait e_full %lld  issue %lld  commit %lld (leader %d)\n", prof.acc[0], prof.acc[1],
+    if (prof.on) W2_PROF_PRINT("w2 prof MMA : other %lld  wait s_full %lld  wait e_full %lld  issue %lld  commit %lld (leader %d)\n", prof.acc[0], prof.acc[1],
              prof.acc[2], prof.acc[3], prof.acc[4], (int)leader);
   } else {
     // ------------------------------------------------ warps 0..3, 6..11: build the expanded operand (0..3 then run the
-    // epilogue); warps 12..15: fetch the raw Q1 words two steps ahead and stage them in shared memory.  The roles are split
+    // epilogue); warps 12..15: bring the raw Q1 words of the next steps into the staging buffers.  The roles are split
     // because the generic->async proxy fence that publishes the operand compiles to MEMBAR.ALL.CTA, which waits for every
     // outstanding global load of the executing thread: a warp that prefetches AND builds exposes the full load latency
-    // (~1 us under load) in every step.  The staging area is double-buffered and handed over with arrive / wait named
-    // barriers, so the fetch warps' instruction chain (~150 dependent instructions per step) runs beside the build instead
-    // of in series with it (measured with everything else disabled: 0.36 ms of the first form's 0.55 ms was this chain).
+    // (~1 us under load) in every step.  The staging area has nsb buffers handed over with arrive / wait named barriers,
+    // so the fetch warps run nsb - 1 steps ahead of the builders.
+    // Where the time goes now (per-role cycle counters, -DCGAN3D_W2_PROF; `first` at C3, ~1590 cycles per step): the 8
+    // N = 256 MMAs of a step read 96 KB of shared memory, the TMA fills write 23 KB (mirrors included), the builders move
+    // 36 KB, the staging 10 KB: ~165 KB per step against 128 B/clk = 1290 cycles.  Shared-memory bandwidth, not the tensor
+    // pipe (8 x 128 cycles), bounds the step (DESIGN fact 13); deeper rings, more operand stages and a consumer-side fence
+    // (CGAN3D_W2_RING / _STAGES / _CFENCE) change nothing.
     const int ZqW = p.Zq >> 1;
     const SegIterW2 range(ncols, p.npairs);
     const uint32_t total = (uint32_t)range.steps();
@@ -319,70 +338,89 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
     if (warp >= kFetchWarp0W2) {
       const int tid = (warp - kFetchWarp0W2) * 32 + lane;  // 0..127
       const int total_words = 2 * p.L * p.LW;
-      // word i of this thread: staging index tid + 128 i = (h, l, w); rel = its offset from the step's base pointer; the
-      // z-range check does not depend on the step (meta < 0: never loaded)
-      int meta[kMaxPrefW2], rel[kMaxPrefW2];
+      // word i of this thread: staging index tid + 128 i = (h, l, w); rel = its offset from the step's base pointer.  Validity
+      // is a bit mask over i: z range (fixed), line in [0, Yq) (changes with the column), plane in [0, Xq) (changes with the
+      // step, one mask per plane h).  The words travel global -> shared as 4-byte zero-filling cp.async (src-size 0 for an
+      // invalid word): no branches, no registers, and the load latency is covered by nsb - 1 steps of lookahead instead of
+      // being exposed in this warp (first form: 11 branchy __ldg + st.shared per thread and step = 1700 cycles per step with
+      // the warps never idle — the kernel's bottleneck).
+      int rel[kMaxPrefW2];
+      uint32_t zmask = 0, mh[2] = {0, 0};
+      uint64_t lpack = 0;  // 4 bits of l per word
 #pragma unroll
       for (int i = 0; i < kMaxPrefW2; ++i) {
         const int idx = tid + kFetchersW2 * i;
-        meta[i] = -1; rel[i] = 0;
+        rel[i] = 0;
         if (idx < total_words) {
           const int w = idx % p.LW, hl = idx / p.LW, l = hl % p.L, h = hl / p.L;
           const int wq = w - p.P / 2;  // staged word 0 holds Q1 z elements (-P, -P + 1); P is even
-          if ((unsigned)wq < (unsigned)ZqW) { meta[i] = l | (h << 8); rel[i] = (h * p.Yq + l) * ZqW + w; }
+          if ((unsigned)wq < (unsigned)ZqW) zmask |= 1u << i;
+          mh[h] |= 1u << i;
+          lpack |= (uint64_t)l << (4 * i);  // L <= 15
+          rel[i] = (h * p.Yq + l) * ZqW + w;
         }
       }
       ProfW2 prof((p.debug & 16) && blockIdx.x == 0 && tid == 0);
       StepWalkW2 walk(range);
-      int cur_col = -1, yb = 0;
+      int cur_col = -1;
+      uint32_t ymask = 0;
       const uint32_t *col_base = q1;  // Q1 word (b, x = 0, y = yb, z = -P) of the current column
       const long long plane_words = (long long)p.Yq * ZqW;
-      auto fetch = [&](uint32_t (&pref)[kMaxPrefW2]) {  // raw Q1 words of this CTA's next step -> registers
+      const uint32_t stage_u32 = tc::smem_u32(stage) + (uint32_t)tid * 4u, stage_stride = p.stage_words * 4u;
+      auto issue = [&](uint32_t buf) {  // raw Q1 words of this CTA's next step -> staging buffer `buf`
         if (walk.col != cur_col) {
           cur_col = walk.col;
           const int b = cur_col / p.nyt, y0 = (cur_col - b * p.nyt) * p.Yt;
-          yb = y0 - p.P;
+          const int yb = y0 - p.P;
           col_base = q1 + ((long long)b * p.Xq * p.Yq + yb) * ZqW - p.P / 2;
+          ymask = 0;
+#pragma unroll
+          for (int i = 0; i < kMaxPrefW2; ++i)
+            if ((unsigned)(yb + (int)((lpack >> (4 * i)) & 15)) < (unsigned)p.Yq) ymask |= 1u << i;
         }
         const int xb = 2 * walk.pair - p.P;
         walk.advance();
         // base may point outside the tensor (halo): it is only dereferenced for in-range (plane, line)
         const uint32_t *base = col_base + (long long)xb * plane_words;
-        const bool hv0 = (unsigned)xb < (unsigned)p.Xq, hv1 = (unsigned)(xb + 1) < (unsigned)p.Xq;
+        uint32_t valid = zmask & ymask & (((unsigned)xb < (unsigned)p.Xq ? mh[0] : 0u) | ((unsigned)(xb + 1) < (unsigned)p.Xq ? mh[1] : 0u));
+        if (p.debug & 8) valid = 0;
+        const uint32_t dst = stage_u32 + buf * stage_stride;
 #pragma unroll
         for (int i = 0; i < kMaxPrefW2; ++i) {
-          uint32_t v = 0;
-          if (meta[i] >= 0) {
-            const bool hv = (meta[i] >> 8) ? hv1 : hv0;
-            if (hv && (unsigned)(yb + (meta[i] & 0xFF)) < (unsigned)p.Yq && !(p.debug & 8)) v = __ldg(base + rel[i]);
+          if (tid + kFetchersW2 * i < total_words) {  // uniform per (thread, i): resolved once, not data dependent
+            const bool ok = (valid >> i) & 1u;
+            const uint32_t *src = ok ? base + rel[i] : q1;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)(kFetchersW2 * i) * 4u), "l"(src), "r"(ok ? 4u : 0u) : "memory");
           }
-          pref[i] = v;
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      auto put = [&](uint32_t k, uint32_t (&pref)[kMaxPrefW2]) {
-        const uint32_t sb = k & 1;
+      // steps k .. k + nsb - 2 are in flight while step k is handed over; buffer (k + nsb - 1) % nsb was read by step k - 1
+      const uint32_t nsb = (uint32_t)p.nsb, ahead = nsb - 1;
+      uint32_t issued = 0, ibuf = 0, buf = 0;
+      for (; issued < ahead && issued < total; ++issued) {
+        issue(ibuf);
+        if (++ibuf == nsb) ibuf = 0;
+      }
+      for (; n < total; ++n) {
         prof.lap(0);
-        if (k >= 2) bar_sync_id(3 + sb);  // the builders have finished reading step k - 2 from this buffer
-        prof.lap(1);
-        uint32_t *dst = stage + sb * p.stage_words;
-#pragma unroll
-        for (int i = 0; i < kMaxPrefW2; ++i)
-          if (tid + kFetchersW2 * i < total_words) dst[tid + kFetchersW2 * i] = pref[i];
+        // the group of step n is the oldest of (issued - n) pending ones
+        if (issued - n >= 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (issued - n == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         prof.lap(2);
-        bar_arrive_id(1 + sb);
-        if (k + 2 < total) fetch(pref);
-      };
-      uint32_t prefA[kMaxPrefW2], prefB[kMaxPrefW2];
-      if (total > 0) fetch(prefA);
-      if (total > 1) fetch(prefB);
-      while (n < total) {
-        put(n, prefA);
-        if (++n >= total) break;
-        put(n, prefB);
-        ++n;
+        bar_arrive_id(1 + buf);
+        if (++buf == nsb) buf = 0;
+        if (issued < total) {
+          if (issued >= nsb) bar_sync_id(1 + kMaxStageBufsW2 + ibuf);  // the builders have finished reading step issued - nsb
+          prof.lap(1);
+          issue(ibuf);
+          ++issued;
+          if (++ibuf == nsb) ibuf = 0;
+        }
       }
       prof.lap(0);
-      if (prof.on) printf("w2 prof FETCH: fetch+issue %lld  wait empty %lld  sts(+load latency) %lld  steps %u\n", prof.acc[0], prof.acc[1], prof.acc[2], total);
+      if (prof.on) W2_PROF_PRINT("w2 prof FETCH: issue %lld  wait empty %lld  wait loads %lld  steps %u\n", prof.acc[0], prof.acc[1], prof.acc[2], total);
     } else {
       const int bw = warp < 4 ? warp : warp - 2;  // builder warp 0..9
       // E2[l * Zt + r][h][j] = line(h, l)[r + j], j = 0..7.  A warp iteration = 32 rows of one staged line (h, l): 5
@@ -398,16 +436,48 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
       const uint32_t lane_dst = (uint32_t)lane * 32u;
       const uint32_t swz = (uint32_t)((lane >> 2) & 1);  // rows advance by 32 per iteration: the swizzle phase is the lane's
       const uint32_t sh = (uint32_t)(lane & 1) << 4;
-      uint32_t st = 0, use = 0;  // operand stage of step n and how often it has been used before
+      uint32_t st = 0, use = 0, sb = 0;  // operand stage of step n and how often it has been used before; staging buffer
+      // Z-pair fast path: a warp's iterations are the same in every step, so their shared-memory offsets live in registers
+      // and all loads of a step are issued before the first store (the looped form below exposes the LDS -> STS latency of
+      // every iteration: 240 cycles each while the tensor core is reading shared memory).
+      constexpr int kFastPerW2 = 6;
+      const bool fast = ZP && per <= kFastPerW2 && !(p.debug & 32);  // debug bit 32: looped form
+      uint32_t f_src[kFastPerW2], f_dst[kFastPerW2], f_ok = 0;
+#pragma unroll
+      for (int q = 0; q < kFastPerW2; ++q) {
+        f_src[q] = f_dst[q] = 0;
+        const int it = it0 + q;
+        if (fast && it < it1) {
+          const int hl = it / ipl, rb = it - hl * ipl, h = hl >= p.L ? 1 : 0, l = hl - h * p.L;
+          if (rb * 32 + lane < p.zr) f_ok |= 1u << q;
+          f_src[q] = (uint32_t)(hl * p.LW + rb * 32 + lane) * 4u;
+          f_dst[q] = (uint32_t)(l * p.zr + rb * 32 + lane) * 32u + (((uint32_t)h ^ swz) << 4);
+        }
+      }
       ProfW2 prof((p.debug & 16) && blockIdx.x == 0 && threadIdx.x == 0);
       for (; n < total; ++n) {
-        const uint32_t sb = n & 1;
         prof.lap(0);
         bar_sync_id(1 + sb);  // the fetch warps have written this step's staging buffer
         prof.lap(1);
         if (use > 0) tc::mbar_wait(&e_empty[st], (use - 1) & 1);
         prof.lap(2);
-        if (!(p.debug & 1)) {
+        if (fast && !(p.debug & 1)) {
+          const uint32_t sbase = tc::smem_u32(stage) + sb * stage_stride, dbase = tc::smem_u32(e2) + st * p.e2_bytes;
+          uint32_t a[kFastPerW2][4];
+#pragma unroll
+          for (int q = 0; q < kFastPerW2; ++q)
+            if ((f_ok >> q) & 1u) {
+              const uint32_t src = sbase + f_src[q];
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a[q][0]) : "r"(src));
+              asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(a[q][1]) : "r"(src));
+              asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(a[q][2]) : "r"(src));
+              asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(a[q][3]) : "r"(src));
+            }
+#pragma unroll
+          for (int q = 0; q < kFastPerW2; ++q)
+            if ((f_ok >> q) & 1u)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dbase + f_dst[q]), "r"(a[q][0]), "r"(a[q][1]), "r"(a[q][2]), "r"(a[q][3]) : "memory");
+        } else if (!(p.debug & 1)) {
           const uint32_t dst_u32 = tc::smem_u32(e2) + st * p.e2_bytes + lane_dst;
           int it = it0, hl = hl0, rb = rb0;
           while (it < it1) {
@@ -438,15 +508,15 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
           }
         }
         prof.lap(3);
-        if (n + 2 < total) bar_arrive_id(3 + sb);  // this warp has read the staging buffer: the fetch warps may refill it
+        if (n + (uint32_t)p.nsb < total) bar_arrive_id(1 + kMaxStageBufsW2 + sb);  // this warp has read the staging buffer: the fetch warps may refill it
+        if (++sb == (uint32_t)p.nsb) sb = 0;
         if (!p.cfence) tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&e_full[st]);
         if (++st == (uint32_t)p.nst) { st = 0; ++use; }
         prof.lap(4);
       }
-      if (prof.on)
-        printf("w2 prof BUILD: other %lld  wait full %lld  wait e_empty %lld  build %lld  fence+arrive %lld\n", prof.acc[0], prof.acc[1],
+      if (prof.on) W2_PROF_PRINT("w2 prof BUILD: other %lld  wait full %lld  wait e_empty %lld  build %lld  fence+arrive %lld\n", prof.acc[0], prof.acc[1],
                prof.acc[2], prof.acc[3], prof.acc[4]);
     }
     // epilogue: TMEM lane m = (dy = m >> 4, dx_lo = (m >> 3) & 1, dz = m & 7); column = 16 * j + c, dx = 6 - j + dx_lo
@@ -515,6 +585,8 @@ static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
   p.zr = p.zp ? p.Zt / 2 : p.Zt;
   p.nst = 2;
   if (const char *e = getenv("CGAN3D_W2_STAGES")) p.nst = mx(2, mn(kMaxStagesW2, atoi(e)));
+  p.nsb = 3;
+  if (const char *e = getenv("CGAN3D_W2_STAGEBUFS")) p.nsb = mx(2, mn(kMaxStageBufsW2, atoi(e)));
   p.cfence = 0;
   if (const char *e = getenv("CGAN3D_W2_CFENCE")) p.cfence = atoi(e) ? 1 : 0;
   // pass 0 only takes a tile whose ring is the deep one (14 logical slots, >= 4 mirrored); pass 1 takes what fits
@@ -526,16 +598,21 @@ static bool plan_w2(const cgan3d_conv_geom &g, ThinW2Plan &p) {
     const uint32_t slot = (uint32_t)Yt * p.Zt * 32u;
     const uint32_t e2b = ((uint32_t)L * p.zr * 32u + 1023u) / 1024u * 1024u;
     const uint32_t stage_words = ((uint32_t)(2 * L * p.LW) + 3u) & ~3u;
-    const uint32_t fixed = (uint32_t)p.nst * e2b + 2 * stage_words * 4 + 512;
+    const uint32_t fixed = (uint32_t)p.nst * e2b + (uint32_t)p.nsb * stage_words * 4 + 512;
     if (slot % 1024) continue;
     int nphys = (int)((kSmemLimitW2 - mn(kSmemLimitW2, fixed)) / slot);
+    const int nphys_fit = nphys;
     if (nphys > kMaxRingW2 + 6) nphys = kMaxRingW2 + 6;
     // ring of 14 (TMA three steps ahead) when at least four of its slots can be mirrored, else 12; a mirrored slot keeps the
     // window of 8 planes contiguous, so most steps need ONE N = 128 MMA per K block
-    const int ring = nphys >= kMaxRingW2 + 4 ? kMaxRingW2 : 12;
+    int ring = nphys >= kMaxRingW2 + 4 ? kMaxRingW2 : 12;
+    if (const char *e = getenv("CGAN3D_W2_RING")) {  // experiment: ring depth / mirror split
+      const int want = mx(10, mn(kRingCapW2, atoi(e))) & ~1;
+      if (nphys_fit >= want) { ring = want; nphys = mn(nphys_fit, ring + 6); }
+    }
     if (nphys < ring + 2 && Yt > 1) continue;
     if (nphys < ring) continue;
-    if (pass == 0 && ring != kMaxRingW2) continue;
+    if (pass == 0 && ring < kMaxRingW2) continue;
     if (nphys > ring + 6) nphys = ring + 6;  // windows start at even slots <= ring - 2: six mirrors make every window contiguous
     if (const char *e = getenv("CGAN3D_W2_NPHYS")) nphys = mx(ring, mn(nphys, atoi(e)));  // experiment: fewer mirrored slots
     p.Yt = Yt; p.L = L; p.nphys = nphys; p.ring = ring;
