@@ -608,24 +608,31 @@ conv_s1_stack_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // the next plane writes the OTHER exchange buffer; this one is rewritten two planes on, after the next bar.sync
       }
     }
-    if constexpr (STATS) {  // a thread saw at most a few dozen rows: fp32 partials, fp64 across threads
+    if constexpr (STATS) {
+      // a thread saw at most a few dozen rows: fp32 partials; fp64 across the CTA in shared memory (the exchange buffers are
+      // free now), then ONE global atomic per channel and CTA: with every thread adding its own partials 148 CTAs queued
+      // ~1800 fp64 atomics on each of the 128 addresses at the same moment, ~18 us at the end of every launch
+      double *sst = reinterpret_cast<double *>(xch);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < N2) sst[tid] = 0.0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       warp_reduce64(ssum, lane);
       warp_reduce64(ssq, lane);
       const int ch = warp_reduce64_channel(lane);
 #pragma unroll
       for (int i = 0; i < 2; ++i)
         if (ch + i < N) {
-          atomicAdd(&bn_sums[0 + ch + i], (double)ssum[i]);
-          atomicAdd(&bn_sums[N + 0 + ch + i], (double)ssq[i]);
+          atomicAdd(&sst[ch + i], (double)ssum[i]);
+          atomicAdd(&sst[N + ch + i], (double)ssq[i]);
         }
       if (frow < MT * 4) {
         for (int j = 0; j < cpt && j < 4; ++j) {
-          if (fsum[j] != 0.f || fsq[j] != 0.f) {
-            atomicAdd(&bn_sums[fch + j], (double)fsum[j]);
-            atomicAdd(&bn_sums[N + fch + j], (double)fsq[j]);
-          }
+          atomicAdd(&sst[fch + j], (double)fsum[j]);
+          atomicAdd(&sst[N + fch + j], (double)fsq[j]);
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < N2) atomicAdd(&bn_sums[tid], sst[tid]);
     }
   }
   tc::tc_fence_before();
