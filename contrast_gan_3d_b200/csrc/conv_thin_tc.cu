@@ -25,7 +25,8 @@ using bf16 = __nv_bfloat16;
 
 constexpr uint32_t kSmemLimitThin = 232448 - 1024;
 constexpr int kTapTilesA = 49;
-constexpr uint32_t kTileBytesA = 2048;  // [2 z-chunks][64 n][8 z] bf16
+constexpr uint32_t kTileBytesA = 2048;  // [2 z-chunks][64 n][8 z] bf16 (4 output z per item); 4096 with 8 output z (N = 128)
+constexpr uint32_t kTileBytesAMax = 4096;
 
 struct ThinAPlan {
   int B, Xi, Yi, Zi;  // 1-channel input
@@ -38,19 +39,25 @@ struct ThinAPlan {
   int zshift[2];
   int debug;
   int pair;       // CTA pairs (cta_group::2): consecutive work items go to the two CTAs, each holds half of the N rows
+  int zb;         // output z per item: 4 (N = 64) or 8 (N = 128, CTA pairs only: one 65-cycle MMA instead of two 59-cycle ones)
 };
 
 // PAIR: see conv_tc.cu — the two CTAs of a cluster process consecutive work items in lockstep; each holds the Toeplitz
 // rows of two of the four output z (32 of the 64 N rows), and the rank-0 CTA issues every MMA for both.
-template <int MT, bool STATS, bool PAIR>
+// ZB = 8: an item covers 8 output z, N = 128.  A cta_group::2 MMA costs 59 cycles up to N = 96 and 65 at N = 128
+// (profiles/r01_mma2_microbench.txt), the 14-voxel input window of 8 outputs still fits K = 16, and every window then starts
+// on a 16-byte boundary of ONE shifted copy of the input.  Half the MMAs, half the slab loads, half the items.
+template <int MT, bool STATS, bool PAIR, int ZB = 4>
 __global__ void __launch_bounds__(192, 1)
 conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const bf16 *__restrict__ wT,
                    bf16 *__restrict__ out, const __grid_constant__ ThinAPlan p, double *__restrict__ bn_sums) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t kTileB = PAIR ? kTileBytesA / 2 : kTileBytesA;
+  constexpr uint32_t NN = ZB * 16;                       // GEMM N = output z x 16 channels
+  constexpr uint32_t kTileFull = 2 * NN * 16;            // [2 z-chunks][NN n][8 z] bf16
+  constexpr uint32_t kTileB = PAIR ? kTileFull / 2 : kTileFull;
   // accumulator ring: with one M tile per item an item is only ~2 us of MMAs, so the MMA -> epilogue -> MMA hand-off
   // latency must be hidden behind several buffers (all 512 TMEM columns are used)
-  constexpr uint32_t NACC = 512 / (MT * 64);
+  constexpr uint32_t NACC = 512 / (MT * NN);
   uint8_t *bres = smem;                                    // 49 resident Toeplitz tiles
   uint8_t *ring = bres + kTapTilesA * kTileB;              // slab slots
   uint8_t *stage = ring + (size_t)p.nslots * p.slot_bytes; // epilogue store staging: 4 warps x 32 rows x 128 B
@@ -98,21 +105,22 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     b = it / p.nxt;
     x0 = xt * p.Xt; xlen = min(p.Xt, p.Xo - x0);
     y0 = yt * p.Yt; ylen = min(p.Yt, p.Yo - y0);
-    z0 = zb * 4;
+    z0 = zb * ZB;
     return live;
   };
 
   if (warp == 4) {
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmA);
-      if constexpr (PAIR) {  // one box per CTA: its 49 half tiles (49 KB as 196 rows of 256 bytes), counted on the rank-0 barrier
+      if constexpr (PAIR) {  // boxes of 196 rows of 256 bytes (49 KB): this CTA's 49 half tiles, counted on the rank-0 barrier
         if (cta_rank == 0) tc::mbar_expect_tx(b_ready, 2 * kTapTilesA * kTileB);
-        tc::tma_load_2d_2cta(bres, &tmW, b_ready, 0, (int)cta_rank * (int)(kTapTilesA * kTileB / 256));
+        constexpr int rows_cta = (int)(kTapTilesA * kTileB / 256);
+        for (int r0 = 0; r0 < rows_cta; r0 += 196)
+          tc::tma_load_2d_2cta(bres + (size_t)r0 * 256, &tmW, b_ready, 0, (int)cta_rank * rows_cta + r0);
       } else {
-        tc::mbar_expect_tx(b_ready, kTapTilesA * kTileBytesA);
+        tc::mbar_expect_tx(b_ready, kTapTilesA * kTileFull);
         for (int t = 0; t < kTapTilesA; ++t)
-          tc::bulk_g2s(bres + (size_t)t * kTileBytesA, reinterpret_cast<const uint8_t *>(wT) + (size_t)t * kTileBytesA, kTileBytesA,
-                       b_ready);
+          tc::bulk_g2s(bres + (size_t)t * kTileFull, reinterpret_cast<const uint8_t *>(wT) + (size_t)t * kTileFull, kTileFull, b_ready);
       }
       uint32_t e = 0;
       for (int it = i_begin; it < i_end; ++it, ++e) {
@@ -122,7 +130,7 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
         uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
         // TMA needs a 16-byte aligned start along z: block parity selects the copy whose z shift makes it so
-        const int cp = (z0 >> 2) & 1;
+        const int cp = ZB == 8 ? 0 : (z0 >> 2) & 1;
         const int c0 = z0 - p.P - p.zshift[cp] + 8;
         if constexpr (PAIR) {
           if (cta_rank == 0) tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
@@ -138,9 +146,9 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // odd CTA of a pair: the rank-0 CTA issues the MMAs for both
   } else if (warp == 5) {
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 256 : 128, 64, 0, 0);
+    const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 256 : 128, (int)NN, 0, 0);
     const uint32_t ring_u32 = tc::smem_u32(ring), b_u32 = tc::smem_u32(bres);
-    const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc(0, (PAIR ? 32 : 64) * 16, 128);
+    const uint64_t a_hi = tc::make_desc_sw(0, 256, 32), b_hi = tc::make_desc(0, (PAIR ? NN / 2 : NN) * 16, 128);
     tc::mbar_wait(b_ready, 0);
     tc::tc_fence_after();
     uint32_t e = 0;
@@ -150,7 +158,7 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc::mbar_wait(&s_full[slot], (e / p.nslots) & 1);
       tc::tc_fence_after();
       const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
-      const uint32_t d_base = tmem_base + q * (uint32_t)(MT * 64);
+      const uint32_t d_base = tmem_base + q * (uint32_t)(MT * NN);
       // lean issue loop: the seven dy taps of one dx go out back to back with descriptor adds only (a loop iteration
       // per MMA costs ~120 cycles of dependent scalar work on the single issuing warp, more than the MMA itself)
       const uint64_t a_it = a_hi | (uint64_t)(a_slot & 0x3FFF), b_it = b_hi | (uint64_t)((b_u32 >> 4) & 0x3FFF);
@@ -164,9 +172,9 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t accum = dy != 0 ? 1u : (uint32_t)(dx != 0);
               if constexpr (PAIR)
-                tc::umma_bf16_2cta(d_base + mt * 64, a_dx + (uint64_t)(2 * dy + mt * 256), b_dx + (uint64_t)(dy * (kTileB >> 4)), idesc, accum);
+                tc::umma_bf16_2cta(d_base + mt * NN, a_dx + (uint64_t)(2 * dy + mt * 256), b_dx + (uint64_t)(dy * (kTileB >> 4)), idesc, accum);
               else
-                tc::umma_bf16(d_base + mt * 64, a_dx + (uint64_t)(2 * dy + mt * 256), b_dx + (uint64_t)(dy * (kTileB >> 4)), idesc, accum);
+                tc::umma_bf16(d_base + mt * NN, a_dx + (uint64_t)(2 * dy + mt * 256), b_dx + (uint64_t)(dy * (kTileB >> 4)), idesc, accum);
             }
           }
         }
@@ -187,21 +195,23 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int j = 0; j < 16; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
     }
     for (int it = i_begin; it < i_end; ++it, ++e) {
-      int b, x0, xlen, y0, ylen, z0;
-      const bool live = decode(it, b, x0, xlen, y0, ylen, z0);
+      int b, x0, xlen, y0, ylen, z0_item;
+      const bool live = decode(it, b, x0, xlen, y0, ylen, z0_item);
       const uint32_t q = e % NACC;
       tc::mbar_wait(&tm_full[q], (e / NACC) & 1);
       tc::tc_fence_after();
-      const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(MT * 64);
+      const uint32_t d_base = tmem_base + ((uint32_t)(warp * 32) << 16) + q * (uint32_t)(MT * NN);
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mth = 0; mth < MT * (ZB / 4); ++mth) {  // (M tile, group of four output z)
+        const int mt = mth / (ZB / 4), zh = (mth % (ZB / 4)) * 4;
         const int r = mt * 128 + warp * 32 + lane;
         const int xx = r / p.Yh, yy = r - xx * p.Yh;
         const bool valid = live && xx < xlen && yy < ylen && !(p.debug & 4);
+        const int z0 = z0_item + zh;
         bf16 *dst = out + ((((size_t)b * p.Xo + (x0 + xx)) * p.Yo + (y0 + yy)) * p.Zo + z0) * 16;
-        uint32_t v[4][16];  // the four output z of this row: all TMEM loads in flight before one wait
+        uint32_t v[4][16];  // four output z of this row: all TMEM loads in flight before one wait
 #pragma unroll
-        for (int zo = 0; zo < 4; ++zo) tc::tmem_ld16(d_base + (uint32_t)(mt * 64 + zo * 16), v[zo]);
+        for (int zo = 0; zo < 4; ++zo) tc::tmem_ld16(d_base + (uint32_t)(mt * NN + (zh + zo) * 16), v[zo]);
         tc::tmem_ld_wait();
         // A lane owns one (x,y) row = 128 contiguous output bytes, but neighbouring lanes are a whole z line (4 KB) apart:
         // direct stores would be 32 quarter-line writes per instruction.  Stage the warp's 32 x 128 B in shared memory
@@ -267,19 +277,20 @@ conv7_c1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // Toeplitz tiles: T[(dx,dy)][zi/8][n = zo*16 + co][zi%8] = w(dx,dy,zi-zo,co) for 0 <= zi-zo < 7, else 0.
 // wp is the packed filter [tap][Cb][Cs] with Cb*Cs == 16; flip = 1 reverses the taps (transposed convolution).
 // split = 1 (CTA pairs): [half][(dx,dy)][zi/8][32 n][8], half = n / 32.
-__global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip, int split) {
-  const int total = kTapTilesA * 2 * 64 * 8;
+// NN = 64 or 128 N rows (4 or 8 output z).
+__global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict__ wt, int flip, int split, int NN) {
+  const int total = kTapTilesA * 2 * NN * 8, Nh = NN >> 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int z8 = i & 7;
     int t = i >> 3;
     int n, chunk, tile;
     if (split) {
-      const int nl = t & 31; t >>= 5;
+      const int nl = t % Nh; t /= Nh;
       chunk = t & 1; t >>= 1;
       tile = t % kTapTilesA;
-      n = (t / kTapTilesA) * 32 + nl;
+      n = (t / kTapTilesA) * Nh + nl;
     } else {
-      n = t & 63; t >>= 6;
+      n = t % NN; t /= NN;
       chunk = t & 1;
       tile = t >> 1;
     }
@@ -299,7 +310,7 @@ __global__ void toeplitz_a_kernel(const bf16 *__restrict__ wp, bf16 *__restrict_
 // One WARP per input line (8 lines per block): the line is staged in shared memory (with zero margins) and written out as
 // 16-byte chunks.
 __global__ void __launch_bounds__(256)
-shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc, int s0, int s1) {
+shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long long rows, int Z, int Zc, int s0, int s1, int ncopies) {
   extern __shared__ uint16_t lines[];  // per warp: line[8 + z] = in[z], zeros in [0, 8) and beyond Z
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = (Zc + 24 + 7) & ~7;
@@ -313,7 +324,7 @@ shifted_copies_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, long 
   }
   __syncwarp();
   const int chunks = Zc >> 3;
-  for (int i = lane; i < 2 * chunks; i += 32) {
+  for (int i = lane; i < ncopies * chunks; i += 32) {
     const int cp = i >= chunks, j = i - cp * chunks;
     const int base = j * 8 + (cp ? s1 : s0);  // out[c] = in[c - 8 + s] = line[c + s]
     uint32_t w[4];
@@ -835,23 +846,27 @@ static bool plan_thin_a(const cgan3d_conv_geom &g, int op, ThinAPlan &best) {
   p.B = g.B;
   if (op == 0) { p.Xi = g.Xb; p.Yi = g.Yb; p.Zi = g.Zb; p.Xo = g.Xs; p.Yo = g.Ys; p.Zo = g.Zs; p.P = g.pad; }
   else         { p.Xi = g.Xs; p.Yi = g.Ys; p.Zi = g.Zs; p.Xo = g.Xb; p.Yo = g.Yb; p.Zo = g.Zb; p.P = 6 - g.pad; }
-  p.nzb = (p.Zo + 3) / 4;
   p.zshift[0] = ((0 - p.P) % 8 + 8) % 8;
   p.zshift[1] = ((4 - p.P) % 8 + 8) % 8;
   p.Zc = round_up(p.Zi + 16, 8);
   {
-    static int off = -1;
+    static int off = -1, zb4 = -1;
     if (off < 0) off = getenv("CGAN3D_NO_PAIR") ? 1 : 0;
+    if (zb4 < 0) zb4 = getenv("CGAN3D_THIN_ZB4") ? 1 : 0;  // A/B timing: four output z per item (N = 64)
     p.pair = off ? 0 : 1;
+    p.zb = (p.pair && !zb4) ? 8 : 4;
   }
-  const uint32_t fixed = kTapTilesA * kTileBytesA / (p.pair ? 2 : 1) + 16384 + 512;  // Toeplitz tiles, store staging, barriers
+  p.nzb = (p.Zo + p.zb - 1) / p.zb;
+  const uint32_t tile_full = p.zb == 8 ? kTileBytesAMax : kTileBytesA;
+  const int max_mt = p.zb == 8 ? 2 : 4;  // the accumulator ring needs at least two buffers of mtiles * N columns
+  const uint32_t fixed = kTapTilesA * tile_full / (p.pair ? 2 : 1) + 16384 + 512;  // Toeplitz tiles, store staging, barriers
   double best_score = 0;
   bool found = false;
   for (int nyt = 1; nyt <= p.Yo; ++nyt) {
     const int Yt = (p.Yo + nyt - 1) / nyt, Yh = Yt + 6;
     if ((p.Yo + Yt - 1) / Yt != nyt) continue;
     if (Yh > 256) continue;
-    for (int mt = 1; mt <= 4; ++mt) {
+    for (int mt = 1; mt <= max_mt; ++mt) {
       if (Yt > mt * 128) continue;
       const int Xt = mn(p.Xo, (mt * 128 - Yt) / Yh + 1), Xh = Xt + 6;
       if (Xh > 256) continue;
@@ -937,7 +952,7 @@ static size_t thin_a_repitch_bytes(const ThinAPlan &p) { return (size_t)2 * p.B 
 size_t thin_workspace_bytes(const cgan3d_conv_geom &g, int dtype, int op) {
   if (dtype != CGAN3D_BF16) return 0;
   ThinAPlan p;
-  if ((op == 0 || op == 1) && plan_thin_a(g, op, p)) return (size_t)kTapTilesA * kTileBytesA + 256 + thin_a_repitch_bytes(p) + 256;
+  if ((op == 0 || op == 1) && plan_thin_a(g, op, p)) return (size_t)kTapTilesA * kTileBytesAMax + 256 + thin_a_repitch_bytes(p) + 256;
   ThinBPlan pb;
   if ((op == 0 || op == 1) && plan_thin_b(g, op, pb)) return (size_t)kTapTilesB * kTileBytesB + 256;
   ThinCPlan pc;
@@ -956,12 +971,14 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(outp) & 15) || (reinterpret_cast<uintptr_t>(ws) & 255))
     return fail(CGAN3D_E_ARG, "tcgen05 thin conv: pointers must be 16-byte aligned (workspace 256)");
   bf16 *wt = reinterpret_cast<bf16 *>(ws);
-  toeplitz_a_kernel<<<49, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op, p.pair);
+  const uint32_t tile_full = p.zb == 8 ? kTileBytesAMax : kTileBytesA;
+  toeplitz_a_kernel<<<49, 256, 0, st>>>(reinterpret_cast<const bf16 *>(wp), wt, op, p.pair, p.zb * 16);
   CG_LAUNCH_CHECK("toeplitz_a");
-  bf16 *rp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kTapTilesA * kTileBytesA + 256);
+  bf16 *rp = reinterpret_cast<bf16 *>(reinterpret_cast<uint8_t *>(ws) + (size_t)kTapTilesA * kTileBytesAMax + 256);
   const long long rows = (long long)p.B * p.Xi * p.Yi;
+  // 8 output z per item: every window starts on a 16-byte boundary of copy 0, the second copy is not needed
   shifted_copies_kernel<<<(unsigned)((rows + 7) / 8), 256, (size_t)8 * ((p.Zc + 24 + 7) & ~7) * 2, st>>>(
-      reinterpret_cast<const bf16 *>(in), rp, rows, p.Zi, p.Zc, p.zshift[0], p.zshift[1]);
+      reinterpret_cast<const bf16 *>(in), rp, rows, p.Zi, p.Zc, p.zshift[0], p.zshift[1], p.zb == 8 ? 1 : 2);
   CG_LAUNCH_CHECK("shifted_copies");
   CUtensorMap tm;
   const cuuint64_t zc = (cuuint64_t)p.Zc;
@@ -972,9 +989,9 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
   if (r) return r;
   CUtensorMap tmw{};
   if (p.pair) {  // the Toeplitz tiles as rows of 256 bytes: 196 rows per CTA half
-    const cuuint64_t wdim[2] = {64, (cuuint64_t)(kTapTilesA * kTileBytesA / 256)};
+    const cuuint64_t wdim[2] = {64, (cuuint64_t)(kTapTilesA * tile_full / 256)};
     const cuuint64_t wstr[1] = {256};
-    const cuuint32_t wbox[2] = {64, (cuuint32_t)(kTapTilesA * kTileBytesA / 512)};
+    const cuuint32_t wbox[2] = {64, 196};  // 49 KB per box: one per CTA at N = 64, two at N = 128
     r = encode_map_raw(&tmw, wt, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, wdim, wstr, wbox);
     if (r) return r;
   }
@@ -1007,6 +1024,37 @@ static int run_thin_a(const cgan3d_conv_geom &g, int op, const void *in, const v
     CG_LAUNCH_CHECK("conv7_c1_tc_kernel");
     return 0;
   };
+  auto launch_z8 = [&](auto mt_tag, auto st_tag) -> int {  // CTA pairs, 8 output z per item
+    constexpr int MT = decltype(mt_tag)::value;
+    constexpr bool ST = decltype(st_tag)::value;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv7_c1_tc_kernel<MT, ST, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimitThin + 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv7_c1_tc_kernel, 8 z)");
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = p.smem_bytes + 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv7_c1_tc_kernel<MT, ST, true, 8>, tm, tmw, (const bf16 *)wt, reinterpret_cast<bf16 *>(outp), p, bn_sums);
+    if (e != cudaSuccess) return cuda_fail(e, "conv7_c1_tc_kernel (8 z) launch");
+    CG_LAUNCH_CHECK("conv7_c1_tc_kernel");
+    return 0;
+  };
+  if (p.zb == 8) {
+    if (p.mtiles == 1) return bn_sums ? launch_z8(std::integral_constant<int, 1>{}, std::true_type{}) : launch_z8(std::integral_constant<int, 1>{}, std::false_type{});
+    if (p.mtiles == 2) return bn_sums ? launch_z8(std::integral_constant<int, 2>{}, std::true_type{}) : launch_z8(std::integral_constant<int, 2>{}, std::false_type{});
+    return fail(CGAN3D_E_UNSUPPORTED, "tcgen05 thin conv (8 z): mtiles %d not built", p.mtiles);
+  }
   auto launch = [&](auto mt_tag) -> int {
     if (p.pair) return bn_sums ? launch_s(mt_tag, std::true_type{}, std::true_type{}) : launch_s(mt_tag, std::false_type{}, std::true_type{});
     return bn_sums ? launch_s(mt_tag, std::true_type{}, std::false_type{}) : launch_s(mt_tag, std::false_type{}, std::false_type{});

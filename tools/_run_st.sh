@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_c3_shapes.py tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/st_test.log 2>&1; echo test_rc=$?
-tail -3 gpurun_out/st_test.log
-timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --breakdown gpurun_out/r2_break16.txt > gpurun_out/r2_b16.json 2> gpurun_out/r2_b16.err; echo bench_rc=$?
+for w in 0.02 0.05 0.1 0.2 0.4; do
+CGAN3D_THIN_HALO_W=$w timeout 120 python tools/bench_conv.py --cases first_c3 --ops gather --impls tc --iters 20 2>&1 | grep '"ms"' | cut -c1-90 | sed "s/^/w=$w /"
+CGAN3D_THIN_HALO_W=$w timeout 120 python tools/bench_conv.py --cases last_c3 --ops scatter --impls tc --iters 20 2>&1 | grep '"ms"' | cut -c1-90 | sed "s/^/w=$w /"
+done
