@@ -811,15 +811,41 @@ reflect_pad_line_kernel(const U *__restrict__ in, U *__restrict__ out, int X, in
   }
 }
 
+// Short lines (the generator's 1-channel input: 134 two-byte elements per padded line): a block per line is 290 000 blocks
+// of half-idle threads, 0.20 ms for 150 MB.  Here a WARP owns a line and a block walks 32 lines of one padded (b, x) plane.
+template <typename U>
+__global__ void __launch_bounds__(256)
+reflect_pad_warpline_kernel(const U *__restrict__ in, U *__restrict__ out, int X, int Y, int Z, int upv, int p) {
+  const int Yp = Y + 2 * p, Zp = Z + 2 * p, Xp = X + 2 * p;
+  const int x = blockIdx.y, b = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx = reflect_idx(x - p, X);
+  const int n = Zp * upv;
+  for (int k = 0; k < 4; ++k) {
+    const int y = (blockIdx.x * 4 + k) * 8 + warp;
+    if (y >= Yp) break;
+    const int sy = reflect_idx(y - p, Y);
+    const U *src = in + (((int64_t)b * X + sx) * Y + sy) * (int64_t)Z * upv;
+    U *dst = out + (((int64_t)b * Xp + x) * Yp + y) * (int64_t)Zp * upv;
+    for (int i = lane; i < n; i += 32) {
+      const int z = i / upv, c = i - z * upv;
+      dst[i] = src[reflect_idx(z - p, Z) * upv + c];
+    }
+  }
+}
+
 // one block per interior (b, x, y) line: no per-element index division, the mirror sources of x and y are block-uniform
 template <typename T>
 __global__ void __launch_bounds__(256)
-reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *__restrict__ gi, int B, int X, int Y, int Z, int cpv, int p) {
+reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *__restrict__ gi, int B, int X, int Y, int Z, int cpv, int p, int lpb) {
   constexpr int VEC = 16 / (int)sizeof(T);
   const int Yp = Y + 2 * p, Zp = Z + 2 * p, Xp = X + 2 * p;
-  const int y = blockIdx.x, x = blockIdx.y, b = blockIdx.z;
-  int sx[3], sy[3];
-  const int nx = reflect_sources(x, X, p, sx), ny = reflect_sources(y, Y, p, sy);
+  const int x = blockIdx.y, b = blockIdx.z;
+  int sx[3];
+  const int nx = reflect_sources(x, X, p, sx);
+  // lpb lines per block: a line of 128 voxels x 16 channels is ONE 16-byte chunk per thread, too little in flight
+  for (int y = blockIdx.x * lpb; y < min(Y, (int)(blockIdx.x + 1) * lpb); ++y) {
+  int sy[3];
+  const int ny = reflect_sources(y, Y, p, sy);
   uint4 *dst = gi + (((int64_t)b * X + x) * Y + y) * (int64_t)Z * cpv;
   for (int i = threadIdx.x; i < Z * cpv; i += blockDim.x) {
     const int z = i / cpv, c = i - z * cpv;
@@ -846,6 +872,7 @@ reflect_pad_bwd_vec_kernel(const uint4 *__restrict__ gp, uint4 *__restrict__ gi,
     for (int k = 0; k < VEC; ++k) e[k] = from_f<T>(acc[k]);
     dst[i] = o;
   }
+  }
 }
 
 int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z, int C, int pad, cudaStream_t st) {
@@ -855,7 +882,13 @@ int reflect_pad(const void *in, void *out, int dtype, int B, int X, int Y, int Z
     const dim3 grid((unsigned)Yp, (unsigned)Xp, (unsigned)B);
     if ((C * esz) % 16 == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15))
       reflect_pad_line_kernel<uint4><<<grid, 256, 0, st>>>((const uint4 *)in, (uint4 *)out, X, Y, Z, C * esz / 16, pad);
-    else if (dtype == CGAN3D_F32)
+    else if ((Z + 2 * pad) * C <= 512) {  // short lines: a warp per line
+      const dim3 gridw((unsigned)((Yp + 31) / 32), (unsigned)Xp, (unsigned)B);
+      if (dtype == CGAN3D_F32)
+        reflect_pad_warpline_kernel<float><<<gridw, 256, 0, st>>>((const float *)in, (float *)out, X, Y, Z, C, pad);
+      else
+        reflect_pad_warpline_kernel<__nv_bfloat16><<<gridw, 256, 0, st>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, X, Y, Z, C, pad);
+    } else if (dtype == CGAN3D_F32)
       reflect_pad_line_kernel<float><<<grid, 256, 0, st>>>((const float *)in, (float *)out, X, Y, Z, C, pad);
     else
       reflect_pad_line_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, X, Y, Z, C, pad);
@@ -878,11 +911,14 @@ int reflect_pad_backward(const void *gp, void *gi, int dtype, int B, int X, int 
   const int esz = dtype == CGAN3D_F32 ? 4 : 2;
   if ((C * esz) % 16 == 0 && !((uintptr_t)gp & 15) && !((uintptr_t)gi & 15) && X <= 65535 && B <= 65535) {
     const int cpv = C * esz / 16;
-    const dim3 bl((unsigned)Y, (unsigned)X, (unsigned)B);
+    static int lpb_env = -1;
+    if (lpb_env < 0) { const char *e = getenv("CGAN3D_PADBWD_LPB"); lpb_env = e ? mx(1, atoi(e)) : 0; }
+    const int lpb = lpb_env ? lpb_env : ((int64_t)B * X * Y >= 65536 && Z * cpv <= 512 ? 4 : 1);
+    const dim3 bl((unsigned)((Y + lpb - 1) / lpb), (unsigned)X, (unsigned)B);
     if (dtype == CGAN3D_F32)
-      reflect_pad_bwd_vec_kernel<float><<<bl, 256, 0, st>>>((const uint4 *)gp, (uint4 *)gi, B, X, Y, Z, cpv, pad);
+      reflect_pad_bwd_vec_kernel<float><<<bl, 256, 0, st>>>((const uint4 *)gp, (uint4 *)gi, B, X, Y, Z, cpv, pad, lpb);
     else
-      reflect_pad_bwd_vec_kernel<__nv_bfloat16><<<bl, 256, 0, st>>>((const uint4 *)gp, (uint4 *)gi, B, X, Y, Z, cpv, pad);
+      reflect_pad_bwd_vec_kernel<__nv_bfloat16><<<bl, 256, 0, st>>>((const uint4 *)gp, (uint4 *)gi, B, X, Y, Z, cpv, pad, lpb);
     CG_LAUNCH_CHECK("reflect_pad_bwd_vec");
     return 0;
   }

@@ -1,4 +1,3 @@
-for w in 0.02 0.05 0.1 0.2 0.4; do
-CGAN3D_THIN_HALO_W=$w timeout 120 python tools/bench_conv.py --cases first_c3 --ops gather --impls tc --iters 20 2>&1 | grep '"ms"' | cut -c1-90 | sed "s/^/w=$w /"
-CGAN3D_THIN_HALO_W=$w timeout 120 python tools/bench_conv.py --cases last_c3 --ops scatter --impls tc --iters 20 2>&1 | grep '"ms"' | cut -c1-90 | sed "s/^/w=$w /"
-done
+timeout 200 python tools/bench_pad.py
+for l in 1 2 8; do CGAN3D_PADBWD_LPB=$l timeout 200 python tools/bench_pad.py | tail -1 | sed "s/^/lpb=$l /"; done
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "pad or reflect or train or generator" 2>&1 | tail -3
