@@ -260,7 +260,9 @@ static ColGrid col_grid8(int64_t n_rows, int C, int ns) {
   const int lanes = 256 / (C >> 3);
   ColGrid g;
   g.rows_per_block = 0;  // rows are walked grid-strided
-  static int per_sm = getenv("CGAN3D_RED_BLOCKS") ? atoi(getenv("CGAN3D_RED_BLOCKS")) : 4;
+  // two blocks per SM = one resident wave (measured at 16x128^3x16 / 16x64^3x32 / 16x32^3x64 bf16: 2 -> 90 / 81 / 56 % of the HBM
+  // peak, 4 -> 89 / 75 / 52 %, 8 -> 87 / 71 / 39 %; eight row pairs in flight per thread instead of four: slower)
+  static int per_sm = getenv("CGAN3D_RED_BLOCKS") ? atoi(getenv("CGAN3D_RED_BLOCKS")) : 2;
   g.blocks = (int)mx<int64_t>(1, mn<int64_t>((n_rows + lanes - 1) / lanes, (int64_t)num_sms() * per_sm));
   g.smem = (size_t)ns * lanes * C * sizeof(double);
   return g;
@@ -304,7 +306,7 @@ struct BnC8 {
   }
 };
 
-template <typename T, int ACT>
+template <typename T, int ACT, int U = 4>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t n_rows, int C, int rpb,
                       const float *__restrict__ mi, const float *__restrict__ gamma, const float *__restrict__ beta, int act,
@@ -320,7 +322,7 @@ bn_bwd_reduce8_kernel(const T *__restrict__ dz, const T *__restrict__ y, int64_t
     k8.b[k] = beta[c0 + k] - mean * k8.a[k];
   }
   constexpr int NV = (int)sizeof(T) / 2;
-  col_reduce8_body<2, 4, 2 * NV>(
+  col_reduce8_body<2, U, 2 * NV>(
       n_rows, C, sums,
       [&](int64_t r, uint4 *raw) { load8raw(y + r * C + c0, raw); load8raw(dz + r * C + c0, raw + NV); },
       [&](int64_t, const uint4 *raw, float (&v)[2][8]) {

@@ -1,3 +1,3 @@
-timeout 200 python tools/bench_pad.py
-for l in 1 2 8; do CGAN3D_PADBWD_LPB=$l timeout 200 python tools/bench_pad.py | tail -1 | sed "s/^/lpb=$l /"; done
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "pad or reflect or train or generator" 2>&1 | tail -3
+for v in "" "CGAN3D_BNRED_U8=1" "CGAN3D_RED_BLOCKS=2" "CGAN3D_RED_BLOCKS=2 CGAN3D_BNRED_U8=1" "CGAN3D_RED_BLOCKS=8" "CGAN3D_RED_BLOCKS=6 CGAN3D_BNRED_U8=1"; do
+echo "== $v"; env $v timeout 200 python tools/bench_ew.py 2>&1 | grep "bn_bwd_reduce\|bn_stats" | cut -c1-120
+done
