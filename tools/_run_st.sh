@@ -1,3 +1,5 @@
-for v in "" "CGAN3D_BNRED_U8=1" "CGAN3D_RED_BLOCKS=2" "CGAN3D_RED_BLOCKS=2 CGAN3D_BNRED_U8=1" "CGAN3D_RED_BLOCKS=8" "CGAN3D_RED_BLOCKS=6 CGAN3D_BNRED_U8=1"; do
-echo "== $v"; env $v timeout 200 python tools/bench_ew.py 2>&1 | grep "bn_bwd_reduce\|bn_stats" | cut -c1-120
-done
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2_t18.log 2>&1; echo test_rc=$?
+tail -3 gpurun_out/r2_t18.log
+timeout 600 python bench.py --steps 20 --warmup 5 --breakdown gpurun_out/r2_break18.txt > gpurun_out/r2_b18.json 2> gpurun_out/r2_b18.err; echo bench_rc=$?
+timeout 900 python tools/bench_conv.py --sweep --impls tc,cudnn --ops gather,scatter,wgrad --iters 10 > gpurun_out/r2_c5_sweep2.jsonl 2> gpurun_out/r2_c5_2.err; echo sweep_rc=$?
+timeout 300 python tools/bench_conv.py --cases res,down0_c3,down1,first_c3,last_c3,d_first,d_mid0 --impls tc,cudnn --ops gather,scatter,wgrad --iters 10 > gpurun_out/r2_vs_cudnn.jsonl 2> gpurun_out/r2_vs_cudnn.err; echo vs_rc=$?
