@@ -428,7 +428,32 @@ wgrad_kernel(cgan3d_conv_geom g, const T *__restrict__ big, const T *__restrict_
   const int64_t n_lines = (int64_t)g.B * g.Xs * g.Ys;
   const int64_t l0 = blockIdx.y * vox_per_chunk;
   const int64_t l1 = min(n_lines, l0 + vox_per_chunk);
-  if (lane < lanes) {
+  if (lane < lanes && 2 * g.Zs <= lanes) {
+    // short output lines (the critic's 7^3 logits map: 7 voxels per line against 16 lanes): lanes stride over the chunk's
+    // voxels instead of idling inside one line, the index arithmetic per voxel is cheap next to a 44-deep serial line loop
+    for (int64_t v = l0 * g.Zs + lane; v < l1 * g.Zs; v += lanes) {
+      const int64_t l = v / g.Zs;
+      const int oz = (int)(v - l * g.Zs);
+      const int oy = (int)(l % g.Ys);
+      const int64_t t = l / g.Ys;
+      const int ox = (int)(t % g.Xs);
+      const int b = (int)(t / g.Xs);
+      const int ix = ox * S - g.pad + kx, iy = oy * S - g.pad + ky, iz = oz * S - g.pad + kz;
+      if ((unsigned)ix >= (unsigned)g.Xb || (unsigned)iy >= (unsigned)g.Yb || (unsigned)iz >= (unsigned)g.Zb) continue;
+      float xv[CBV], yv[CSV];
+      load_n<T, CBV>(big + ((((int64_t)b * g.Xb + ix) * g.Yb + iy) * (int64_t)g.Zb + iz) * g.Cb + cb0, xv);
+      load_n<T, CSV>(small + v * (int64_t)g.Cs + cs0, yv);
+#pragma unroll
+      for (int a = 0; a < CBV; ++a)
+#pragma unroll
+        for (int c = 0; c < CSV; ++c) acc[a][c] = fmaf(xv[a], yv[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < CBV; ++a)
+#pragma unroll
+      for (int c = 0; c < CSV; ++c)
+        atomicAdd(&red[(tcb * CBV + a) * (ncs * CSV) + tcs * CSV + c], acc[a][c]);
+  } else if (lane < lanes) {
     for (int64_t l = l0; l < l1; ++l) {
       const int oy = (int)(l % g.Ys);
       const int64_t t = l / g.Ys;

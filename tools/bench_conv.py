@@ -39,6 +39,7 @@ CASES = {
     "last": (False, 16, 1, 7, 1, 0, 0, 2, (134, 134, 134)),
     "d_first": (False, 1, 8, 4, 2, 1, 0, 16, (128, 128, 128)),
     "d_mid0": (False, 8, 16, 4, 2, 1, 0, 16, (64, 64, 64)),
+    "d_last": (False, 64, 1, 4, 1, 1, 0, 16, (8, 8, 8)),
 }
 
 
