@@ -211,3 +211,43 @@ def test_train_steps_bf16_full_patch_size_post_step_weights():
                 if du.numel() > 100:
                     cos = float(du @ dr / (du.norm() * dr.norm() + 1e-30))
                     assert cos >= 0.9, f"critic {k}: update cosine {cos:.4f}"
+
+
+def test_validate_at_reference_patch_size_tcgen05_vs_cuda_core():
+    """Trainer.validate at the reference's validation patch size (256, 256, 128), batch 2 per scan type (reference
+    constants.py:12, trainer/Trainer.py:247-308): eval-mode BatchNorm, non-cubic extents through every generator / critic
+    kernel.  The tcgen05 path against the CUDA-core kernels on the same bf16 weights (the CPU oracle needs minutes here)."""
+    from contrast_gan_3d_b200 import _lib, ops
+    from contrast_gan_3d_b200.model import HULoss, PatchGANDiscriminator, ResnetGenerator
+    from contrast_gan_3d_b200.optim import FusedAdam
+    from contrast_gan_3d_b200.trainer.Trainer import NullLogger, Trainer
+
+    torch.manual_seed(0)
+    dt = torch.bfloat16
+    tr = Trainer(10, 1, None, 1, 1, 1, 0, partial(ResnetGenerator, 4, 2, 16, compute_dtype=dt),
+                 partial(PatchGANDiscriminator, 1, 8, 3, negative_slope=0.2, compute_dtype=dt),
+                 partial(FusedAdam, lr=2e-4, betas=(0.5, 0.999)), partial(FusedAdam, lr=2e-4, betas=(0.5, 0.999)),
+                 HULoss(0.18666666666666668, 0.35333333333333333), NullLogger(), torch.device(DEV), weight_clip=0.01,
+                 checkpoint_every=None)
+    # running statistics away from their initial (0, 1) so that the eval-mode normalisation is not the identity
+    gen = torch.Generator().manual_seed(5)
+    for m in list(tr.generator.modules()) + list(tr.critic.modules()):
+        if hasattr(m, "running_mean") and m.running_mean is not None:
+            m.running_mean.copy_((torch.rand(m.running_mean.shape, generator=gen) - 0.5) * 0.2)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) * 0.5 + 0.75)
+    vpatch = (256, 256, 128)
+    batches = [O.synthetic_patches(gen, (2, 1, *vpatch)) for _ in range(3)]
+
+    def run(impl):
+        old = ops.set_conv_impl(impl)
+        try:
+            loaders = {0: iter([dict(data=batches[0])]), -1: iter([dict(data=batches[1])]), 1: iter([dict(data=batches[2])])}
+            out = tr.validate(loaders, 400)
+            torch.cuda.synchronize()
+            return {k: float(v) for k, v in out.items()}
+        finally:
+            ops.set_conv_impl(old)
+
+    got, ref = run(_lib.IMPL_AUTO), run(_lib.IMPL_GENERIC)
+    for k in ("D", "G", "sim"):
+        assert np.isfinite(got[k]) and abs(got[k] - ref[k]) <= 2e-2 * abs(ref[k]) + 2e-3, (k, got[k], ref[k])
