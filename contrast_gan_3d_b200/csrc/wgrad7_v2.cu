@@ -8,12 +8,12 @@
 // What the first kernel lost (profiles/r01_ncu_full_wgrad7_last.txt: 0.198 of the bf16 peak, 3.4 GB of DRAM traffic for a
 // 1.3 GB problem) and what changes here:
 //   * the z-expanded operand E[v][j] = Q1[v + j] was materialised in HBM by a pre-pass (16 B per voxel written, then read
-//     2.75x through the y halo).  Here it is built IN SHARED MEMORY by the four epilogue warps from the raw 1-channel
-//     lines (2 B per voxel, L2 resident): DRAM traffic = one read of S16.
+//     2.75x through the y halo).  Here it is built IN SHARED MEMORY by ten warps from the raw 1-channel lines (2 B per
+//     voxel, L2 resident) that four more warps stage with cp.async: DRAM traffic = one read of S16.
 //   * M was 64 (8 dy x 8 dz) with N = 64 (4 x-planes x 16 channels) and 2.5 MMAs per plane on average.  Here one E row
 //     carries TWO x-planes (32-byte rows = [dx_lo][dz], SWIZZLE_32B MN-major, blocks of 16 M elements one slab LINE apart
 //     = 8 dy blocks): M = 128.  N = 128 = the 8 S16 planes xe-6 .. xe+1 x 16 channels sitting in adjacent ring slots
-//     (a ring of 10 planes whose first slots are mirrored behind its end, so a window never wraps): ONE M = 128, N = 128
+//     (a ring of 14 planes whose first slots are mirrored behind its end, so a window never wraps): ONE M = 128, N = 128
 //     MMA per 16 voxels and per PAIR of E planes, 14 of its 16 (dx_lo, plane) blocks and 49 of 64 rows useful.
 //   * accumulator column = 16 * (plane - first plane of the window): the filter x-offset is dx = 6 - j + dx_lo.
 // Split-K over CTAs (whole (b, y-tile) columns dealt round-robin, see SegIterW2), fp32 atomics at the end.
@@ -79,19 +79,6 @@ struct SegIterW2 {
     end = total * (blockIdx.x + 1) / gridDim.x;
   }
   __device__ __forceinline__ long long steps() const { return (long long)rounds * n + (end - idx); }
-  // step k (0-based, in processing order) of this CTA -> (column, plane pair)
-  __device__ __forceinline__ void locate(long long k, long long idx0, int &col, int &pair) const {
-    if (k < (long long)rounds * n) {
-      const int rr = (int)(k / n);
-      col = rr * (int)gridDim.x + (int)blockIdx.x;
-      pair = (int)(k - (long long)rr * n);
-    } else {
-      const long long flat = idx0 + (k - (long long)rounds * n);
-      const long long c = flat / n;
-      col = (int)(rem_col0 + c);
-      pair = (int)(flat - c * n);
-    }
-  }
   __device__ __forceinline__ bool next(int &col, int &p0, int &plen) {
     if (r < rounds) {
       col = r * (int)gridDim.x + (int)blockIdx.x;
@@ -206,12 +193,12 @@ wgrad7_v2_kernel(const __grid_constant__ CUtensorMap tmS, const uint32_t *__rest
   const long long ncols = (long long)p.B * p.nyt;
 
   if (warp == 4) {
-    // ------------------------------------------------ S16 plane producer (TMA).  Measured (profiles/README.md, round 2): a
-    // SWIZZLE_32B map is limited to 32-byte inner rows and the TMA engine spends ~3 cycles per row, so the planes of one
-    // step (2 planes + mirrors = 660 rows) cost ~2000 cycles: this, not the MMAs (1350 cycles), is the kernel's floor.  A
-    // 16-byte cp.async producer warp with the swizzle applied by hand was tried and is slower still (5400 cycles / step).  Planes are numbered by the order in which
-    // this CTA loads them (q): slot q % ring, mirrored at ring + slot when that exists.  A segment loads its 6 warm-up
-    // planes and then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
+    // ------------------------------------------------ S16 plane producer (TMA).  A swizzled tensor map moves one inner row
+    // (32 B of one voxel, or 64 B of a z pair) per request at ~3 cycles each, so the z-pair rows halve the engine's work
+    // per plane; with everything else disabled the plane loads add 0.08 ms to the kernel.  A 16-byte cp.async producer
+    // warp with the swizzle applied by hand was tried and is slower (5400 cycles per step).  Planes are numbered by the
+    // order in which this CTA loads them: slot q % ring, mirrored at ring + slot when that exists.  A segment loads its 6
+    // warm-up planes and then two planes per step, (ring - 8) / 2 steps ahead of the MMAs.
     if (lane == 0) {
       tc::tma_prefetch_desc(&tmS);
       // plane q of this CTA goes to slot q % ring on its (q / ring)-th use: both kept incrementally (a runtime division costs
