@@ -76,6 +76,37 @@ static bool build_program(const cgan3d_conv_geom &g, int scatter, ProgPlan &p) {
     auto cls = [&](int d) { return (d - 1) & 1; };
     auto shift = [&](int d) { return (d - 1 + cls(d)) / 2; };  // rows of the sub-slab, >= 0
     bool first = true;
+    if (p.zpair) {
+      // rows are z pairs (2j, 2j + 1) of one y class, the slab starts at pair z0 - 1: tap dz reads input z = 2*o + dz - 1,
+      // i.e. dz = 0 -> pair o - 1, second voxel; dz = 1 -> pair o, first voxel; dz = 2 -> pair o, second voxel
+      if (k != 3) return false;
+      for (int dx = 0; dx < k; ++dx)
+        for (int q = 0; q < 2; ++q) {
+          ProgEntry E{};
+          E.cx = (int8_t)(dx - 1); E.cy = (int8_t)(-q); E.cz = (int8_t)(-1);
+          E.tap0 = (uint8_t)nt; E.ntaps = 0;
+          for (int dy = 0; dy < k; ++dy) {
+            if (cls(dy) != q) continue;
+            for (int dz = 0; dz < k; ++dz) {
+              if (nt >= kMaxTaps) return false;
+              ProgTap T{};
+              T.row_shift = (uint16_t)(shift(dy) * p.Zh + (dz == 0 ? 0 : 1));
+              T.khalf = (uint8_t)(dz == 1 ? 0 : 1);
+              T.btile = (uint8_t)((dx * k + dy) * k + dz);
+              T.acc = 0; T.first = first ? 1 : 0;
+              first = false;
+              p.taps[nt++] = T; E.ntaps++;
+            }
+          }
+          if (E.ntaps == 0) continue;
+          if (ne >= kMaxEntries) return false;
+          p.entries[ne++] = E;
+        }
+      p.nacc = 1;
+      p.nentries = ne;
+      p.ntaps = nt;
+      return true;
+    }
     for (int dx = 0; dx < k; ++dx)
       for (int q = 0; q < 2; ++q)
         for (int r = 0; r < 2; ++r) {
@@ -246,7 +277,11 @@ static bool plan_prog_split(const cgan3d_conv_geom &g, int scatter, ProgPlan &be
   }
   const uint32_t b_total = (p.nbt * p.btile_bytes + 1023) / 1024 * 1024;
   if (b_total + 40000 > kSmemLimitProg) return false;
-  const int a_swz = (!paired && Cin <= 64) ? 2 * Cin : 0;
+  static int zpair_off = -1;
+  if (zpair_off < 0) zpair_off = getenv("CGAN3D_NO_ZPAIR") ? 1 : 0;  // A/B timing: per-class strided slab loads
+  const bool zpair = !zpair_off && !scatter && !paired && (Cin == 16 || Cin == 32) && g.k == 3 && g.Zb % 2 == 0;
+  p.zpair = zpair ? 1 : 0;
+  const int a_swz = zpair ? 4 * Cin : ((!paired && Cin <= 64) ? 2 * Cin : 0);
   double best_score = 0;
   bool found = false;
   for (int nzt = 1; nzt <= 4; ++nzt) {
@@ -333,11 +368,14 @@ int tc_prog_run(const cgan3d_conv_geom &g, int scatter, const void *in, const vo
   if ((reinterpret_cast<uintptr_t>(outp) & 15) || (p.Nout * 2) % 16 || (p.out_pitch * 2) % 16) return fail(CGAN3D_E_ARG, "tcgen05 strided conv: output rows must be 16-byte aligned");
   const int es = p.in_scale;
   CUtensorMap tm;
-  const cuuint64_t gdim[5] = {(cuuint64_t)Ci, (cuuint64_t)Zi, (cuuint64_t)Yi, (cuuint64_t)Xi, (cuuint64_t)g.B};
-  const cuuint64_t gstr[4] = {(cuuint64_t)Ci * 2, (cuuint64_t)Zi * Ci * 2, (cuuint64_t)Yi * Zi * Ci * 2,
+  // z-pair gather: the innermost dimension is a PAIR of z-adjacent voxels (dense along z, element stride 2 only on y)
+  const cuuint64_t zp = p.zpair ? 2 : 1;
+  const cuuint64_t gdim[5] = {(cuuint64_t)Ci * zp, (cuuint64_t)Zi / zp, (cuuint64_t)Yi, (cuuint64_t)Xi, (cuuint64_t)g.B};
+  const cuuint64_t gstr[4] = {(cuuint64_t)Ci * 2 * zp, (cuuint64_t)Zi * Ci * 2, (cuuint64_t)Yi * Zi * Ci * 2,
                               (cuuint64_t)Xi * Yi * Zi * Ci * 2};
-  const cuuint32_t box[5] = {(cuuint32_t)(p.a_swz ? Ci : 8), (cuuint32_t)(es * (p.Zh - 1) + 1), (cuuint32_t)(es * (p.Yh - 1) + 1), 1, 1};
-  const cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)(p.a_swz ? Ci * (int)zp : 8), (cuuint32_t)(p.zpair ? p.Zh : es * (p.Zh - 1) + 1),
+                             (cuuint32_t)(es * (p.Yh - 1) + 1), 1, 1};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)(p.zpair ? 1 : es), (cuuint32_t)es, 1, 1};
   const CUtensorMapSwizzle swz = p.a_swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : (p.a_swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (p.a_swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in), gdim, gstr, box, estr,

@@ -41,7 +41,8 @@ struct ProgTap {
   uint8_t btile;       // resident filter tile
   uint8_t acc;         // accumulator (output phase)
   uint8_t first;       // 1 = first MMA group into this accumulator (overwrite)
-  uint8_t pad[3];
+  uint8_t khalf;       // z-pair gather: 1 = the tap reads the SECOND voxel of the row (K offset of Cin elements)
+  uint8_t pad[2];
 };
 struct ProgEntry {
   int8_t cx, cy, cz;  // TMA start coordinate = scale * tile origin + c*
@@ -73,6 +74,8 @@ struct ProgPlan {
   int acc_stride, mt_stride;     // TMEM columns between accumulators (phases) / between M-tiles
   int8_t tile_phase_tap[kMaxTaps][8];
   int pair;                      // 1: CTA pairs (cta_group::2); btile_bytes is then the HALF tile (Nmma/2 rows) held by one CTA
+  int zpair;                     // 1: gather whose slab rows are z-adjacent voxel PAIRS (both z parity classes in one dense
+                                 // 4*Cin-byte row): half the TMA requests of the per-class strided loads (DESIGN fact 10)
 };
 
 // STATS: the epilogue also accumulates the per-channel sum / sum of squares of the fp32 accumulators (BatchNorm batch
@@ -160,7 +163,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t slot = e % p.nslots, use = e / p.nslots;
           if (use > 0) tc::mbar_wait(&s_empty[slot], (use - 1) & 1);
           uint8_t *dst = ring + (size_t)slot * p.slot_bytes;
-          const int cz = p.in_scale * z0 + E.cz, cy = p.in_scale * y0 + E.cy, cx = p.in_scale * x + E.cx;
+          const int cz = (p.zpair ? z0 : p.in_scale * z0) + E.cz, cy = p.in_scale * y0 + E.cy, cx = p.in_scale * x + E.cx;
           if constexpr (PAIR) {  // one box per slab (swizzled whole voxels, or the 8-channel critic slabs)
             if (cta_rank == 0) tc::mbar_expect_tx(&s_full[slot], 2 * p.box_bytes);
             tc::tma_load_5d_2cta(dst, &tmA, &s_full[slot], 0, cz, cy, cx, b);
@@ -208,7 +211,7 @@ conv_prog_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t a_slot = (ring_u32 + slot * p.slot_bytes) >> 4;
         for (int t = 0; t < E.ntaps; ++t) {
           const ProgTap &T = p.taps[E.tap0 + t];
-          const uint64_t a0 = a_hi | (uint64_t)((a_slot + T.row_shift * a_row) & 0x3FFF);
+          const uint64_t a0 = a_hi | (uint64_t)((a_slot + T.row_shift * a_row + (uint32_t)T.khalf * (uint32_t)(p.Cin >> 3)) & 0x3FFF);
           const uint64_t b0 = b_hi | (uint64_t)(((b_u32 + (uint32_t)T.btile * p.btile_bytes) >> 4) & 0x3FFF);
           const uint32_t d0 = d_base + (uint32_t)T.acc * p.acc_stride;
           const uint32_t keep = T.first ? 0u : 1u;
